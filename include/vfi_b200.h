@@ -1,0 +1,120 @@
+/*
+ * vfi_b200.h -- C ABI of libvfi_b200.so: the B200 (sm_100a) implementation of the warp + DeformConv2d hot path
+ * of 424635328/video-frame-interpolation.
+ *
+ * Every entry point replaces one edge of the reference's L2->L1 boundary.  The reference
+ * reaches these ops through Python, so "the reference's FFI for this path" is a ctypes binding; the one shipped in
+ * video-frame-interpolation_b200/_lib.py is the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller (in practice the PyTorch caching allocator),
+ *     including the workspace.  The library allocates nothing on the data path and keeps no reference to any buffer.
+ *   - Work is enqueued on the stream passed in; no call synchronises the device or the stream.
+ *   - Every function returns a vfi_status; 0 is success.  Nothing throws across the boundary.  A human-readable
+ *     description of the last failure on the calling thread is available from vfi_last_error().
+ *   - Tensors are described by vfi_tensor: logical NCHW extents plus element strides, so NCHW-contiguous,
+ *     channels-last and channel-padded channels-last buffers all go through the same call.  The kernels pick a
+ *     vectorised / TMA / tcgen05 specialisation when the strides allow and a strided path otherwise.
+ *   - There is NO CPU fallback and no multi-architecture dispatch: the device must be compute capability 10.x.
+ */
+#ifndef VFI_B200_H_
+#define VFI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFI_B200_ABI_VERSION 1
+
+typedef void* vfi_stream_t; /* cudaStream_t */
+
+typedef enum vfi_status {
+  VFI_OK = 0,
+  VFI_ERR_INVALID = 1,      /* bad argument: null pointer, shape mismatch, negative extent ...           */
+  VFI_ERR_UNSUPPORTED = 2,  /* well-formed but outside the geometry this library implements               */
+  VFI_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed; message carries cudaGetErrorString     */
+  VFI_ERR_WORKSPACE = 4,    /* workspace missing or smaller than vfi_dcn_workspace_bytes() asked for       */
+  VFI_ERR_DEVICE = 5        /* current device is not sm_100 (B200)                                         */
+} vfi_status;
+
+typedef enum vfi_dtype { VFI_F32 = 0, VFI_BF16 = 1, VFI_F16 = 2 } vfi_dtype;
+
+typedef struct vfi_tensor {
+  void* data;            /* device pointer to element (0,0,0,0)            */
+  int32_t dtype;         /* vfi_dtype                                      */
+  int32_t reserved;      /* must be 0                                      */
+  int64_t n, c, h, w;    /* logical extents                                */
+  int64_t sn, sc, sh, sw;/* strides in elements                            */
+} vfi_tensor;
+
+/* Arithmetic used by the DCN contraction. */
+typedef enum vfi_dcn_math {
+  VFI_DCN_MATH_AUTO = 0,  /* fp32 tensors -> FP32, bf16/f16 tensors -> BF16_TC                                      */
+  VFI_DCN_MATH_FP32 = 1,  /* fp32 gather + FFMA contraction: the parity mode (max-abs 1e-5 vs torchvision fp32)     */
+  VFI_DCN_MATH_BF16_TC = 2/* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma (C = O = 67 geometry only)      */
+} vfi_dcn_math;
+
+/* ---- library ----------------------------------------------------------------------------------------------- */
+int vfi_abi_version(void);
+const char* vfi_version_string(void);
+const char* vfi_last_error(void);            /* thread-local; never NULL                                       */
+int vfi_check_device(void);                  /* VFI_OK when the current CUDA device is sm_100                  */
+/* number of kernels this library has launched on the calling thread since the last vfi_reset_launch_count() */
+int64_t vfi_launch_count(void);
+void vfi_reset_launch_count(void);
+
+/* ---- warp: replaces EMA_VFI.warp, /root/reference/src/models/ema_vfi.py:149-171 ----------------------------- */
+/* out[b,c,y,x] = bilinear(src[b,c], x + flow[b,0,y,x], y + flow[b,1,y,x]), zeros outside, align_corners=True,
+ * with the reference's normalise/un-normalise round trip replayed in fp32.
+ * src/out: [B,C,H,W] same dtype (f32|bf16|f16); flow: [B,2,H,W] f32 or the dtype of src. */
+int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, vfi_stream_t stream);
+
+/* Autograd of the above (aten::grid_sampler_2d_backward chained through ema_vfi.py:165-166).
+ * grad_flow [B,2,H,W] f32 is always written.  grad_src may be NULL (the model path: frame2 needs no grad); when
+ * given it must be f32, zero-filled by the caller, and receives atomic scatter-adds. */
+int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, const vfi_tensor* flow,
+                 const vfi_tensor* grad_flow, const vfi_tensor* grad_src, vfi_stream_t stream);
+
+/* North-star extension with no reference counterpart: one pass computing
+ * out = m * warp(src_a, flow_a) + (1 - m) * warp(src_b, flow_b), m: [B,1,H,W]. */
+int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flow_a, const vfi_tensor* src_b,
+                       const vfi_tensor* flow_b, const vfi_tensor* m, const vfi_tensor* out, vfi_stream_t stream);
+
+/* ---- DCNv2: replaces torchvision.ops.deform_conv2d as called from ema_vfi.py:60 ---------------------------- */
+/* Geometry is the reference's: 3x3 kernel, stride 1, padding 1, dilation 1, groups 1, one offset group, mask on
+ * (ema_vfi.py:45-51).  x [B,C,H,W]; offset [B,18,H,W] (2k = row shift, 2k+1 = column shift of tap k = 3i+j);
+ * mask [B,9,H,W]; weight [O,C,3,3] contiguous; bias [O] or NULL; out [B,O,H,W]. */
+size_t vfi_dcn_workspace_bytes(int64_t B, int64_t C, int64_t O, int64_t H, int64_t W, int32_t math);
+
+/* Packs weight [O,C,3,3] (f32|bf16|f16) into the K-major bf16 operand image the tcgen05 kernel TMA-loads:
+ * [80 rows (o, zero padded)][656 (tap-major: k*72 + c, zero padded)] bf16.  `packed` needs vfi_dcn_packed_weight_bytes(). */
+size_t vfi_dcn_packed_weight_bytes(void);
+int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
+                        vfi_stream_t stream);
+
+/* Converts an activation tensor of any supported layout/dtype into the channel-padded channels-last bf16 image
+ * the tcgen05 kernel gathers from: [B,H,W,72] bf16 (channels >= C are zero). */
+int vfi_dcn_pack_input(const vfi_tensor* x, void* packed_nhwc72, vfi_stream_t stream);
+
+int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
+                int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out, int64_t O,
+                int32_t math, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
+
+/* Gradients (torchvision::_deform_conv2d_backward).  grad_out must have x's dtype.  All gradient tensors are f32.  grad_x must be zero-filled by
+ * the caller (atomic scatter-add target); grad_weight / grad_bias likewise (accumulated with atomics so that a
+ * caller may point them into a flat gradient bucket).  Any of the three outputs of bwd_data may be NULL. */
+int vfi_dcn_bwd_data(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset,
+                     const vfi_tensor* mask, const void* weight, int32_t weight_dtype, int64_t O,
+                     const vfi_tensor* grad_x, const vfi_tensor* grad_offset, const vfi_tensor* grad_mask,
+                     void* workspace, size_t workspace_bytes, vfi_stream_t stream);
+int vfi_dcn_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset,
+                       const vfi_tensor* mask, int64_t O, float* grad_weight, float* grad_bias,
+                       vfi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFI_B200_H_ */

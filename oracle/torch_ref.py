@@ -58,6 +58,8 @@ def dcn(x, offset, mask, weight, bias):
 
 def dcn_stock(x, offset, mask, weight, bias):
     """Same as :func:`dcn` but always the stock torchvision kernel, even when the drop-in is installed."""
+    import torchvision  # noqa: F401  (registers torch.ops.torchvision)
+
     return torch.ops.torchvision.deform_conv2d(x, weight, offset, mask, bias, 1, 1, 1, 1, 1, 1, 1, 1, True)
 
 

@@ -1,0 +1,145 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/vfi_b200.h declares,
+the Python binding declares the same set, the seams patch and restore, and nothing silently falls back on CPU."""
+import ctypes
+import os
+import re
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+import vfi_b200
+from vfi_b200 import _lib, dropin
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "vfi_b200.h").read_text()
+
+
+def declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(vfi_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vfi_b200.h but not exported"
+
+
+def test_python_binding_matches_header():
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+    lib = _lib.load()
+    assert lib.vfi_abi_version() == int(re.search(r"VFI_B200_ABI_VERSION (\d+)", HEADER).group(1))
+    assert b"sm_100a" in lib.vfi_version_string()
+    assert lib.vfi_dcn_packed_weight_bytes() == 80 * 656 * 2
+    assert lib.vfi_dcn_workspace_bytes(1, 67, 67, 8, 8, _lib.MATH_FP32) >= 2 * 9 * 72 * 72 * 4
+
+
+def test_struct_layout_matches_header():
+    # 8 (ptr) + 4 + 4 + 8 * 8
+    assert ctypes.sizeof(_lib.VfiTensor) == 80
+    t = torch.zeros(2, 3, 4, 5).to(memory_format=torch.channels_last)
+    d = _lib.desc(t)
+    assert (d.n, d.c, d.h, d.w) == (2, 3, 4, 5) and (d.sn, d.sc, d.sh, d.sw) == (60, 1, 15, 3)
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vfi_b200.warp(torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vfi_b200.deform_conv2d(torch.zeros(1, 67, 4, 4), torch.zeros(1, 18, 4, 4), torch.zeros(67, 67, 3, 3),
+                               torch.zeros(67), stride=1, padding=1, dilation=1, mask=torch.zeros(1, 9, 4, 4))
+
+
+def test_geometry_outside_the_path_is_refused():
+    x, w = torch.zeros(1, 67, 4, 4), torch.zeros(67, 67, 3, 3)
+    off, m = torch.zeros(1, 18, 4, 4), torch.zeros(1, 9, 4, 4)
+    with pytest.raises(NotImplementedError):
+        vfi_b200.deform_conv2d(x, off, w, None, stride=2, padding=1, dilation=1, mask=m)
+    with pytest.raises(NotImplementedError):
+        vfi_b200.deform_conv2d(x, off, w, None, stride=1, padding=0, dilation=1, mask=m)
+    with pytest.raises(NotImplementedError):
+        vfi_b200.deform_conv2d(x, off, w, None, stride=1, padding=1, dilation=1, mask=None)
+    with pytest.raises(NotImplementedError):
+        vfi_b200.deform_conv2d(x, torch.zeros(1, 36, 4, 4), w, None, stride=1, padding=1, dilation=1, mask=m)
+    with pytest.raises(NotImplementedError):
+        vfi_b200.deform_conv2d(x, off, torch.zeros(67, 67, 5, 5), None, stride=1, padding=1, dilation=1, mask=m)
+
+
+def test_abi_argument_validation_without_a_gpu():
+    """Bad descriptors are rejected before any CUDA call, with a message."""
+    lib = _lib.load()
+    src = _lib.VfiTensor(1, 0, 0, 1, 3, 4, 4, 48, 16, 4, 1)      # fake non-null pointer, never dereferenced
+    flow_bad = _lib.VfiTensor(1, 0, 0, 1, 3, 4, 4, 48, 16, 4, 1)  # 3 channels instead of 2
+    rc = lib.vfi_warp_fwd(ctypes.byref(src), ctypes.byref(flow_bad), ctypes.byref(src), None)
+    assert rc == 1 and b"flow must be [B,2,H,W]" in lib.vfi_last_error()
+    rc = lib.vfi_warp_fwd(None, None, None, None)
+    assert rc == 1 and b"null" in lib.vfi_last_error()
+    x = _lib.VfiTensor(1, 0, 0, 1, 100, 4, 4, 1600, 16, 4, 1)
+    off = _lib.VfiTensor(1, 0, 0, 1, 18, 4, 4, 288, 16, 4, 1)
+    m = _lib.VfiTensor(1, 0, 0, 1, 9, 4, 4, 144, 16, 4, 1)
+    out = _lib.VfiTensor(1, 0, 0, 1, 100, 4, 4, 1600, 16, 4, 1)
+    rc = lib.vfi_dcn_fwd(ctypes.byref(x), ctypes.byref(off), ctypes.byref(m), 1, 0, None, 0, ctypes.byref(out), 100,
+                         _lib.MATH_FP32, 1, 1 << 20, None)
+    assert rc == 2 and b"at most 72" in lib.vfi_last_error()
+
+
+def test_dropin_patches_and_restores_both_seams():
+    import torchvision.ops
+    import torchvision.ops.deform_conv as tv
+
+    sys.path.insert(0, str(ROOT))
+    from oracle.torch_ref import WarpHost
+
+    orig_tv, orig_warp = tv.deform_conv2d, WarpHost.warp
+    dropin.install(WarpHost)
+    try:
+        assert dropin.installed()
+        assert tv.deform_conv2d is not orig_tv and torchvision.ops.deform_conv2d is tv.deform_conv2d
+        assert WarpHost.warp is not orig_warp
+        # the patched seams reach the CUDA ops -- which refuse CPU tensors instead of falling back
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            WarpHost().warp(torch.zeros(1, 3, 4, 4), None, torch.zeros(1, 2, 4, 4))
+        blk = torchvision.ops.DeformConv2d(67, 67, 3, padding=1)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            blk(torch.zeros(1, 67, 4, 4), torch.zeros(1, 18, 4, 4), torch.zeros(1, 9, 4, 4))
+        assert sorted(blk.state_dict()) == ["bias", "weight"] and blk.weight.shape == (67, 67, 3, 3)
+    finally:
+        dropin.uninstall()
+    assert tv.deform_conv2d is orig_tv and WarpHost.warp is orig_warp and not dropin.installed()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
+def test_dropin_intercepts_the_unmodified_reference_model():
+    """EMA_VFI.forward must hit the warp seam first (call site ema_vfi.py:130); on a CPU box the CUDA op then refuses."""
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.ema_vfi import EMA_VFI
+    finally:
+        sys.path.remove("/root/reference")
+    torch.manual_seed(0)
+    model = EMA_VFI().eval()
+    keys = [k for k in model.state_dict() if "dcn_v2" in k]
+    assert keys == [f"attention_blocks.{i}.dcn_v2.{n}" for i in range(3) for n in ("weight", "bias")]
+    before = dropin.call_counts()
+    dropin.install(EMA_VFI)
+    try:
+        with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+            model(torch.rand(1, 3, 16, 16), torch.rand(1, 3, 16, 16))
+        assert dropin.call_counts()["warp"] == before["warp"] + 1
+    finally:
+        dropin.uninstall()
+    with torch.no_grad():
+        assert model(torch.rand(1, 3, 16, 16), torch.rand(1, 3, 16, 16)).shape == (1, 3, 16, 16)
+
+
+def test_launcher_shims():
+    from vfi_b200 import run
+
+    run.apply_compat_shims()
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1)
+    torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.5, patience=5, verbose=True)  # train.py:84

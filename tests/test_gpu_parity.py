@@ -1,0 +1,303 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Every op is called through the C ABI (ctypes -> libvfi_b200.so)
+and compared with
+
+* the committed golden vectors produced by the unmodified reference (tests/golden/*.npz),
+* the C oracle (oracle/vfi_oracle.c) on seeded random inputs at sizes it finishes in seconds,
+* the stock torch / torchvision kernels (oracle/torch_ref.py) at larger sizes, and
+* size-independent properties at BASELINE.json's full sizes (1080p batch 8, 4K).
+
+Tolerances: fp32 max-abs 1e-5 (north star), scaled by max|ref| for tensors whose magnitude exceeds 1 (gradients);
+bf16: max|delta| / max|ref| <= 1e-2 against fp32 arithmetic on bf16-rounded inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import vfi_b200
+from conftest import load_golden
+from oracle import torch_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+WARP_CASES = ["warp_rand", "warp_integer", "warp_tiny_flow", "warp_w1", "warp_h1", "warp_urban2"]
+DCN_CASES = ["dcn_c67_sigma3", "dcn_c67_zero", "dcn_c5_o7_sigma1", "dcn_c67_sigma16"]
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def maxabs(a, b):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if a.size else 0.0
+
+
+def tol(ref, base=1e-5):
+    ref = ref.detach().float().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref)
+    return base * max(1.0, float(np.max(np.abs(ref)))) if ref.size else base
+
+
+def relerr(a, ref):
+    ref = ref.detach().float().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref)
+    return maxabs(a, ref) / max(float(np.max(np.abs(ref))), 1e-30)
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+def test_library_runs_on_this_device():
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    assert vfi_b200._lib.load().vfi_check_device() == 0
+
+
+# ------------------------------------------------------------------------------------------------------------ warp
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_warp_fwd_golden(name):
+    z = load_golden(name)
+    out = vfi_b200.warp(cu(z["src"]), cu(z["flow"]))
+    assert maxabs(out, z["out"]) <= 1e-5
+
+
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_warp_bwd_golden(name):
+    z = load_golden(name)
+    src = cu(z["src"]).requires_grad_("grad_src" in z)
+    flow = cu(z["flow"]).requires_grad_(True)
+    vfi_b200.warp(src, flow).backward(cu(z["grad_out"]))
+    assert maxabs(flow.grad, z["grad_flow"]) <= tol(z["grad_flow"])
+    if "grad_src" in z:
+        assert maxabs(src.grad, z["grad_src"]) <= tol(z["grad_src"])
+
+
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 64, 96), 0.03), ((1, 3, 270, 480), 8.0), ((3, 3, 33, 61), 20.0),
+                                         ((1, 5, 47, 52), 3.0)])
+def test_warp_fwd_bwd_vs_oracle(shape, sigma):
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = shape
+    src = torch.randn(shape, generator=g)
+    flow = sigma * torch.randn(B, 2, H, W, generator=g)
+    go = torch.randn(shape, generator=g)
+    f = flow.to(DEV).requires_grad_(True)
+    out = vfi_b200.warp(src.to(DEV), f)
+    out.backward(go.to(DEV))
+    assert maxabs(out, oracle.warp_fwd(src.numpy(), flow.numpy())) <= 1e-5
+    ref = oracle.warp_bwd(go.numpy(), src.numpy(), flow.numpy())
+    assert maxabs(f.grad, ref) <= tol(ref)
+
+
+def test_warp_strided_and_channels_last_inputs():
+    g = torch.Generator().manual_seed(12)
+    src = torch.randn(2, 3, 40, 64, generator=g)
+    flow = 4 * torch.randn(2, 2, 40, 64, generator=g)
+    ref = oracle.warp_fwd(src.numpy(), flow.numpy())
+    # channels_last source (NHWC in memory) and a flow that is a slice of a wider tensor
+    s_cl = src.to(DEV).contiguous(memory_format=torch.channels_last)
+    wide = torch.zeros(2, 5, 40, 64, device=DEV)
+    wide[:, 1:3] = flow.to(DEV)
+    out = vfi_b200.warp(s_cl, wide[:, 1:3])
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    assert maxabs(out, ref) <= 1e-5
+    # odd width -> scalar (non-vectorised) kernel
+    out2 = vfi_b200.warp(src[..., :63].contiguous().to(DEV), flow[..., :63].contiguous().to(DEV))
+    assert maxabs(out2, oracle.warp_fwd(src[..., :63].numpy(), flow[..., :63].numpy())) <= 1e-5
+
+
+def test_warp_empty_batch_and_errors():
+    out = vfi_b200.warp(torch.zeros(0, 3, 8, 8, device=DEV), torch.zeros(0, 2, 8, 8, device=DEV))
+    assert out.shape == (0, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="flow must be"):
+        vfi_b200.warp(torch.zeros(1, 3, 8, 8, device=DEV), torch.zeros(1, 3, 8, 8, device=DEV))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_warp_low_precision(dtype):
+    g = torch.Generator().manual_seed(13)
+    src = torch.randn(2, 3, 72, 128, generator=g).to(dtype)
+    flow = (6 * torch.randn(2, 2, 72, 128, generator=g)).to(dtype)
+    ref = oracle.warp_fwd(src.float().numpy(), flow.float().numpy())
+    out = vfi_b200.warp(src.to(DEV), flow.to(DEV))
+    assert out.dtype == dtype
+    assert relerr(out, ref) <= 1e-2
+    out32 = vfi_b200.warp(src.to(DEV), flow.float().to(DEV))      # fp32 flow with low-precision frames
+    assert relerr(out32, ref) <= 1e-2
+
+
+def test_warp_blend_matches_composition():
+    g = torch.Generator().manual_seed(14)
+    a, b = torch.randn(2, 2, 3, 50, 70, generator=g)
+    fa, fb = 3 * torch.randn(2, 2, 2, 50, 70, generator=g)
+    m = torch.rand(2, 1, 50, 70, generator=g)
+    out = vfi_b200.warp_blend(a.to(DEV), fa.to(DEV), b.to(DEV), fb.to(DEV), m.to(DEV))
+    ref = oracle.warp_blend_fwd(a.numpy(), fa.numpy(), b.numpy(), fb.numpy(), m.numpy())
+    assert maxabs(out, ref) <= 1e-5
+
+
+def test_warp_full_size_properties_1080p_batch8_and_4k():
+    """BASELINE configs 2 and 4 at full size.  Properties that need no oracle: the op is exactly linear in the frame
+    (scaling by 2 commutes bit for bit), a constant frame stays constant wherever all four corners are inside, and
+    every batch entry agrees with the stock aten::grid_sampler_2d kernel driven the way the reference drives it.
+    (Zero flow is NOT the identity: the reference's normalise/un-normalise round trip moves samples by ~1e-4 px.)"""
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    for shape, sigma in [((8, 3, 1080, 1920), 8.0), ((1, 3, 2160, 3840), 64.0)]:
+        B, C, H, W = shape
+        src = torch.randn(shape, device=DEV, generator=g)
+        flow = sigma * torch.randn(B, 2, H, W, device=DEV, generator=g)       # incoherent displacement field
+        a = vfi_b200.warp(src, flow)
+        assert torch.equal(vfi_b200.warp(2.0 * src, flow), 2.0 * a)
+        for b in range(B):
+            ref = torch_ref.warp(src[b:b + 1], flow[b:b + 1])
+            assert maxabs(a[b:b + 1], ref) <= 1e-5
+        ones = vfi_b200.warp(torch.ones(1, 1, H, W, device=DEV), 0.4 * torch.ones(1, 2, H, W, device=DEV))
+        assert float((ones[:, :, : H - 1, : W - 1] - 1.0).abs().max()) <= 1e-6
+        del src, flow, a, ref, ones
+        torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------------------ DCN
+def run_dcn(z, dtype=torch.float32, math="auto", grads=True):
+    t = {k: cu(z[k], dtype if k in ("x", "offset", "mask", "weight", "bias", "grad_out") else None) for k in z}
+    leaves = [t[k].requires_grad_(grads) for k in ("x", "offset", "mask", "weight", "bias")]
+    out = vfi_b200.deform_conv2d(t["x"], t["offset"], t["weight"], t["bias"], stride=1, padding=1, dilation=1,
+                                 mask=t["mask"], math=math)
+    if grads:
+        out.backward(t["grad_out"])
+    return out, leaves
+
+
+@pytest.mark.parametrize("name", DCN_CASES)
+def test_dcn_fwd_bwd_golden(name):
+    z = load_golden(name)
+    out, (x, off, m, w, b) = run_dcn(z)
+    assert maxabs(out, z["out"]) <= 1e-5
+    for t, key in ((x, "grad_x"), (off, "grad_offset"), (m, "grad_mask"), (w, "grad_weight"), (b, "grad_bias")):
+        assert maxabs(t.grad, z[key]) <= tol(z[key]), key
+
+
+def rand_dcn(B, C, O, H, W, sigma, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    bound = 1.0 / (C * 9) ** 0.5
+    return dict(x=torch.randn(B, C, H, W, generator=g).numpy(),
+                offset=(sigma * torch.randn(B, 18, H, W, generator=g)).numpy(),
+                mask=torch.sigmoid(torch.randn(B, 9, H, W, generator=g)).numpy(),
+                weight=((torch.rand(O, C, 3, 3, generator=g) * 2 - 1) * bound).numpy(),
+                bias=((torch.rand(O, generator=g) * 2 - 1) * bound).numpy(),
+                grad_out=torch.randn(B, O, H, W, generator=g).numpy())
+
+
+@pytest.mark.parametrize("B,H,W,sigma", [(1, 37, 53, 1.5), (2, 16, 130, 8.0), (1, 64, 64, 0.0)])
+def test_dcn_fwd_bwd_vs_oracle(B, H, W, sigma):
+    z = rand_dcn(B, 67, 67, H, W, sigma, seed=B * 100 + H)
+    out, (x, off, m, w, b) = run_dcn(z)
+    assert maxabs(out, oracle.dcn_fwd(z["x"], z["offset"], z["mask"], z["weight"], z["bias"])) <= 1e-5
+    ref = oracle.dcn_bwd(z["grad_out"], z["x"], z["offset"], z["mask"], z["weight"])
+    for t, r, key in zip((x, off, m, w, b), ref, ("grad_x", "grad_offset", "grad_mask", "grad_weight", "grad_bias")):
+        assert maxabs(t.grad, r) <= tol(r, 2e-5), key
+
+
+def test_dcn_config1_size_vs_stock_torchvision_cuda():
+    """BASELINE config 1 geometry (256x256, batch 1, fp32) against torchvision's own CUDA kernel."""
+    z = rand_dcn(1, 67, 67, 256, 256, 1.5, seed=5)
+    out, (x, off, m, w, b) = run_dcn(z)
+    t = {k: cu(v).requires_grad_(k != "grad_out") for k, v in z.items()}
+    ref = torch_ref.dcn_stock(t["x"], t["offset"], t["mask"], t["weight"], t["bias"])
+    ref.backward(t["grad_out"])
+    assert maxabs(out, ref) <= 1e-5
+    for mine, key in ((x, "x"), (off, "offset"), (m, "mask"), (w, "weight"), (b, "bias")):
+        assert maxabs(mine.grad, t[key].grad) <= tol(t[key].grad, 3e-5), key
+
+
+def test_dcn_strided_inputs_and_mixed_dtypes():
+    z = rand_dcn(2, 67, 67, 24, 40, 2.0, seed=7)
+    ref = oracle.dcn_fwd(z["x"], z["offset"], z["mask"], z["weight"], z["bias"])
+    x_cl = cu(z["x"]).contiguous(memory_format=torch.channels_last)
+    out = vfi_b200.deform_conv2d(x_cl, cu(z["offset"]), cu(z["weight"]), cu(z["bias"]), stride=1, padding=1, dilation=1,
+                                 mask=cu(z["mask"]))
+    assert maxabs(out, ref) <= 1e-5
+    # what CUDA autocast hands over: fp32 activations, half-precision offsets and mask
+    off16, m16 = cu(z["offset"], torch.float16), cu(z["mask"], torch.float16)
+    ref16 = oracle.dcn_fwd(z["x"], off16.float().cpu().numpy(), m16.float().cpu().numpy(), z["weight"], z["bias"])
+    out16 = vfi_b200.deform_conv2d(cu(z["x"]), off16, cu(z["weight"]), cu(z["bias"]), stride=1, padding=1, dilation=1, mask=m16)
+    assert out16.dtype == torch.float32 and maxabs(out16, ref16) <= 1e-5
+
+
+def test_dcn_zero_offset_unit_mask_is_a_plain_convolution_1080p():
+    """Full 1080p frame: with offsets 0 and mask 1 DCNv2 degenerates to conv2d (checked against cuDNN)."""
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.randn(1, 67, 1080, 1920, device=DEV, generator=g)
+    w = (torch.rand(67, 67, 3, 3, device=DEV, generator=g) * 2 - 1) / 603 ** 0.5
+    b = torch.randn(67, device=DEV, generator=g) * 0.01
+    off = torch.zeros(1, 18, 1080, 1920, device=DEV)
+    m = torch.ones(1, 9, 1080, 1920, device=DEV)
+    out = vfi_b200.deform_conv2d(x, off, w, b, stride=1, padding=1, dilation=1, mask=m, math="fp32")
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.conv2d(x, w, b, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert maxabs(out, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_dcn_bf16_tensors(dtype):
+    """bf16 tensors: reference = fp32 arithmetic on bf16-rounded inputs (there is no native bf16 torchvision kernel)."""
+    z = rand_dcn(2, 67, 67, 40, 72, 1.5, seed=9)
+    zr = {k: bf16_round(v) for k, v in z.items()}
+    ref = oracle.dcn_fwd(zr["x"], zr["offset"], zr["mask"], zr["weight"], zr["bias"])
+    out, _ = run_dcn(z, dtype=dtype, grads=False)
+    assert out.dtype == dtype
+    assert relerr(out, ref) <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------------ path
+def test_model_hot_path_fixture_through_the_dropin():
+    """Replay of the tensors recorded inside the unmodified EMA_VFI.forward (golden model_24x32): warp -> cat -> 3 x
+    (split, DCN) with both seams patched, compared with what the reference model computed."""
+    import torchvision.ops
+
+    z = load_golden("model_24x32")
+    vfi_b200.install(torch_ref.WarpHost)
+    try:
+        host = torch_ref.WarpHost()
+        warped = host.warp(cu(z["frame2"]), cu(z["feat"]), cu(z["flow"]))
+        assert maxabs(warped, z["warped"]) <= 1e-5
+        x = torch.cat([cu(z["feat"]), warped], 1)
+        for i in range(3):
+            blk = torchvision.ops.DeformConv2d(67, 67, 3, padding=1).to(DEV)
+            blk.load_state_dict({"weight": cu(z[f"dcn_weight_{i}"]), "bias": cu(z[f"dcn_bias_{i}"])})
+            off, m = torch_ref.pack_split(cu(z[f"conv27_{i}"]))
+            x = blk(x, off, m)
+            assert maxabs(x, z[f"block_out_{i}"]) <= 2e-5, i
+        assert vfi_b200.dropin.call_counts()["dcn"] >= 3
+    finally:
+        vfi_b200.uninstall()
+
+
+def test_fusion_block_training_step_matches_stock_torchvision():
+    """A ModulatedDeformConvPack-shaped block trained one step through the drop-in vs through stock torchvision."""
+    torch.manual_seed(0)
+    blk = torch_ref.FusionBlock(67).to(DEV)
+    with torch.no_grad():
+        blk.offset_conv.weight.normal_(0, 0.02)
+        blk.offset_conv.bias.normal_(0, 0.5)
+    x = torch.randn(2, 67, 32, 48, device=DEV)
+    blk(x).square().mean().backward()
+    ref = {k: p.grad.clone() for k, p in blk.named_parameters()}
+    blk.zero_grad()
+    vfi_b200.install()
+    try:
+        blk(x).square().mean().backward()
+    finally:
+        vfi_b200.uninstall()
+    for k, p in blk.named_parameters():
+        assert maxabs(p.grad, ref[k]) <= tol(ref[k], 3e-5), k
+
+
+def test_smoke_entry():
+    import __graft_entry__
+
+    __graft_entry__.smoke()

@@ -1,0 +1,99 @@
+// abi.cu -- library-level entry points of libvfi_b200.so: version, errors, device check, DCN dispatch.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vfi {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+// dcn_simt.cu
+size_t dcn_simt_workspace_bytes();
+int dcn_simt_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
+                 int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st);
+// dcn_tc.cu
+bool dcn_tc_available();
+size_t dcn_tc_workspace_bytes(long long B, long long H, long long W);
+size_t dcn_tc_packed_weight_bytes();
+int dcn_tc_pack_weight(const void* weight, int weight_dtype, long long O, long long C, void* packed, cudaStream_t st);
+int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st);
+int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
+               int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, void* workspace,
+               size_t workspace_bytes, cudaStream_t st);
+
+}  // namespace vfi
+
+using namespace vfi;
+
+extern "C" int vfi_abi_version(void) { return VFI_B200_ABI_VERSION; }
+extern "C" const char* vfi_version_string(void) { return "vfi_b200 0.1 (sm_100a; warp + DCNv2 hot path)"; }
+extern "C" const char* vfi_last_error(void) { return g_err; }
+extern "C" int64_t vfi_launch_count(void) { return g_launches; }
+extern "C" void vfi_reset_launch_count(void) { g_launches = 0; }
+
+extern "C" int vfi_check_device(void) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no usable CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    return VFI_ERR_DEVICE;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; libvfi_b200 is built for sm_100a (B200) only", dev, major, minor);
+    return VFI_ERR_DEVICE;
+  }
+  return VFI_OK;
+}
+
+static int resolve_math(const vfi_tensor* x, int32_t math) {
+  if (math != VFI_DCN_MATH_AUTO) return math;
+  if (!dcn_tc_available()) return VFI_DCN_MATH_FP32;   // fp32 arithmetic on whatever dtype the tensors have
+  return (x && x->dtype == VFI_F32) ? VFI_DCN_MATH_FP32 : VFI_DCN_MATH_BF16_TC;
+}
+
+extern "C" size_t vfi_dcn_workspace_bytes(int64_t B, int64_t C, int64_t O, int64_t H, int64_t W, int32_t math) {
+  (void)C; (void)O;
+  size_t simt = dcn_simt_workspace_bytes();
+  if (math == VFI_DCN_MATH_FP32) return simt;
+  size_t tc = dcn_tc_workspace_bytes(B, H, W);
+  return tc > simt ? tc : simt;
+}
+
+extern "C" size_t vfi_dcn_packed_weight_bytes(void) { return dcn_tc_packed_weight_bytes(); }
+
+extern "C" int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
+                                   vfi_stream_t stream) {
+  return dcn_tc_pack_weight(weight, weight_dtype, O, C, packed, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_pack_input(const vfi_tensor* x, void* packed_nhwc72, vfi_stream_t stream) {
+  return dcn_tc_pack_input(x, packed_nhwc72, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
+                           int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out, int64_t O,
+                           int32_t math, void* workspace, size_t workspace_bytes, vfi_stream_t stream) {
+  VFI_REQUIRE(x, VFI_ERR_INVALID, "vfi_dcn_fwd: null tensor descriptor");
+  int m = resolve_math(x, math);
+  if (m == VFI_DCN_MATH_FP32)
+    return dcn_simt_fwd(x, offset, mask, weight, weight_dtype, bias, bias_dtype, out, O, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+  if (m == VFI_DCN_MATH_BF16_TC)
+    return dcn_tc_fwd(x, offset, mask, weight, weight_dtype, bias, bias_dtype, out, O, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+  set_error("vfi_dcn_fwd: unknown math mode %d", (int)math);
+  return VFI_ERR_INVALID;
+}

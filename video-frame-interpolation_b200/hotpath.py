@@ -1,0 +1,115 @@
+"""The hot path as one callable: warp -> concat -> 3 x (offset/mask split, DCNv2), i.e. lines 130-138 of
+/root/reference/src/models/ema_vfi.py with the tensors that stock convolutions produce (feat, flow, the three
+27-channel offset_conv outputs) taken as inputs.  This is the public API `bench.py` measures:
+
+* :meth:`HotPath.run`       -- inputs already resident in HBM (device tensors in, device tensor out)
+* :meth:`HotPath.run_host`  -- pinned HOST buffers in, pinned host buffer out; the call does the H2D copies, the
+  kernels and the D2H copy, pipelined frame by frame over three CUDA streams so PCIe in, compute and PCIe out overlap.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import ops
+
+
+def pack_split(conv27: torch.Tensor):
+    """ema_vfi.py:57-59 (stock PyTorch glue): thirds (0, 2) -> offset, sigmoid(third 1) -> mask."""
+    a, m, b = conv27.split(9, dim=1)
+    return torch.cat((a, b), dim=1), torch.sigmoid(m)
+
+
+class HotPath:
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], *, math: str = "auto"):
+        if len(weights) != len(biases):
+            raise ValueError("one bias per DCN block")
+        self.weights = list(weights)
+        self.biases = list(biases)
+        self.math = math
+        self._streams = None
+
+    # ---------------------------------------------------------------------------------------------- device API
+    def run(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor,
+            convs27: Sequence[torch.Tensor]) -> torch.Tensor:
+        warped = ops.warp(frame2, flow)
+        x = torch.cat((feat, warped), dim=1)
+        for w, b, c27 in zip(self.weights, self.biases, convs27):
+            offset, mask = pack_split(c27)
+            x = ops.deform_conv2d(x, offset, w, b, stride=1, padding=1, dilation=1, mask=mask, math=self.math)
+        return x
+
+    # ---------------------------------------------------------------------------------------------- host API
+    def run_host(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor, convs27: Sequence[torch.Tensor],
+                 out: torch.Tensor, chunk: int = 1) -> torch.Tensor:
+        """All arguments are pinned host tensors ([B,...]); ``out`` [B,O,H,W] receives the result.  Frames are
+        processed in chunks of ``chunk`` so that copy-in of chunk i+1, compute of chunk i and copy-out of chunk i-1
+        run concurrently.  Returns ``out`` after the last copy has completed (stream-synchronised)."""
+        dev = self.weights[0].device
+        for t in (frame2, flow, feat, out, *convs27):
+            if t.is_cuda or not t.is_pinned():
+                raise ValueError("run_host takes pinned host tensors")
+        if self._streams is None:
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        s_in, s_run, s_out = self._streams
+        cur = torch.cuda.current_stream(dev)
+        for s in self._streams:
+            s.wait_stream(cur)
+        B = frame2.shape[0]
+        keep = []
+        for i in range(0, B, chunk):
+            sl = slice(i, min(i + chunk, B))
+            with torch.cuda.stream(s_in):
+                d = [t[sl].to(dev, non_blocking=True) for t in (frame2, flow, feat, *convs27)]
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ready)
+                y = self.run(d[0], d[1], d[2], d[3:])
+                for t in d:
+                    t.record_stream(s_run)
+                done = torch.cuda.Event()
+                done.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                out[sl].copy_(y, non_blocking=True)
+                y.record_stream(s_out)
+            keep.append((d, y))
+        s_out.synchronize()
+        return out
+
+
+def synthetic_inputs(B: int, H: int, W: int, *, dtype=torch.bfloat16, device="cuda", seed: int = 1234,
+                     flow_sigma: float = 8.0, offset_sigma: float = 1.5, pinned_host: bool = False):
+    """Synthetic tensors of the shapes the path sees inside EMA_VFI.forward: ImageNet-normalised
+    uniform frames, Gaussian flow, N(0,1) features, and 27-channel offset_conv outputs whose offset thirds are
+    N(0, sigma^2) px and whose mask third is N(0,1) (-> sigmoid)."""
+    g = torch.Generator(device="cpu" if pinned_host else device).manual_seed(seed)
+    where = "cpu" if pinned_host else device
+
+    def fin(t):
+        t = t.to(dtype)
+        return t.pin_memory() if pinned_host else t
+
+    mean = torch.tensor([0.485, 0.456, 0.406], device=where).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=where).view(1, 3, 1, 1)
+    frame2 = fin((torch.rand(B, 3, H, W, generator=g, device=where) - mean) / std)
+    flow = fin(flow_sigma * torch.randn(B, 2, H, W, generator=g, device=where))
+    feat = fin(torch.randn(B, 64, H, W, generator=g, device=where))
+    convs = []
+    for _ in range(3):
+        c = torch.randn(B, 27, H, W, generator=g, device=where)
+        c[:, :9] *= offset_sigma
+        c[:, 18:] *= offset_sigma
+        convs.append(fin(c))
+    return frame2, flow, feat, convs
+
+
+def synthetic_weights(C: int = 67, *, dtype=torch.bfloat16, device="cuda", seed: int = 4321, blocks: int = 3):
+    """torchvision's DeformConv2d default init: kaiming-uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in)) for weight and bias."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    bound = 1.0 / (C * 9) ** 0.5
+    ws = [((torch.rand(C, C, 3, 3, generator=g) * 2 - 1) * bound).to(device=device, dtype=dtype) for _ in range(blocks)]
+    bs = [((torch.rand(C, generator=g) * 2 - 1) * bound).to(device=device, dtype=dtype) for _ in range(blocks)]
+    return ws, bs

@@ -1,0 +1,185 @@
+"""Autograd operators of the hot path, implemented by libvfi_b200.so (hand-written sm_100a CUDA).
+
+* :func:`warp`            -- ``EMA_VFI.warp`` (/root/reference/src/models/ema_vfi.py:149-171)
+* :func:`warp_blend`      -- north-star extension (no reference counterpart)
+* :func:`deform_conv2d`   -- ``torchvision.ops.deform_conv2d`` for the reference geometry (ema_vfi.py:45-60)
+
+Every op raises when its inputs are not on a B200: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, desc, dtype_code, ref, require_cuda, stream_handle
+
+__all__ = ["warp", "warp_blend", "deform_conv2d", "dcn_workspace_bytes", "launch_count", "reset_launch_count"]
+
+
+def launch_count() -> int:
+    return int(_lib.load().vfi_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().vfi_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------------ warp
+class _WarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+        dev = require_cuda(src, flow)
+        if src.dim() != 4 or flow.dim() != 4:
+            raise ValueError("warp expects src [B,C,H,W] and flow [B,2,H,W]")
+        if flow.dtype != torch.float32 and flow.dtype != src.dtype:
+            flow = flow.float()
+        out = torch.empty_like(src)   # keeps src's memory format (NCHW or channels_last)
+        with torch.cuda.device(dev):
+            check(_lib.load().vfi_warp_fwd(ref(desc(src)), ref(desc(flow)), ref(desc(out)), stream_handle(dev)),
+                  "vfi_warp_fwd")
+        ctx.save_for_backward(src, flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        src, flow = ctx.saved_tensors
+        dev = src.device
+        need_src, need_flow = ctx.needs_input_grad
+        if grad_out.dtype != src.dtype:
+            grad_out = grad_out.to(src.dtype)
+        gflow = torch.empty(flow.shape, dtype=torch.float32, device=dev)
+        gsrc = torch.zeros(src.shape, dtype=torch.float32, device=dev) if need_src else None
+        with torch.cuda.device(dev):
+            check(_lib.load().vfi_warp_bwd(ref(desc(grad_out)), ref(desc(src)), ref(desc(flow)), ref(desc(gflow)),
+                                           ref(desc(gsrc)) if gsrc is not None else None, stream_handle(dev)),
+                  "vfi_warp_bwd")
+        return (gsrc.to(src.dtype) if need_src else None), (gflow.to(flow.dtype) if need_flow else None)
+
+
+def warp(src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """Backward-warp ``src`` [B,C,H,W] by ``flow`` [B,2,H,W] (pixels; channel 0 = x, 1 = y).
+
+    Same result as the reference's grid build + normalise + ``F.grid_sample(bilinear, zeros,
+    align_corners=True)`` (fp32: max-abs 1e-5), in one kernel and without materialising the grid.
+    """
+    return _WarpFn.apply(src, flow)
+
+
+def warp_blend(src_a, flow_a, src_b, flow_b, m) -> torch.Tensor:
+    """``m * warp(src_a, flow_a) + (1 - m) * warp(src_b, flow_b)`` in one pass (forward only; m is [B,1,H,W])."""
+    dev = require_cuda(src_a, flow_a, src_b, flow_b, m)
+    if flow_a.dtype != torch.float32 and flow_a.dtype != src_a.dtype:
+        flow_a = flow_a.float()
+    flow_b = flow_b.to(flow_a.dtype)
+    m = m.to(src_a.dtype)
+    out = torch.empty_like(src_a, memory_format=torch.contiguous_format)
+    with torch.cuda.device(dev):
+        check(_lib.load().vfi_warp_blend_fwd(ref(desc(src_a)), ref(desc(flow_a)), ref(desc(src_b)), ref(desc(flow_b)),
+                                             ref(desc(m)), ref(desc(out)), stream_handle(dev)), "vfi_warp_blend_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ DCN
+_MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC}
+
+
+def dcn_workspace_bytes(B: int, C: int, O: int, H: int, W: int, math: str = "auto") -> int:
+    return int(_lib.load().vfi_dcn_workspace_bytes(B, C, O, H, W, _MATH[math]))
+
+
+def _workspace(dev, nbytes: int) -> torch.Tensor:
+    # Caller-owned workspace (the library never allocates): one uint8 tensor from the caching allocator.
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+
+
+class _DcnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, offset, mask, weight, bias, math: int):
+        dev = require_cuda(x, offset, mask, weight, bias)
+        B, C, H, W = x.shape
+        O = weight.shape[0]
+        if offset.dtype != mask.dtype:
+            mask = mask.to(offset.dtype)
+        weight_c = weight.contiguous()
+        bias_c = None if bias is None else bias.contiguous()
+        out = torch.empty((B, O, H, W), dtype=x.dtype, device=dev)
+        lib = _lib.load()
+        nbytes = int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, math))
+        ws = _workspace(dev, nbytes)
+        with torch.cuda.device(dev):
+            check(lib.vfi_dcn_fwd(ref(desc(x)), ref(desc(offset)), ref(desc(mask)), weight_c.data_ptr(),
+                                  dtype_code(weight_c.dtype), None if bias_c is None else bias_c.data_ptr(),
+                                  dtype_code(bias_c.dtype) if bias_c is not None else 0, ref(desc(out)), O, math,
+                                  ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_fwd")
+        ctx.save_for_backward(x, offset, mask, weight_c)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, offset, mask, weight = ctx.saved_tensors
+        dev = x.device
+        need_x, need_off, need_mask, need_w, need_b, _ = ctx.needs_input_grad
+        need_b = need_b and ctx.has_bias
+        B, C, H, W = x.shape
+        O = weight.shape[0]
+        if grad_out.dtype != x.dtype:
+            grad_out = grad_out.to(x.dtype)
+        lib = _lib.load()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gx = torch.zeros(x.shape, **f32) if need_x else None
+        goff = torch.empty(offset.shape, **f32) if need_off else None
+        gmask = torch.empty(mask.shape, **f32) if need_mask else None
+        with torch.cuda.device(dev):
+            if need_x or need_off or need_mask:
+                ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, _lib.MATH_FP32)))
+                check(lib.vfi_dcn_bwd_data(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)),
+                                           weight.data_ptr(), dtype_code(weight.dtype), O,
+                                           ref(desc(gx)) if need_x else None, ref(desc(goff)) if need_off else None,
+                                           ref(desc(gmask)) if need_mask else None, ws.data_ptr(), ws.numel(),
+                                           stream_handle(dev)), "vfi_dcn_bwd_data")
+            gw = torch.zeros(weight.shape, **f32) if need_w else None
+            gb = torch.zeros((O,), **f32) if need_b else None
+            if need_w or need_b:
+                check(lib.vfi_dcn_bwd_weight(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O,
+                                             gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
+                                             stream_handle(dev)), "vfi_dcn_bwd_weight")
+        return (gx.to(x.dtype) if need_x else None, goff.to(offset.dtype) if need_off else None,
+                gmask.to(mask.dtype) if need_mask else None, gw.to(weight.dtype) if need_w else None,
+                gb.to(ctx.bias_dtype) if need_b else None, None)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def deform_conv2d(input: torch.Tensor, offset: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask: Optional[torch.Tensor] = None,
+                  math: str = "auto") -> torch.Tensor:
+    """Drop-in for ``torchvision.ops.deform_conv2d`` (same positional/keyword arguments, same error for bad shapes)
+    restricted to the geometry the reference uses: 3x3 kernel, stride 1, padding 1, dilation 1, one weight group,
+    one offset group, modulation mask present.  Anything else raises ``NotImplementedError`` -- by design there is
+    no fallback to torchvision.
+    """
+    if input.dim() != 4 or weight.dim() != 4 or offset.dim() != 4:
+        raise ValueError("deform_conv2d expects 4-D input, offset and weight")
+    kh, kw = weight.shape[-2:]
+    geometry = (_pair(stride), _pair(padding), _pair(dilation), (kh, kw))
+    if geometry != ((1, 1), (1, 1), (1, 1), (3, 3)):
+        raise NotImplementedError(
+            f"vfi_b200.deform_conv2d implements stride=1, padding=1, dilation=1, 3x3 only (got stride={stride}, "
+            f"padding={padding}, dilation={dilation}, kernel={kh}x{kw})")
+    if mask is None:
+        raise NotImplementedError("vfi_b200.deform_conv2d implements the modulated (mask) form only (DCNv2)")
+    if weight.shape[1] != input.shape[1]:
+        raise NotImplementedError("vfi_b200.deform_conv2d implements groups=1 only")
+    if offset.shape[1] != 2 * kh * kw or mask.shape[1] != kh * kw:
+        raise NotImplementedError("vfi_b200.deform_conv2d implements one offset group only "
+                                  f"(offset has {offset.shape[1]} channels, mask {mask.shape[1]})")
+    if math not in _MATH:
+        raise ValueError(f"math must be one of {sorted(_MATH)}")
+    return _DcnFn.apply(input, offset, mask, weight, bias, _MATH[math])
