@@ -66,22 +66,30 @@ int vfi_check_device(void);                  /* VFI_OK when the current CUDA dev
 int64_t vfi_launch_count(void);
 void vfi_reset_launch_count(void);
 
+/* Flags of the warp entry points.  The reference line `2.0 * v / max(size-1, 1)` (ema_vfi.py:165-166) has two
+ * bit-level meanings: a true IEEE division when the reference runs on CPU (BASELINE config 1, the golden vectors),
+ * and a multiplication by the fp32 reciprocal when it runs on CUDA (aten's tensor/scalar fast path).  Default = IEEE. */
+#define VFI_WARP_DIV_IEEE 0
+#define VFI_WARP_DIV_RECIPROCAL 1
+
 /* ---- warp: replaces EMA_VFI.warp, /root/reference/src/models/ema_vfi.py:149-171 ----------------------------- */
 /* out[b,c,y,x] = bilinear(src[b,c], x + flow[b,0,y,x], y + flow[b,1,y,x]), zeros outside, align_corners=True,
  * with the reference's normalise/un-normalise round trip replayed in fp32.
  * src/out: [B,C,H,W] same dtype (f32|bf16|f16); flow: [B,2,H,W] f32 or the dtype of src. */
-int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, vfi_stream_t stream);
+int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, int32_t flags,
+                 vfi_stream_t stream);
 
 /* Autograd of the above (aten::grid_sampler_2d_backward chained through ema_vfi.py:165-166).
  * grad_flow [B,2,H,W] f32 is always written.  grad_src may be NULL (the model path: frame2 needs no grad); when
  * given it must be f32, zero-filled by the caller, and receives atomic scatter-adds. */
 int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, const vfi_tensor* flow,
-                 const vfi_tensor* grad_flow, const vfi_tensor* grad_src, vfi_stream_t stream);
+                 const vfi_tensor* grad_flow, const vfi_tensor* grad_src, int32_t flags, vfi_stream_t stream);
 
 /* North-star extension with no reference counterpart: one pass computing
  * out = m * warp(src_a, flow_a) + (1 - m) * warp(src_b, flow_b), m: [B,1,H,W]. */
 int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flow_a, const vfi_tensor* src_b,
-                       const vfi_tensor* flow_b, const vfi_tensor* m, const vfi_tensor* out, vfi_stream_t stream);
+                       const vfi_tensor* flow_b, const vfi_tensor* m, const vfi_tensor* out, int32_t flags,
+                       vfi_stream_t stream);
 
 /* ---- DCNv2: replaces torchvision.ops.deform_conv2d as called from ema_vfi.py:60 ---------------------------- */
 /* Geometry is the reference's: 3x3 kernel, stride 1, padding 1, dilation 1, groups 1, one offset group, mask on

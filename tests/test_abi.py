@@ -74,9 +74,9 @@ def test_abi_argument_validation_without_a_gpu():
     lib = _lib.load()
     src = _lib.VfiTensor(1, 0, 0, 1, 3, 4, 4, 48, 16, 4, 1)      # fake non-null pointer, never dereferenced
     flow_bad = _lib.VfiTensor(1, 0, 0, 1, 3, 4, 4, 48, 16, 4, 1)  # 3 channels instead of 2
-    rc = lib.vfi_warp_fwd(ctypes.byref(src), ctypes.byref(flow_bad), ctypes.byref(src), None)
+    rc = lib.vfi_warp_fwd(ctypes.byref(src), ctypes.byref(flow_bad), ctypes.byref(src), 0, None)
     assert rc == 1 and b"flow must be [B,2,H,W]" in lib.vfi_last_error()
-    rc = lib.vfi_warp_fwd(None, None, None, None)
+    rc = lib.vfi_warp_fwd(None, None, None, 0, None)
     assert rc == 1 and b"null" in lib.vfi_last_error()
     x = _lib.VfiTensor(1, 0, 0, 1, 100, 4, 4, 1600, 16, 4, 1)
     off = _lib.VfiTensor(1, 0, 0, 1, 18, 4, 4, 288, 16, 4, 1)

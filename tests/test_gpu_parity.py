@@ -148,12 +148,17 @@ def test_warp_full_size_properties_1080p_batch8_and_4k():
         flow = sigma * torch.randn(B, 2, H, W, device=DEV, generator=g)       # incoherent displacement field
         a = vfi_b200.warp(src, flow)
         assert torch.equal(vfi_b200.warp(2.0 * src, flow), 2.0 * a)
+        # the reference as it runs on CPU (true division): one batch entry through the stock CPU kernel
+        ref = torch_ref.warp(src[:1].cpu(), flow[:1].cpu())
+        assert maxabs(a[:1], ref) <= 1e-5
+        # the reference as it runs on CUDA (aten multiplies by the reciprocal): every batch entry, stock CUDA kernel
+        r = vfi_b200.warp(src, flow, division="reciprocal")
         for b in range(B):
             ref = torch_ref.warp(src[b:b + 1], flow[b:b + 1])
-            assert maxabs(a[b:b + 1], ref) <= 1e-5
+            assert maxabs(r[b:b + 1], ref) <= 1e-5
         ones = vfi_b200.warp(torch.ones(1, 1, H, W, device=DEV), 0.4 * torch.ones(1, 2, H, W, device=DEV))
         assert float((ones[:, :, : H - 1, : W - 1] - 1.0).abs().max()) <= 1e-6
-        del src, flow, a, ref, ones
+        del src, flow, a, r, ref, ones
         torch.cuda.empty_cache()
 
 

@@ -18,6 +18,7 @@ VFI_OK = 0
 ERR_NAMES = {1: "VFI_ERR_INVALID", 2: "VFI_ERR_UNSUPPORTED", 3: "VFI_ERR_CUDA", 4: "VFI_ERR_WORKSPACE", 5: "VFI_ERR_DEVICE"}
 F32, BF16, F16 = 0, 1, 2
 MATH_AUTO, MATH_FP32, MATH_BF16_TC = 0, 1, 2
+WARP_DIV_IEEE, WARP_DIV_RECIPROCAL = 0, 1
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 
@@ -36,9 +37,9 @@ SIGNATURES = {
     "vfi_check_device": (c_int, []),
     "vfi_launch_count": (c_int64, []),
     "vfi_reset_launch_count": (None, []),
-    "vfi_warp_fwd": (c_int, [_T, _T, _T, c_void_p]),
-    "vfi_warp_bwd": (c_int, [_T, _T, _T, _T, _T, c_void_p]),
-    "vfi_warp_blend_fwd": (c_int, [_T, _T, _T, _T, _T, _T, c_void_p]),
+    "vfi_warp_fwd": (c_int, [_T, _T, _T, c_int32, c_void_p]),
+    "vfi_warp_bwd": (c_int, [_T, _T, _T, _T, _T, c_int32, c_void_p]),
+    "vfi_warp_blend_fwd": (c_int, [_T, _T, _T, _T, _T, _T, c_int32, c_void_p]),
     "vfi_dcn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int32]),
     "vfi_dcn_packed_weight_bytes": (c_size_t, []),
     "vfi_dcn_pack_weight": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p]),

@@ -229,15 +229,17 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const WarpBwdParams q) {
   }
   // d(grid)/d(flow): aten scales by (size-1)/2, autograd of "2.0 * v / denom" divides by denom and doubles.
   float* gf = q.gflow + b * q.gf_sn + y * q.gf_sh + x * q.gf_sw;
-  gf[0] = __fmul_rn(__fdiv_rn(__fmul_rn(q.mult_x, gix), p.ax.denom), 2.0f);
-  gf[q.gf_sc] = __fmul_rn(__fdiv_rn(__fmul_rn(q.mult_y, giy), p.ay.denom), 2.0f);
+  const float ggx = __fmul_rn(q.mult_x, gix), ggy = __fmul_rn(q.mult_y, giy);
+  gf[0] = __fmul_rn(p.ax.recip ? __fmul_rn(ggx, p.ax.inv_denom) : __fdiv_rn(ggx, p.ax.denom), 2.0f);
+  gf[q.gf_sc] = __fmul_rn(p.ay.recip ? __fmul_rn(ggy, p.ay.inv_denom) : __fdiv_rn(ggy, p.ay.denom), 2.0f);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 int check_common(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, const char* who) {
   VFI_REQUIRE(src && flow && out, VFI_ERR_INVALID, "%s: null tensor descriptor", who);
-  VFI_REQUIRE(src->data && flow->data && out->data, VFI_ERR_INVALID, "%s: null data pointer", who);
   VFI_REQUIRE(src->n >= 0 && src->c >= 0 && src->h >= 0 && src->w >= 0, VFI_ERR_INVALID, "%s: negative extent", who);
+  const bool empty = src->n == 0 || src->c == 0 || src->h == 0 || src->w == 0;
+  VFI_REQUIRE(empty || (src->data && flow->data && out->data), VFI_ERR_INVALID, "%s: null data pointer", who);
   VFI_REQUIRE(same_shape(src, out), VFI_ERR_INVALID, "%s: out shape must equal src shape", who);
   VFI_REQUIRE(flow->n == src->n && flow->c == 2 && flow->h == src->h && flow->w == src->w, VFI_ERR_INVALID,
               "%s: flow must be [B,2,H,W] matching src (got [%lld,%lld,%lld,%lld])", who, (long long)flow->n,
@@ -252,7 +254,7 @@ int check_common(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor
   return VFI_OK;
 }
 
-WarpParams make_params(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out) {
+WarpParams make_params(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, int flags) {
   WarpParams p;
   p.src = src->data; p.flow = flow->data; p.out = out ? out->data : nullptr;
   p.s_sn = src->sn; p.s_sc = src->sc; p.s_sh = src->sh; p.s_sw = src->sw;
@@ -260,8 +262,8 @@ WarpParams make_params(const vfi_tensor* src, const vfi_tensor* flow, const vfi_
   if (out) { p.o_sn = out->sn; p.o_sc = out->sc; p.o_sh = out->sh; p.o_sw = out->sw; }
   else { p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0; }
   p.B = (int)src->n; p.C = (int)src->c; p.H = (int)src->h; p.W = (int)src->w;
-  p.ax = make_warp_axis(src->w);
-  p.ay = make_warp_axis(src->h);
+  p.ax = make_warp_axis(src->w, flags & VFI_WARP_DIV_RECIPROCAL);
+  p.ay = make_warp_axis(src->h, flags & VFI_WARP_DIV_RECIPROCAL);
   return p;
 }
 
@@ -292,12 +294,13 @@ int launch_fwd(const WarpParams& p, bool vec4, cudaStream_t st) {
 
 using namespace vfi;
 
-extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, vfi_stream_t stream) {
+extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, int32_t flags,
+                            vfi_stream_t stream) {
   int rc = check_common(src, flow, out, "vfi_warp_fwd");
   if (rc) return rc;
   if (src->n == 0 || src->c == 0 || src->h == 0 || src->w == 0) return VFI_OK;
   VFI_REQUIRE((long long)src->n * src->h * src->w < (1LL << 40), VFI_ERR_UNSUPPORTED, "vfi_warp_fwd: too many pixels");
-  WarpParams p = make_params(src, flow, out);
+  WarpParams p = make_params(src, flow, out, flags);
   bool vec4 = rows_vec4(flow) && rows_vec4(out);
   cudaStream_t st = (cudaStream_t)stream;
   VFI_DISPATCH(src->dtype, TS, {
@@ -309,18 +312,18 @@ extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const
 
 extern "C" int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flow_a, const vfi_tensor* src_b,
                                   const vfi_tensor* flow_b, const vfi_tensor* m, const vfi_tensor* out,
-                                  vfi_stream_t stream) {
+                                  int32_t flags, vfi_stream_t stream) {
   int rc = check_common(src_a, flow_a, out, "vfi_warp_blend_fwd");
   if (rc) return rc;
   rc = check_common(src_b, flow_b, out, "vfi_warp_blend_fwd");
   if (rc) return rc;
-  VFI_REQUIRE(m && m->data && m->n == out->n && m->c == 1 && m->h == out->h && m->w == out->w, VFI_ERR_INVALID,
+  VFI_REQUIRE(m && m->n == out->n && m->c == 1 && m->h == out->h && m->w == out->w, VFI_ERR_INVALID,
               "vfi_warp_blend_fwd: m must be [B,1,H,W]");
   VFI_REQUIRE(m->dtype == out->dtype && flow_a->dtype == flow_b->dtype, VFI_ERR_INVALID,
               "vfi_warp_blend_fwd: dtype mismatch");
   if (out->n == 0 || out->c == 0 || out->h == 0 || out->w == 0) return VFI_OK;
   BlendParams q;
-  q.a = make_params(src_a, flow_a, out);
+  q.a = make_params(src_a, flow_a, out, flags);
   q.src_b = src_b->data; q.flow_b = flow_b->data; q.m = m->data;
   q.b_sn = src_b->sn; q.b_sc = src_b->sc; q.b_sh = src_b->sh; q.b_sw = src_b->sw;
   q.g_sn = flow_b->sn; q.g_sc = flow_b->sc; q.g_sh = flow_b->sh; q.g_sw = flow_b->sw;
@@ -337,9 +340,11 @@ extern "C" int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flo
 }
 
 extern "C" int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, const vfi_tensor* flow,
-                            const vfi_tensor* grad_flow, const vfi_tensor* grad_src, vfi_stream_t stream) {
+                            const vfi_tensor* grad_flow, const vfi_tensor* grad_src, int32_t flags,
+                            vfi_stream_t stream) {
   VFI_REQUIRE(grad_out && grad_flow && src && flow, VFI_ERR_INVALID, "vfi_warp_bwd: null tensor descriptor");
-  VFI_REQUIRE(grad_out->data && src->data && flow->data, VFI_ERR_INVALID, "vfi_warp_bwd: null data pointer");
+  const bool empty_b = src->n == 0 || src->c == 0 || src->h == 0 || src->w == 0;
+  VFI_REQUIRE(empty_b || (grad_out->data && src->data && flow->data), VFI_ERR_INVALID, "vfi_warp_bwd: null data pointer");
   VFI_REQUIRE(same_shape(src, grad_out), VFI_ERR_INVALID, "vfi_warp_bwd: grad_out shape must equal src shape");
   VFI_REQUIRE(flow->n == src->n && flow->c == 2 && flow->h == src->h && flow->w == src->w, VFI_ERR_INVALID,
               "vfi_warp_bwd: flow must be [B,2,H,W] matching src");
@@ -348,7 +353,7 @@ extern "C" int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, c
   VFI_REQUIRE((src->h - 1) * llabs(src->sh) + (src->w - 1) * llabs(src->sw) < 2147483647LL, VFI_ERR_UNSUPPORTED,
               "vfi_warp_bwd: one source plane must span < 2^31 elements");
   int rc = VFI_OK;
-  VFI_REQUIRE(same_shape(grad_flow, flow) && grad_flow->dtype == VFI_F32 && grad_flow->data, VFI_ERR_INVALID,
+  VFI_REQUIRE(same_shape(grad_flow, flow) && grad_flow->dtype == VFI_F32 && (empty_b || grad_flow->data), VFI_ERR_INVALID,
               "vfi_warp_bwd: grad_flow must be f32 [B,2,H,W]");
   if (grad_src) {
     VFI_REQUIRE(same_shape(grad_src, src) && grad_src->dtype == VFI_F32 && grad_src->data, VFI_ERR_INVALID,
@@ -356,7 +361,7 @@ extern "C" int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, c
   }
   if (src->n == 0 || src->h == 0 || src->w == 0) return VFI_OK;
   WarpBwdParams q;
-  q.f = make_params(src, flow, nullptr);
+  q.f = make_params(src, flow, nullptr, flags);
   q.gout = grad_out->data; q.gflow = (float*)grad_flow->data; q.gsrc = grad_src ? (float*)grad_src->data : nullptr;
   q.go_sn = grad_out->sn; q.go_sc = grad_out->sc; q.go_sh = grad_out->sh; q.go_sw = grad_out->sw;
   q.gf_sn = grad_flow->sn; q.gf_sc = grad_flow->sc; q.gf_sh = grad_flow->sh; q.gf_sw = grad_flow->sw;

@@ -38,10 +38,12 @@ struct WarpAxis {
   float inv_denom;  // RN(1 / denom), host-computed
   float size_m1;    // float(size-1)
   float hi;         // float(size) + 4: positions outside [-4, hi] touch no valid corner
+  int recip;        // 1: a / d is computed as a * RN(1/d), which is what aten's CUDA `tensor / python_scalar` does
 };
 
-static inline WarpAxis make_warp_axis(long long size) {
+static inline WarpAxis make_warp_axis(long long size, int recip = 0) {
   WarpAxis a;
+  a.recip = recip;
   a.denom = (float)(size - 1 > 1 ? size - 1 : 1);
   a.inv_denom = 1.0f / a.denom;
   a.size_m1 = (float)(size - 1);
@@ -49,9 +51,14 @@ static inline WarpAxis make_warp_axis(long long size) {
   return a;
 }
 
-// Correctly rounded a / ax.denom.
+// Correctly rounded a / ax.denom (IEEE mode), or a * RN(1/denom) (reciprocal mode).
+//
+// Two references exist for this one line of ema_vfi.py: on CPU `tensor / python_scalar` is a true IEEE division, on
+// CUDA aten multiplies by the fp32 reciprocal of the scalar (div_true_kernel_cuda).  The two differ by 1 ulp of the
+// coordinate often enough to move noise-frame outputs by ~1e-3 at 1080p/4K, so both are offered (vfi_b200.h flags).
 VFI_HD float vfi_div_exact(float a, const WarpAxis& ax) {
   float q = VFI_MUL(a, ax.inv_denom);
+  if (ax.recip) return q;
   float r = VFI_FMA(-q, ax.denom, a);
   return VFI_FMA(r, ax.inv_denom, q);
 }

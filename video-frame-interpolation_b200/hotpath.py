@@ -81,9 +81,11 @@ class HotPath:
 
 
 def synthetic_inputs(B: int, H: int, W: int, *, dtype=torch.bfloat16, device="cuda", seed: int = 1234,
-                     flow_sigma: float = 8.0, offset_sigma: float = 1.5, pinned_host: bool = False):
+                     flow_sigma: float = 8.0, offset_sigma: float = 1.5, pinned_host: bool = False,
+                     flow_kind: str = "smooth"):
     """Synthetic tensors of the shapes the path sees inside EMA_VFI.forward: ImageNet-normalised
-    uniform frames, Gaussian flow, N(0,1) features, and 27-channel offset_conv outputs whose offset thirds are
+    uniform frames, a flow field (``smooth``: N(0,1) at 1/32 resolution, bilinearly up-sampled, times ``flow_sigma`` px --
+    the locality real optical flow has; ``iid``: per-pixel N(0, sigma^2), the worst-case gather), N(0,1) features, and 27-channel offset_conv outputs whose offset thirds are
     N(0, sigma^2) px and whose mask third is N(0,1) (-> sigmoid)."""
     g = torch.Generator(device="cpu" if pinned_host else device).manual_seed(seed)
     where = "cpu" if pinned_host else device
@@ -95,7 +97,14 @@ def synthetic_inputs(B: int, H: int, W: int, *, dtype=torch.bfloat16, device="cu
     mean = torch.tensor([0.485, 0.456, 0.406], device=where).view(1, 3, 1, 1)
     std = torch.tensor([0.229, 0.224, 0.225], device=where).view(1, 3, 1, 1)
     frame2 = fin((torch.rand(B, 3, H, W, generator=g, device=where) - mean) / std)
-    flow = fin(flow_sigma * torch.randn(B, 2, H, W, generator=g, device=where))
+    if flow_kind == "smooth":
+        coarse = torch.randn(B, 2, max(H // 32, 2), max(W // 32, 2), generator=g, device=where)
+        flow = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True) * flow_sigma
+    elif flow_kind == "iid":
+        flow = flow_sigma * torch.randn(B, 2, H, W, generator=g, device=where)
+    else:
+        raise ValueError(f"unknown flow_kind {flow_kind!r}")
+    flow = fin(flow)
     feat = fin(torch.randn(B, 64, H, W, generator=g, device=where))
     convs = []
     for _ in range(3):

@@ -30,15 +30,16 @@ def reset_launch_count() -> None:
 # ------------------------------------------------------------------------------------------------------ warp
 class _WarpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    def forward(ctx, src: torch.Tensor, flow: torch.Tensor, flags: int = 0) -> torch.Tensor:
         dev = require_cuda(src, flow)
+        ctx.flags = flags
         if src.dim() != 4 or flow.dim() != 4:
             raise ValueError("warp expects src [B,C,H,W] and flow [B,2,H,W]")
         if flow.dtype != torch.float32 and flow.dtype != src.dtype:
             flow = flow.float()
         out = torch.empty_like(src)   # keeps src's memory format (NCHW or channels_last)
         with torch.cuda.device(dev):
-            check(_lib.load().vfi_warp_fwd(ref(desc(src)), ref(desc(flow)), ref(desc(out)), stream_handle(dev)),
+            check(_lib.load().vfi_warp_fwd(ref(desc(src)), ref(desc(flow)), ref(desc(out)), flags, stream_handle(dev)),
                   "vfi_warp_fwd")
         ctx.save_for_backward(src, flow)
         return out
@@ -47,28 +48,35 @@ class _WarpFn(torch.autograd.Function):
     def backward(ctx, grad_out: torch.Tensor):
         src, flow = ctx.saved_tensors
         dev = src.device
-        need_src, need_flow = ctx.needs_input_grad
+        need_src, need_flow = ctx.needs_input_grad[:2]
         if grad_out.dtype != src.dtype:
             grad_out = grad_out.to(src.dtype)
         gflow = torch.empty(flow.shape, dtype=torch.float32, device=dev)
         gsrc = torch.zeros(src.shape, dtype=torch.float32, device=dev) if need_src else None
         with torch.cuda.device(dev):
             check(_lib.load().vfi_warp_bwd(ref(desc(grad_out)), ref(desc(src)), ref(desc(flow)), ref(desc(gflow)),
-                                           ref(desc(gsrc)) if gsrc is not None else None, stream_handle(dev)),
-                  "vfi_warp_bwd")
-        return (gsrc.to(src.dtype) if need_src else None), (gflow.to(flow.dtype) if need_flow else None)
+                                           ref(desc(gsrc)) if gsrc is not None else None, ctx.flags,
+                                           stream_handle(dev)), "vfi_warp_bwd")
+        return (gsrc.to(src.dtype) if need_src else None), (gflow.to(flow.dtype) if need_flow else None), None
 
 
-def warp(src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+_DIVISION = {"ieee": _lib.WARP_DIV_IEEE, "reciprocal": _lib.WARP_DIV_RECIPROCAL}
+
+
+def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee") -> torch.Tensor:
     """Backward-warp ``src`` [B,C,H,W] by ``flow`` [B,2,H,W] (pixels; channel 0 = x, 1 = y).
 
     Same result as the reference's grid build + normalise + ``F.grid_sample(bilinear, zeros,
     align_corners=True)`` (fp32: max-abs 1e-5), in one kernel and without materialising the grid.
+
+    ``division`` selects which bit-level meaning of the reference's ``2.0 * v / (size-1)`` is replayed: ``"ieee"``
+    (what the reference computes on CPU -- BASELINE config 1 and the golden vectors) or ``"reciprocal"`` (what aten
+    computes for ``tensor / python_scalar`` on CUDA: a multiplication by the fp32 reciprocal).
     """
-    return _WarpFn.apply(src, flow)
+    return _WarpFn.apply(src, flow, _DIVISION[division])
 
 
-def warp_blend(src_a, flow_a, src_b, flow_b, m) -> torch.Tensor:
+def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch.Tensor:
     """``m * warp(src_a, flow_a) + (1 - m) * warp(src_b, flow_b)`` in one pass (forward only; m is [B,1,H,W])."""
     dev = require_cuda(src_a, flow_a, src_b, flow_b, m)
     if flow_a.dtype != torch.float32 and flow_a.dtype != src_a.dtype:
@@ -78,7 +86,8 @@ def warp_blend(src_a, flow_a, src_b, flow_b, m) -> torch.Tensor:
     out = torch.empty_like(src_a, memory_format=torch.contiguous_format)
     with torch.cuda.device(dev):
         check(_lib.load().vfi_warp_blend_fwd(ref(desc(src_a)), ref(desc(flow_a)), ref(desc(src_b)), ref(desc(flow_b)),
-                                             ref(desc(m)), ref(desc(out)), stream_handle(dev)), "vfi_warp_blend_fwd")
+                                             ref(desc(m)), ref(desc(out)), _DIVISION[division], stream_handle(dev)),
+              "vfi_warp_blend_fwd")
     return out
 
 
