@@ -97,8 +97,10 @@ int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flow_a, const 
  * mask [B,9,H,W]; weight [O,C,3,3] contiguous; bias [O] or NULL; out [B,O,H,W]. */
 size_t vfi_dcn_workspace_bytes(int64_t B, int64_t C, int64_t O, int64_t H, int64_t W, int32_t math);
 
-/* Packs weight [O,C,3,3] (f32|bf16|f16) into the K-major bf16 operand image the tcgen05 kernel TMA-loads:
- * [80 rows (o, zero padded)][656 (tap-major: k*72 + c, zero padded)] bf16.  `packed` needs vfi_dcn_packed_weight_bytes(). */
+/* Packs weight [O,C,3,3] (f32|bf16|f16) into the bf16 B-operand image the tcgen05 kernel bulk-copies into shared
+ * memory: 11 K blocks x [80 rows (o, zero padded)] x 128 B, K order q = tap*72 + c (zero padded to 704), each row's
+ * eight 16-byte chunks already permuted for the SWIZZLE_128B canonical layout (chunk j of row r stored at j ^ (r & 7)).
+ * `packed` needs vfi_dcn_packed_weight_bytes() = 112,640 bytes, 16-byte aligned. */
 size_t vfi_dcn_packed_weight_bytes(void);
 int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
                         vfi_stream_t stream);
@@ -121,6 +123,12 @@ int vfi_dcn_bwd_data(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_
 int vfi_dcn_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset,
                        const vfi_tensor* mask, int64_t O, float* grad_weight, float* grad_bias,
                        vfi_stream_t stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------------ */
+/* D[128,80] (f32, row-major) = A[128,K] * B[80,K]^T with A, B row-major bf16 in device memory, K % 64 == 0.  One CTA,
+ * serialised; exercises exactly the shared-memory descriptors, swizzle, tcgen05.mma/commit/ld and TMEM allocation the
+ * DCN kernel uses, so a wrong DCN result can be attributed to the tensor-core plumbing or to the gather. */
+int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream);
 
 #ifdef __cplusplus
 }

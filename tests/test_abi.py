@@ -34,7 +34,7 @@ def test_python_binding_matches_header():
     lib = _lib.load()
     assert lib.vfi_abi_version() == int(re.search(r"VFI_B200_ABI_VERSION (\d+)", HEADER).group(1))
     assert b"sm_100a" in lib.vfi_version_string()
-    assert lib.vfi_dcn_packed_weight_bytes() == 80 * 656 * 2
+    assert lib.vfi_dcn_packed_weight_bytes() == 11 * 80 * 128
     assert lib.vfi_dcn_workspace_bytes(1, 67, 67, 8, 8, _lib.MATH_FP32) >= 2 * 9 * 72 * 72 * 4
 
 

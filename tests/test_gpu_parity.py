@@ -247,15 +247,89 @@ def test_dcn_zero_offset_unit_mask_is_a_plain_convolution_1080p():
     assert maxabs(out, ref) <= 2e-5
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16])
-def test_dcn_bf16_tensors(dtype):
-    """bf16 tensors: reference = fp32 arithmetic on bf16-rounded inputs (there is no native bf16 torchvision kernel)."""
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_dcn_low_precision_tensors_fp32_math(dtype):
+    """Low-precision tensors through the fp32-arithmetic kernels (forward and backward): reference = fp32 arithmetic
+    on the rounded inputs (there is no native bf16 torchvision kernel)."""
     z = rand_dcn(2, 67, 67, 40, 72, 1.5, seed=9)
-    zr = {k: bf16_round(v) for k, v in z.items()}
+    zr = {k: torch.from_numpy(v).to(dtype).float().numpy() for k, v in z.items()}
     ref = oracle.dcn_fwd(zr["x"], zr["offset"], zr["mask"], zr["weight"], zr["bias"])
-    out, _ = run_dcn(z, dtype=dtype, grads=False)
+    out, leaves = run_dcn(z, dtype=dtype, math="fp32", grads=True)
+    gref = oracle.dcn_bwd(zr["grad_out"], zr["x"], zr["offset"], zr["mask"], zr["weight"])
+    for t, r in zip(leaves, gref):
+        assert relerr(t.grad, r) <= 2e-2
     assert out.dtype == dtype
     assert relerr(out, ref) <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------------ tcgen05
+def test_umma_selftest_matches_matmul():
+    """The tensor-core plumbing alone (descriptors, SWIZZLE_128B layout, tcgen05.mma/commit/ld, TMEM) as a plain GEMM."""
+    from vfi_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    for K in (64, 192, 704):
+        a = torch.randn(128, K, generator=g).to(torch.bfloat16).to(DEV)
+        b = torch.randn(80, K, generator=g).to(torch.bfloat16).to(DEV)
+        d = ops.selftest_umma(a, b)
+        ref = a.float() @ b.float().t()
+        assert maxabs(d, ref) <= 1e-3 * max(1.0, float(ref.abs().max())), K
+
+
+@pytest.mark.parametrize("B,H,W,sigma", [(1, 8, 16, 0.0), (1, 8, 16, 1.5), (2, 37, 53, 1.5), (1, 64, 96, 8.0)])
+def test_dcn_tensor_core_path(B, H, W, sigma):
+    """bf16 operands / fp32 accumulate through tcgen05: reference = fp32 arithmetic on the bf16-rounded inputs."""
+    z = rand_dcn(B, 67, 67, H, W, sigma, seed=31 + H)
+    zr = {k: bf16_round(v) for k, v in z.items()}
+    ref = oracle.dcn_fwd(zr["x"], zr["offset"], zr["mask"], zr["weight"], zr["bias"])
+    t = {k: cu(z[k], torch.bfloat16) for k in ("x", "offset", "mask", "weight", "bias")}
+    out = vfi_b200.deform_conv2d(t["x"], t["offset"], t["weight"], t["bias"], stride=1, padding=1, dilation=1,
+                                 mask=t["mask"], math="bf16_tc")
+    assert out.shape == (B, 67, H, W) and out.dtype == torch.bfloat16
+    assert out.stride() == (H * W * 72, 1, W * 72, 72)          # channel-padded channels-last view
+    assert relerr(out, ref) <= 1e-2
+    # chained: the packed output feeds the next layer without a layout pass, fp32 offsets/mask accepted
+    out2 = vfi_b200.deform_conv2d(out, cu(z["offset"]), t["weight"], t["bias"], stride=1, padding=1, dilation=1,
+                                  mask=cu(z["mask"]), math="bf16_tc")
+    ref2 = oracle.dcn_fwd(out.float().cpu().numpy(), z["offset"], z["mask"], zr["weight"], zr["bias"])
+    assert relerr(out2, ref2) <= 1e-2
+    # fp32 tensors routed through the tensor-core path (inputs rounded to bf16 inside), NCHW fp32 result
+    out3 = vfi_b200.deform_conv2d(cu(z["x"]), cu(z["offset"]), cu(z["weight"]), cu(z["bias"]), stride=1, padding=1,
+                                  dilation=1, mask=cu(z["mask"]), math="bf16_tc")
+    assert out3.dtype == torch.float32 and out3.is_contiguous()
+    ref3 = oracle.dcn_fwd(zr["x"], z["offset"], z["mask"], zr["weight"], z["bias"])
+    assert relerr(out3, ref3) <= 1e-2
+
+
+def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
+    """Full 1080p frame: tcgen05 result against this library's fp32 parity kernel on the same bf16-rounded inputs."""
+    g = torch.Generator(device=DEV).manual_seed(41)
+    x = torch.randn(1, 67, 1080, 1920, device=DEV, generator=g).to(torch.bfloat16)
+    off = (1.5 * torch.randn(1, 18, 1080, 1920, device=DEV, generator=g)).to(torch.bfloat16)
+    m = torch.sigmoid(torch.randn(1, 9, 1080, 1920, device=DEV, generator=g)).to(torch.bfloat16)
+    w = ((torch.rand(67, 67, 3, 3, device=DEV, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
+    b = (torch.randn(67, device=DEV, generator=g) * 0.01).to(torch.bfloat16)
+    out = vfi_b200.deform_conv2d(x, off, w, b, stride=1, padding=1, dilation=1, mask=m, math="bf16_tc")
+    ref = vfi_b200.deform_conv2d(x.float(), off.float(), w.float(), b.float(), stride=1, padding=1, dilation=1,
+                                 mask=m.float(), math="fp32")
+    err = float((out.float() - ref).abs().max()) / float(ref.abs().max())
+    assert err <= 1e-2, err
+
+
+def test_hot_path_bf16_tensor_core_vs_fp32_reference_psnr():
+    """warp -> fused buffer -> 3 x DCN on the tensor-core path against the fp32 oracle chain on bf16-rounded inputs."""
+    from vfi_b200.hotpath import HotPath, synthetic_inputs, synthetic_weights
+
+    B, H, W = 1, 48, 80
+    frame2, flow, feat, convs = synthetic_inputs(B, H, W, dtype=torch.bfloat16, device=DEV, seed=5)
+    ws, bs = synthetic_weights(dtype=torch.bfloat16, device=DEV)
+    out = HotPath(ws, bs, math="bf16_tc").run(frame2, flow, feat.contiguous(memory_format=torch.channels_last), convs)
+    f = lambda t: t.float().cpu().numpy()  # noqa: E731
+    x = np.concatenate([f(feat), oracle.warp_fwd(f(frame2), f(flow))], 1)
+    for w, b, c in zip(ws, bs, convs):
+        o, m = oracle.pack_split(f(c))
+        x = oracle.dcn_fwd(x, bf16_round(o), bf16_round(m), f(w), f(b))
+    assert relerr(out, x) <= 2e-2     # three chained bf16 layers
 
 
 # ------------------------------------------------------------------------------------------------------------ path

@@ -25,7 +25,9 @@ int dcn_simt_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor
 bool dcn_tc_available();
 size_t dcn_tc_workspace_bytes(long long B, long long H, long long W);
 size_t dcn_tc_packed_weight_bytes();
-int dcn_tc_pack_weight(const void* weight, int weight_dtype, long long O, long long C, void* packed, cudaStream_t st);
+int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
+                       void* packed, float* bias_out, cudaStream_t st);
+int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st);
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
                int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, void* workspace,
@@ -76,7 +78,7 @@ extern "C" size_t vfi_dcn_packed_weight_bytes(void) { return dcn_tc_packed_weigh
 
 extern "C" int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
                                    vfi_stream_t stream) {
-  return dcn_tc_pack_weight(weight, weight_dtype, O, C, packed, (cudaStream_t)stream);
+  return dcn_tc_pack_weight(weight, weight_dtype, nullptr, VFI_F32, O, C, packed, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int vfi_dcn_pack_input(const vfi_tensor* x, void* packed_nhwc72, vfi_stream_t stream) {
@@ -96,4 +98,8 @@ extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const 
                       (cudaStream_t)stream);
   set_error("vfi_dcn_fwd: unknown math mode %d", (int)math);
   return VFI_ERR_INVALID;
+}
+
+extern "C" int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream) {
+  return umma_selftest(a_bf16, b_bf16, d, K, (cudaStream_t)stream);
 }

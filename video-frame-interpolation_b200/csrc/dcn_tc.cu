@@ -1,43 +1,174 @@
-// dcn_tc.cu -- DCNv2 forward as a tcgen05 / TMEM implicit GEMM (bf16 operands, fp32 accumulate).  PLACEHOLDER:
-// the operand packers are real; the tensor-core kernel lands in the next commit.
+// dcn_tc.cu -- DCNv2 forward as a tcgen05 / TMEM implicit GEMM for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Replaces torchvision::deform_conv2d (call site /root/reference/src/models/ema_vfi.py:60) on the throughput path.
+// torchvision materialises columns[603, P] in HBM (40 GB fp32 at 1080p batch 8) and calls a BLAS GEMM; here the
+// modulated bilinear im2col is the A-operand PRODUCER of the GEMM and never leaves the SM:
+//
+//     D[128 px, 80 o] (TMEM, fp32)  +=  A[128 px, 64 k] (smem, written by 8 gather warps)  x  B[80 o, 64 k]^T (smem, bulk copy)
+//
+//   K ordering  : q = tap * 72 + c  (tap = 3i + j, c < 67 real, 67..71 zero) -> 648, padded to 656 = 41 x UMMA_K(16)
+//   A stage     : 128 rows x 128 B, canonical K-major SWIZZLE_128B (16-byte chunk j of row r sits at chunk j ^ (r & 7))
+//   B stage     : 80 rows x 128 B of the pre-swizzled weight image, one cp.async.bulk (UBLKCP) per K block
+//   accumulator : 2 x (128 lanes x 80 columns) in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
+//   tile        : 8 rows x 16 columns of output pixels (keeps the gather footprint, ~75 KB at sigma = 1.5 px, inside L1)
+//
+// Warp roles (416 threads, one persistent CTA per SM):
+//   warps 0-7  producers: per tile compute the 9 x 128 tap geometries once (corner pixel indices + mask-folded weights),
+//              then per K block gather 4 corners x 16 B per (row, chunk) item with 128-bit read-only loads, lerp in fp32,
+//              pack to bf16 and store 16 B into the swizzled A stage; fence.proxy.async; one arrive per warp.
+//   warp 8     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
+//   warps 9-12 epilogue: tcgen05.ld the accumulator (lane = pixel), + bias, convert, store.
+//
+// The activation image the producers gather from is channel-padded channels-last bf16: [B, H, W, 72] (144 B / pixel,
+// nine 16-byte chunks).  Any other layout is converted by pack_input_kernel first (workspace).
 #include "common.cuh"
 
 namespace vfi {
 
-constexpr int TC_N = 80;        // UMMA N: 67 output channels padded to a multiple of 16
-constexpr int TC_CPAD = 72;     // channels per tap in the K dimension (67 padded to a multiple of 8)
-constexpr int TC_K = 656;       // 9 * 72 = 648 padded to a multiple of UMMA_K = 16
+constexpr int TC_M = 128;
+constexpr int TC_N = 80;
+constexpr int TC_CPAD = 72;
+constexpr int TC_TH = 8, TC_TW = 16;                 // output tile (rows x cols) = 128 pixels
+constexpr int TC_CHUNKS = 81;                        // real 16-byte K chunks: 9 taps x 9
+constexpr int TC_KBLOCKS = 11;                       // 128-byte swizzle atoms along K (last one: 2 chunks used)
+constexpr int TC_A_BYTES = TC_M * 128;               // 16384
+constexpr int TC_B_BYTES = TC_N * 128;               // 10240
+constexpr int TC_STAGES = 3;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4) * 32;
+constexpr int TC_TMEM_COLS = 256;                    // two accumulators at column 0 and 128
+constexpr int TC_ACC_STRIDE = 128;
 
-bool dcn_tc_available() { return false; }
-size_t dcn_tc_packed_weight_bytes() { return (size_t)TC_N * TC_K * 2; }
+bool dcn_tc_available() { return true; }
+size_t dcn_tc_packed_weight_bytes() { return (size_t)TC_KBLOCKS * TC_B_BYTES; }   // 112,640
+
+// workspace: [packed weight image | bias f32[80] (512 B) | packed input B*H*W*72 bf16]
+static size_t ws_bias_off() { return dcn_tc_packed_weight_bytes(); }
+static size_t ws_input_off() { return dcn_tc_packed_weight_bytes() + 512; }
 size_t dcn_tc_workspace_bytes(long long B, long long H, long long W) {
-  size_t w = ((dcn_tc_packed_weight_bytes() + 255) / 256) * 256;
-  size_t bias = 512;
   size_t xin = (((size_t)B * H * W * TC_CPAD * 2) + 255) / 256 * 256;
-  return w + bias + xin;
+  return ws_input_off() + xin;
 }
 
 namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// Bounded wait: a protocol bug traps (launch failure) after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (done) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor bits).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                        // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type 2 = SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major (cute::UMMA::InstrDescriptor bits).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ operand packers
 template <typename TW>
-__global__ void pack_weight_kernel(const TW* __restrict__ w, int O, int C, __nv_bfloat16* __restrict__ packed) {
+__global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, int bias_dtype, int O, int C,
+                                   uint8_t* __restrict__ packed, float* __restrict__ bias_out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= TC_N * TC_K) return;
-  int o = idx / TC_K, q = idx % TC_K;
-  int k = q / TC_CPAD, c = q % TC_CPAD;
-  float v = 0.0f;
-  if (o < O && k < 9 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + k]);
-  packed[idx] = __float2bfloat16_rn(v);
+  if (idx < TC_KBLOCKS * TC_N * 64) {
+    int kb = idx / (TC_N * 64), o = (idx / 64) % TC_N, kk = idx % 64;
+    int q = kb * 64 + kk, tap = q / TC_CPAD, c = q % TC_CPAD;
+    float v = 0.0f;
+    if (o < O && tap < 9 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + tap]);
+    size_t off = (size_t)kb * TC_B_BYTES + (size_t)o * 128 + ((((kk >> 3) ^ (o & 7))) << 4) + (kk & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+  }
+  if (bias_out && idx < TC_N) {
+    float bv = 0.0f;
+    if (bias && idx < O) {
+      if (bias_dtype == VFI_F32) bv = reinterpret_cast<const float*>(bias)[idx];
+      else if (bias_dtype == VFI_BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[idx]);
+      else bv = __half2float(reinterpret_cast<const __half*>(bias)[idx]);
+    }
+    bias_out[idx] = bv;
+  }
 }
 
 template <typename TX>
 __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long long sc, long long sh, long long sw, int B,
                                   int C, int H, int W, __nv_bfloat16* __restrict__ packed) {
-  // one thread per (pixel, 8-channel chunk); simple strided reads (v1), 16-byte writes
+  // one thread per (pixel, 8-channel chunk); lanes run over pixels so NCHW reads coalesce
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * W * (TC_CPAD / 8);
-  if (idx >= total) return;
-  int chunk = (int)(idx % (TC_CPAD / 8));
-  long long pix = idx / (TC_CPAD / 8);
+  long long npix = (long long)B * H * W;
+  if (idx >= npix * (TC_CPAD / 8)) return;
+  int chunk = (int)(idx / npix);
+  long long pix = idx % npix;
   int xx = (int)(pix % W);
   long long t = pix / W;
   int y = (int)(t % H);
@@ -51,26 +182,342 @@ __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long l
   }
   *reinterpret_cast<uint4*>(packed + pix * TC_CPAD + chunk * 8) = *reinterpret_cast<uint4*>(v);
 }
+
+// ------------------------------------------------------------------------------------------------ main kernel
+struct TcGeo {
+  int pix[4];      // flattened pixel index (b*H*W + y*W + x) of corners 00, 01, 10, 11, clamped into the image
+  float w[4];      // bilinear weight x modulation mask; 0 for corners outside the image / dead samples / padding rows
+};
+
+struct TcParams {
+  const __nv_bfloat16* x;          // [P][72]
+  const void* offset; const void* mask;
+  long long f_sn, f_sc, f_sh, f_sw;
+  long long m_sn, m_sc, m_sh, m_sw;
+  const uint8_t* wpacked;          // [11][80][128 B] swizzled
+  const float* bias;               // [80]
+  void* out;
+  long long o_sn, o_sc, o_sh, o_sw;
+  int out_packed;                  // 1: out is [P][72] bf16 (channel-padded channels-last), vector stores
+  int B, H, W, O;
+  int tiles_x, tiles_y, num_tiles;
+};
+
+struct __align__(1024) TcSmem {
+  uint8_t a[TC_STAGES][TC_A_BYTES];
+  uint8_t b[TC_STAGES][TC_B_BYTES];
+  TcGeo geo[9][TC_M];
+  float bias[TC_N];
+  unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
+  lo = __uint_as_float(v << 16);
+  hi = __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t lerp_pair(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const float* w) {
+  float al, ah, bl, bh, cl, ch, dl, dh;
+  unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch); unpack2(d, dl, dh);
+  float lo = fmaf(w[3], dl, fmaf(w[2], cl, fmaf(w[1], bl, w[0] * al)));
+  float hi = fmaf(w[3], dh, fmaf(w[2], ch, fmaf(w[1], bh, w[0] * ah)));
+  __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <typename TO>
+__device__ __forceinline__ TcGeo tc_make_geo(const TcParams& p, int b, int y, int x, int k) {
+  TcGeo g;
+  const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
+  const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
+  float dy = to_f32<TO>(__ldg(off + (2 * k) * p.f_sc));
+  float dx = to_f32<TO>(__ldg(off + (2 * k + 1) * p.f_sc));
+  float mk = to_f32<TO>(__ldg(msk + k * p.m_sc));
+  float py = (float)(y - 1 + k / 3) + dy;
+  float px = (float)(x - 1 + k % 3) + dx;
+  bool live = (py > -1.0f) && (py < (float)p.H) && (px > -1.0f) && (px < (float)p.W);
+  if (!live) { py = -2.0f; px = -2.0f; mk = 0.0f; }
+  float fy = floorf(py), fx = floorf(px);
+  int y0 = (int)fy, x0 = (int)fx;
+  float lh = py - fy, lw = px - fx, hh = 1.0f - lh, hw = 1.0f - lw;
+  bool r0 = (unsigned)y0 < (unsigned)p.H, r1 = (unsigned)(y0 + 1) < (unsigned)p.H;
+  bool c0 = (unsigned)x0 < (unsigned)p.W, c1 = (unsigned)(x0 + 1) < (unsigned)p.W;
+  int cy0 = min(max(y0, 0), p.H - 1), cy1 = min(max(y0 + 1, 0), p.H - 1);
+  int cx0 = min(max(x0, 0), p.W - 1), cx1 = min(max(x0 + 1, 0), p.W - 1);
+  int base = b * p.H * p.W;
+  g.pix[0] = base + cy0 * p.W + cx0; g.pix[1] = base + cy0 * p.W + cx1;
+  g.pix[2] = base + cy1 * p.W + cx0; g.pix[3] = base + cy1 * p.W + cx1;
+  g.w[0] = (r0 && c0) ? hh * hw * mk : 0.0f;
+  g.w[1] = (r0 && c1) ? hh * lw * mk : 0.0f;
+  g.w[2] = (r1 && c0) ? lh * hw * mk : 0.0f;
+  g.w[3] = (r1 && c1) ? lh * lw * mk : 0.0f;
+  return g;
+}
+
+// tile index -> (batch, top row, left column)
+__device__ __forceinline__ void tile_origin(const TcParams& p, int tile, int& b, int& y0, int& x0) {
+  int per_img = p.tiles_x * p.tiles_y;
+  b = tile / per_img;
+  int t = tile % per_img;
+  y0 = (t / p.tiles_x) * TC_TH;
+  x0 = (t % p.tiles_x) * TC_TW;
+}
+
+template <typename TO, typename TOUT>
+__global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(smem_u32(&s.full[i]), TC_PRODUCER_WARPS + 1);   // 8 warp arrivals + the expect_tx arrival of the B copy
+      mbar_init(smem_u32(&s.empty[i]), 1);                      // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
+      mbar_init(smem_u32(&s.acc_empty[i]), 4);                  // four epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
+  if (tid < TC_N) s.bias[tid] = p.bias[tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =========================================================================== A-operand producers
+    uint32_t stage = 0, phase = 0;
+    const int rsub = lane >> 3, j = lane & 7;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int b, ty0, tx0;
+      tile_origin(p, tile, b, ty0, tx0);
+      named_bar_sync(1, TC_PRODUCER_WARPS * 32);        // everyone is done reading the previous tile's geometry
+      for (int i = tid; i < 9 * TC_M; i += TC_PRODUCER_WARPS * 32) {
+        int k = i / TC_M, r = i % TC_M;
+        int y = ty0 + r / TC_TW, x = tx0 + r % TC_TW;
+        TcGeo g;
+        if (y < p.H && x < p.W) g = tc_make_geo<TO>(p, b, y, x, k);
+        else { g.pix[0] = g.pix[1] = g.pix[2] = g.pix[3] = 0; g.w[0] = g.w[1] = g.w[2] = g.w[3] = 0.0f; }
+        s.geo[k][r] = g;
+      }
+      named_bar_sync(1, TC_PRODUCER_WARPS * 32);
+      for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
+        mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(smem_u32(&s.full[stage]), TC_B_BYTES);
+          bulk_g2s(smem_u32(&s.b[stage][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, smem_u32(&s.full[stage]));
+        }
+        const int cq = kb * 8 + j;                      // global 16-byte chunk index along K
+        const bool real = cq < TC_CHUNKS;
+        const int tap = real ? cq / 9 : 0;
+        const int cc = real ? cq - tap * 9 : 0;
+        const bool need = cq < TC_CHUNKS + 1;           // chunk 81 is the explicit zero pad of the last UMMA_K step
+        uint4 v[4][4];
+        float wgt[4][4];
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+          const int r = (pass * TC_PRODUCER_WARPS + warp) * 4 + rsub;
+          if (real) {
+            const TcGeo g = s.geo[tap][r];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              wgt[pass][c] = g.w[c];
+              v[pass][c] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)g.pix[c] * TC_CPAD + cc * 8));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { wgt[pass][c] = 0.0f; v[pass][c] = make_uint4(0, 0, 0, 0); }
+          }
+        }
+        if (need) {
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int r = (pass * TC_PRODUCER_WARPS + warp) * 4 + rsub;
+            uint4 o;
+            o.x = lerp_pair(v[pass][0].x, v[pass][1].x, v[pass][2].x, v[pass][3].x, wgt[pass]);
+            o.y = lerp_pair(v[pass][0].y, v[pass][1].y, v[pass][2].y, v[pass][3].y, wgt[pass]);
+            o.z = lerp_pair(v[pass][0].z, v[pass][1].z, v[pass][2].z, v[pass][3].z, wgt[pass]);
+            o.w = lerp_pair(v[pass][0].w, v[pass][1].w, v[pass][2].w, v[pass][3].w, wgt[pass]);
+            *reinterpret_cast<uint4*>(&s.a[stage][r * 128 + ((j ^ (r & 7)) << 4)]) = o;
+          }
+        }
+        fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.full[stage]));
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == TC_PRODUCER_WARPS) {
+    // =========================================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase[2] = {0, 0};
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
+        for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
+          mbar_wait(smem_u32(&s.full[stage]), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[stage][0]));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[stage][0]));
+          const int nk = (kb == TC_KBLOCKS - 1) ? 1 : 4;
+          for (int k = 0; k < nk; ++k)                   // +32 B along K inside the 128 B swizzle atom = +2 encoded
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&s.empty[stage]));        // stage reusable once these MMAs have read it
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&s.acc_full[acc]));         // accumulator complete
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================== epilogue
+    const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
+    const int row = quad * 32 + lane;
+    uint32_t acc = 0, acc_phase[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int b, ty0, tx0;
+      tile_origin(p, tile, b, ty0, tx0);
+      mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
+      uint32_t d[TC_N];
+#pragma unroll
+      for (int c = 0; c < TC_N / 16; ++c) tmem_ld16(taddr + c * 16, d + c * 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+
+      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
+      if (y < p.H && x < p.W) {
+        if (p.out_packed) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ((size_t)(b * p.H + y) * p.W + x) * TC_CPAD;
+#pragma unroll
+          for (int c = 0; c < TC_CPAD / 8; ++c) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(d[c * 8 + 2 * i]) + s.bias[c * 8 + 2 * i],
+                                                       __uint_as_float(d[c * 8 + 2 * i + 1]) + s.bias[c * 8 + 2 * i + 1]);
+              w4[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o + c * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        } else {
+          TOUT* o = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
+#pragma unroll
+          for (int c = 0; c < TC_N; ++c)
+            if (c < p.O) o[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[c]) + s.bias[c]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ UMMA self test
+// D[128, 80] = A[128, K] * Bm[80, K]^T with A, Bm row-major bf16 in global memory, K a multiple of 64.  Uses exactly
+// the descriptor / swizzle / tcgen05 helpers of the kernel above, serialised (one stage, block barriers), so that a
+// wrong answer from the DCN kernel can be attributed either to the tensor-core plumbing or to the gather.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat16* __restrict__ A,
+                                                                const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
+                                                                int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  uint8_t* sa = base;                       // 16384
+  uint8_t* sb = base + TC_A_BYTES;          // 10240
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(base + TC_A_BYTES + TC_B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { mbar_init(smem_u32(bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+  uint32_t parity = 0;
+  for (int kb = 0; kb < K / 64; ++kb) {
+    for (int i = tid; i < TC_M * 8; i += 128) {
+      int r = i >> 3, jj = i & 7;
+      uint4 v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + kb * 64 + jj * 8);
+      *reinterpret_cast<uint4*>(sa + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
+    }
+    for (int i = tid; i < TC_N * 8; i += 128) {
+      int r = i >> 3, jj = i & 7;
+      uint4 v = *reinterpret_cast<const uint4*>(Bm + (size_t)r * K + kb * 64 + jj * 8);
+      *reinterpret_cast<uint4*>(sb + r * 128 + ((jj ^ (r & 7)) << 4)) = v;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_sw128(smem_u32(sa)), bdesc = umma_desc_sw128(smem_u32(sb));
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+      umma_commit(smem_u32(bar));
+    }
+    mbar_wait(smem_u32(bar), parity);
+    parity ^= 1;
+    tc_fence_after();
+    __syncthreads();
+  }
+  uint32_t d[TC_N];
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+  for (int c = 0; c < TC_N / 16; ++c) tmem_ld16(taddr + c * 16, d + c * 16);
+  tmem_ld_wait();
+  const int row = warp * 32 + lane;
+#pragma unroll
+  for (int c = 0; c < TC_N; ++c) D[row * TC_N + c] = __uint_as_float(d[c]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
+bool is_packed_nhwc72(const vfi_tensor* t) {
+  return t->dtype == VFI_BF16 && t->c <= TC_CPAD && t->sc == 1 && t->sw == TC_CPAD && t->sh == t->w * TC_CPAD &&
+         t->sn == t->h * t->w * TC_CPAD && aligned(t->data, 16);
+}
+
 }  // namespace
 
-int dcn_tc_pack_weight(const void* weight, int weight_dtype, long long O, long long C, void* packed, cudaStream_t st) {
+int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
+                       void* packed, float* bias_out, cudaStream_t st) {
   VFI_REQUIRE(weight && packed, VFI_ERR_INVALID, "vfi_dcn_pack_weight: null pointer");
   VFI_REQUIRE(O > 0 && O <= TC_N && C > 0 && C <= TC_CPAD, VFI_ERR_UNSUPPORTED,
-              "vfi_dcn_pack_weight: tensor-core path supports C <= %d, O <= %d", TC_CPAD, TC_N);
+              "vfi_dcn_pack_weight: tensor-core path supports C <= %d, O <= %d (got C=%lld, O=%lld)", TC_CPAD, TC_N, C, O);
+  VFI_REQUIRE(aligned(packed, 16), VFI_ERR_INVALID, "vfi_dcn_pack_weight: destination must be 16-byte aligned");
+  const int n = TC_KBLOCKS * TC_N * 64;
   VFI_DISPATCH(weight_dtype, TW, {
-    pack_weight_kernel<TW><<<ceil_div(TC_N * TC_K, 256), 256, 0, st>>>(reinterpret_cast<const TW*>(weight), (int)O, (int)C,
-                                                                       reinterpret_cast<__nv_bfloat16*>(packed));
+    pack_weight_kernel<TW><<<ceil_div(n, 256), 256, 0, st>>>(reinterpret_cast<const TW*>(weight), bias, bias_dtype, (int)O,
+                                                           (int)C, reinterpret_cast<uint8_t*>(packed), bias_out);
   });
   VFI_LAUNCH_CHECK("pack_weight_kernel");
   return VFI_OK;
 }
 
 int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st) {
-  VFI_REQUIRE(x && x->data && packed, VFI_ERR_INVALID, "vfi_dcn_pack_input: null pointer");
+  VFI_REQUIRE(x && packed, VFI_ERR_INVALID, "vfi_dcn_pack_input: null pointer");
   VFI_REQUIRE(x->c > 0 && x->c <= TC_CPAD, VFI_ERR_UNSUPPORTED, "vfi_dcn_pack_input: C must be <= %d", TC_CPAD);
   VFI_REQUIRE(aligned(packed, 16), VFI_ERR_INVALID, "vfi_dcn_pack_input: destination must be 16-byte aligned");
   long long total = (long long)x->n * x->h * x->w * (TC_CPAD / 8);
   if (total == 0) return VFI_OK;
+  VFI_REQUIRE(x->data, VFI_ERR_INVALID, "vfi_dcn_pack_input: null data pointer");
   VFI_DISPATCH(x->dtype, TX, {
     pack_input_kernel<TX><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const TX*>(x->data), x->sn, x->sc, x->sh,
                                                                x->sw, (int)x->n, (int)x->c, (int)x->h, (int)x->w,
@@ -80,10 +527,71 @@ int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st) {
   return VFI_OK;
 }
 
-int dcn_tc_fwd(const vfi_tensor*, const vfi_tensor*, const vfi_tensor*, const void*, int, const void*, int,
-               const vfi_tensor*, long long, void*, size_t, cudaStream_t) {
-  set_error("vfi_dcn_fwd: the tcgen05 path is not built into this library yet");
-  return VFI_ERR_UNSUPPORTED;
+int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight, int weight_dtype,
+               const void* bias, int bias_dtype, const vfi_tensor* out, long long O, void* workspace, size_t workspace_bytes,
+               cudaStream_t st) {
+  VFI_REQUIRE(x && offset && mask && out && weight, VFI_ERR_INVALID, "vfi_dcn_fwd: null argument");
+  VFI_REQUIRE(x->c <= TC_CPAD && O <= TC_N && O > 0 && x->c > 0, VFI_ERR_UNSUPPORTED,
+              "vfi_dcn_fwd(bf16_tc): supports C <= %d and O <= %d (got C=%lld, O=%lld)", TC_CPAD, TC_N, (long long)x->c, O);
+  VFI_REQUIRE(offset->n == x->n && offset->c == 18 && offset->h == x->h && offset->w == x->w, VFI_ERR_INVALID,
+              "vfi_dcn_fwd: offset must be [B,18,H,W]");
+  VFI_REQUIRE(mask->n == x->n && mask->c == 9 && mask->h == x->h && mask->w == x->w, VFI_ERR_INVALID,
+              "vfi_dcn_fwd: mask must be [B,9,H,W]");
+  VFI_REQUIRE(out->n == x->n && out->c == O && out->h == x->h && out->w == x->w, VFI_ERR_INVALID,
+              "vfi_dcn_fwd: out must be [B,O,H,W]");
+  VFI_REQUIRE(offset->dtype == mask->dtype, VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd: offset and mask must share a dtype");
+  const long long P = (long long)x->n * x->h * x->w;
+  if (P == 0) return VFI_OK;
+  VFI_REQUIRE(x->data && offset->data && mask->data && out->data, VFI_ERR_INVALID, "vfi_dcn_fwd: null data pointer");
+  VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd(bf16_tc): more than 2^30 pixels per call");
+  const bool x_packed = is_packed_nhwc72(x);
+  const size_t need = x_packed ? ws_input_off() : dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
+              "vfi_dcn_fwd(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", need, workspace_bytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* bias_ws = reinterpret_cast<float*>(ws + ws_bias_off());
+  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, x->c, ws, bias_ws, st);
+  if (rc) return rc;
+  const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(x->data);
+  if (!x_packed) {
+    rc = dcn_tc_pack_input(x, ws + ws_input_off(), st);
+    if (rc) return rc;
+    xin = reinterpret_cast<const __nv_bfloat16*>(ws + ws_input_off());
+  }
+  TcParams p;
+  p.x = xin; p.offset = offset->data; p.mask = mask->data;
+  p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
+  p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
+  p.wpacked = ws; p.bias = bias_ws; p.out = out->data;
+  p.o_sn = out->sn; p.o_sc = out->sc; p.o_sh = out->sh; p.o_sw = out->sw;
+  p.out_packed = is_packed_nhwc72(out) ? 1 : 0;
+  p.B = (int)x->n; p.H = (int)x->h; p.W = (int)x->w; p.O = (int)O;
+  p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
+  p.num_tiles = p.B * p.tiles_x * p.tiles_y;
+  int dev = 0, sms = 148;
+  VFI_CUDA(cudaGetDevice(&dev));
+  VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const size_t smem = sizeof(TcSmem) + 1024;
+  VFI_DISPATCH(offset->dtype, TO, {
+    VFI_DISPATCH(out->dtype, TOUT, {
+      auto kern = dcn_tc_fwd_kernel<TO, TOUT>;
+      VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, TC_THREADS, smem, st>>>(p);
+    });
+  });
+  VFI_LAUNCH_CHECK("dcn_tc_fwd_kernel");
+  return VFI_OK;
+}
+
+int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st) {
+  VFI_REQUIRE(A && Bm && D && K > 0 && K % 64 == 0, VFI_ERR_INVALID, "vfi_selftest_umma: need A, B, D and K %% 64 == 0");
+  const size_t smem = TC_A_BYTES + TC_B_BYTES + 64 + 1024;
+  VFI_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(A),
+                                             reinterpret_cast<const __nv_bfloat16*>(Bm), D, K);
+  VFI_LAUNCH_CHECK("umma_selftest_kernel");
+  return VFI_OK;
 }
 
 }  // namespace vfi

@@ -33,8 +33,18 @@ class HotPath:
     # ---------------------------------------------------------------------------------------------- device API
     def run(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor,
             convs27: Sequence[torch.Tensor]) -> torch.Tensor:
-        warped = ops.warp(frame2, flow)
-        x = torch.cat((feat, warped), dim=1)
+        if feat.dtype == torch.bfloat16 and self.math != "fp32" and feat.shape[1] + frame2.shape[1] <= ops.PACKED_C:
+            # tensor-core path: build the fused 67-channel activation directly in the channel-padded channels-last
+            # image the DCN kernel gathers from; the warp writes its 3 channels in place (no torch.cat, no layout pass)
+            B, C, H, W = feat.shape
+            xv = ops.packed_buffer(B, H, W, feat.device).permute(0, 3, 1, 2)
+            xv[:, :C].copy_(feat)
+            xv[:, C + frame2.shape[1]:].zero_()
+            ops.warp(frame2, flow, out=xv[:, C:C + frame2.shape[1]])
+            x = xv[:, :C + frame2.shape[1]]
+        else:
+            warped = ops.warp(frame2, flow)
+            x = torch.cat((feat, warped), dim=1)
         for w, b, c27 in zip(self.weights, self.biases, convs27):
             offset, mask = pack_split(c27)
             x = ops.deform_conv2d(x, offset, w, b, stride=1, padding=1, dilation=1, mask=mask, math=self.math)

@@ -30,14 +30,19 @@ def reset_launch_count() -> None:
 # ------------------------------------------------------------------------------------------------------ warp
 class _WarpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src: torch.Tensor, flow: torch.Tensor, flags: int = 0) -> torch.Tensor:
-        dev = require_cuda(src, flow)
+    def forward(ctx, src: torch.Tensor, flow: torch.Tensor, flags: int = 0, out=None) -> torch.Tensor:
+        dev = require_cuda(src, flow, out)
         ctx.flags = flags
         if src.dim() != 4 or flow.dim() != 4:
             raise ValueError("warp expects src [B,C,H,W] and flow [B,2,H,W]")
         if flow.dtype != torch.float32 and flow.dtype != src.dtype:
             flow = flow.float()
-        out = torch.empty_like(src)   # keeps src's memory format (NCHW or channels_last)
+        if out is None:
+            out = torch.empty_like(src)   # keeps src's memory format (NCHW or channels_last)
+        elif out.shape != src.shape or out.dtype != src.dtype:
+            raise ValueError("warp: out must have src's shape and dtype")
+        else:
+            ctx.mark_dirty(out)
         with torch.cuda.device(dev):
             check(_lib.load().vfi_warp_fwd(ref(desc(src)), ref(desc(flow)), ref(desc(out)), flags, stream_handle(dev)),
                   "vfi_warp_fwd")
@@ -57,13 +62,13 @@ class _WarpFn(torch.autograd.Function):
             check(_lib.load().vfi_warp_bwd(ref(desc(grad_out)), ref(desc(src)), ref(desc(flow)), ref(desc(gflow)),
                                            ref(desc(gsrc)) if gsrc is not None else None, ctx.flags,
                                            stream_handle(dev)), "vfi_warp_bwd")
-        return (gsrc.to(src.dtype) if need_src else None), (gflow.to(flow.dtype) if need_flow else None), None
+        return (gsrc.to(src.dtype) if need_src else None), (gflow.to(flow.dtype) if need_flow else None), None, None
 
 
 _DIVISION = {"ieee": _lib.WARP_DIV_IEEE, "reciprocal": _lib.WARP_DIV_RECIPROCAL}
 
 
-def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee") -> torch.Tensor:
+def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Backward-warp ``src`` [B,C,H,W] by ``flow`` [B,2,H,W] (pixels; channel 0 = x, 1 = y).
 
     Same result as the reference's grid build + normalise + ``F.grid_sample(bilinear, zeros,
@@ -72,8 +77,10 @@ def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee") -> torch
     ``division`` selects which bit-level meaning of the reference's ``2.0 * v / (size-1)`` is replayed: ``"ieee"``
     (what the reference computes on CPU -- BASELINE config 1 and the golden vectors) or ``"reciprocal"`` (what aten
     computes for ``tensor / python_scalar`` on CUDA: a multiplication by the fp32 reciprocal).
+    ``out`` (optional, any strides) receives the result in place -- e.g. channels 64..66 of the fused feature buffer,
+    which removes the ``torch.cat`` of ema_vfi.py:134.
     """
-    return _WarpFn.apply(src, flow, _DIVISION[division])
+    return _WarpFn.apply(src, flow, _DIVISION[division], out)
 
 
 def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch.Tensor:
@@ -93,6 +100,25 @@ def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch
 
 # ------------------------------------------------------------------------------------------------------ DCN
 _MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC}
+PACKED_C = 72   # channel stride of the tensor-core path's activation image
+
+
+def packed_buffer(B: int, H: int, W: int, device) -> torch.Tensor:
+    """Uninitialised [B,H,W,72] bf16 buffer.  ``buf.permute(0,3,1,2)[:, :C]`` is the logical NCHW view of a C-channel
+    activation in the layout the tcgen05 DCN kernel reads and writes directly (pad channels must be finite)."""
+    return torch.empty((B, H, W, PACKED_C), dtype=torch.bfloat16, device=device)
+
+
+def selftest_umma(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Diagnostic: D = a @ b.T for bf16 a [128,K], b [80,K] through the library's tcgen05 plumbing (one CTA)."""
+    dev = require_cuda(a, b)
+    assert a.dtype == b.dtype == torch.bfloat16 and a.shape[0] == 128 and b.shape[0] == 80 and a.shape[1] == b.shape[1]
+    a, b = a.contiguous(), b.contiguous()
+    d = torch.empty((128, 80), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().vfi_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[1], stream_handle(dev)),
+              "vfi_selftest_umma")
+    return d
 
 
 def dcn_workspace_bytes(B: int, C: int, O: int, H: int, W: int, math: str = "auto") -> int:
@@ -114,8 +140,14 @@ class _DcnFn(torch.autograd.Function):
             mask = mask.to(offset.dtype)
         weight_c = weight.contiguous()
         bias_c = None if bias is None else bias.contiguous()
-        out = torch.empty((B, O, H, W), dtype=x.dtype, device=dev)
         lib = _lib.load()
+        tc = math == _lib.MATH_BF16_TC or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
+        if tc and x.dtype == torch.bfloat16 and O <= PACKED_C:
+            # channel-padded channels-last bf16 [B,H,W,72]: what the next tensor-core layer gathers from without a
+            # layout pass; handed back as the logical [B,O,H,W] view (strides (H*W*72, 1, W*72, 72))
+            out = packed_buffer(B, H, W, dev).permute(0, 3, 1, 2)[:, :O]
+        else:
+            out = torch.empty((B, O, H, W), dtype=x.dtype, device=dev)
         nbytes = int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, math))
         ws = _workspace(dev, nbytes)
         with torch.cuda.device(dev):
