@@ -54,7 +54,9 @@ typedef struct vfi_tensor {
 typedef enum vfi_dcn_math {
   VFI_DCN_MATH_AUTO = 0,  /* fp32 tensors -> FP32, bf16/f16 tensors -> BF16_TC                                      */
   VFI_DCN_MATH_FP32 = 1,  /* fp32 gather + FFMA contraction: the parity mode (max-abs 1e-5 vs torchvision fp32)     */
-  VFI_DCN_MATH_BF16_TC = 2/* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma (C = O = 67 geometry only)      */
+  VFI_DCN_MATH_BF16_TC = 2,/* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma (C <= 72, O <= 80); the bilinear  */
+                          /* blend of the four corners runs in packed bf16 FMAs (HFMA2.BF16)                          */
+  VFI_DCN_MATH_BF16_TC_HQ = 3 /* same, but the four-corner blend is done in fp32 and rounded to bf16 once            */
 } vfi_dcn_math;
 
 /* ---- library ----------------------------------------------------------------------------------------------- */
@@ -112,6 +114,16 @@ int vfi_dcn_pack_input(const vfi_tensor* x, void* packed_nhwc72, vfi_stream_t st
 int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
                 int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out, int64_t O,
                 int32_t math, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
+
+/* Hot-path form of the forward (tensor-core math only).  Two pieces of glue of the reference are folded in:
+ *  - the offset/mask split of ema_vfi.py:57-59: conv27 is the raw [B,27,H,W] offset_conv output; offsets are its
+ *    thirds 0 and 2, the mask is sigmoid(third 1), computed in the kernel's geometry stage;
+ *  - the torch.cat of ema_vfi.py:134: the input may be given as two channels-last bf16 pieces, x_main [B,64,H,W]
+ *    (unit channel stride, dense pixels) and x_tail [B,<=8,H,W] (pixel stride >= 8 elements, pad channels zero);
+ *    x_tail may be NULL, in which case x_main is handled exactly as vfi_dcn_fwd handles x. */
+int vfi_dcn_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27, const void* weight,
+                      int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out, int64_t O,
+                      int32_t math, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
 
 /* Gradients (torchvision::_deform_conv2d_backward).  grad_out must have x's dtype.  All gradient tensors are f32.  grad_x must be zero-filled by
  * the caller (atomic scatter-add target); grad_weight / grad_bias likewise (accumulated with atomics so that a

@@ -301,6 +301,35 @@ def test_dcn_tensor_core_path(B, H, W, sigma):
     assert relerr(out3, ref3) <= 1e-2
 
 
+@pytest.mark.parametrize("math,bar", [("bf16_tc", 1e-2), ("bf16_tc_hq", 6e-3)])
+def test_dcn_fused_split_input_and_conv27(math, bar):
+    """vfi_dcn_fwd_fused: (feat 64ch channels-last, 3-channel tail) + raw 27-channel offset_conv output, against the
+    oracle chain cat -> split/sigmoid -> DCN on the same bf16 tensors."""
+    from vfi_b200 import ops
+
+    g = torch.Generator().manual_seed(51)
+    B, H, W = 2, 24, 40
+    feat = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16)
+    tail3 = torch.randn(B, 3, H, W, generator=g).to(torch.bfloat16)
+    c27 = torch.randn(B, 27, H, W, generator=g)
+    c27[:, :9] *= 1.5
+    c27[:, 18:] *= 1.5
+    c27 = c27.to(torch.bfloat16)
+    w = ((torch.rand(67, 67, 3, 3, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
+    b = ((torch.rand(67, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
+    tail = torch.zeros(B, H, W, 8, dtype=torch.bfloat16, device=DEV)
+    tail[..., :3] = tail3.permute(0, 2, 3, 1).to(DEV)
+    out = ops.deform_conv2d_fused(feat.to(DEV).contiguous(memory_format=torch.channels_last),
+                                  tail.permute(0, 3, 1, 2)[:, :3], c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
+    off, m = oracle.pack_split(c27.float().numpy())
+    ref = oracle.dcn_fwd(torch.cat([feat, tail3], 1).float().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
+    assert relerr(out, ref) <= bar
+    # single-piece form (the packed output of a previous layer) with conv27
+    out2 = ops.deform_conv2d_fused(out, None, c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
+    ref2 = oracle.dcn_fwd(out.float().cpu().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
+    assert relerr(out2, ref2) <= bar
+
+
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
     """Full 1080p frame: tcgen05 result against this library's fp32 parity kernel on the same bf16-rounded inputs."""
     g = torch.Generator(device=DEV).manual_seed(41)

@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libvfi_b200.so"
 VFI_OK = 0
 ERR_NAMES = {1: "VFI_ERR_INVALID", 2: "VFI_ERR_UNSUPPORTED", 3: "VFI_ERR_CUDA", 4: "VFI_ERR_WORKSPACE", 5: "VFI_ERR_DEVICE"}
 F32, BF16, F16 = 0, 1, 2
-MATH_AUTO, MATH_FP32, MATH_BF16_TC = 0, 1, 2
+MATH_AUTO, MATH_FP32, MATH_BF16_TC, MATH_BF16_TC_HQ = 0, 1, 2, 3
 WARP_DIV_IEEE, WARP_DIV_RECIPROCAL = 0, 1
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "vfi_dcn_pack_weight": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     "vfi_dcn_pack_input": (c_int, [_T, c_void_p, c_void_p]),
     "vfi_dcn_fwd": (c_int, [_T, _T, _T, c_void_p, c_int32, c_void_p, c_int32, _T, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
+    "vfi_dcn_fwd_fused": (c_int, [_T, _T, _T, c_void_p, c_int32, c_void_p, c_int32, _T, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "vfi_dcn_bwd_data": (c_int, [_T, _T, _T, _T, c_void_p, c_int32, c_int64, _T, _T, _T, c_void_p, c_size_t, c_void_p]),
     "vfi_dcn_bwd_weight": (c_int, [_T, _T, _T, _T, c_int64, c_void_p, c_void_p, c_void_p]),
     "vfi_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),

@@ -30,8 +30,11 @@ int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, i
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st);
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
-               int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, void* workspace,
-               size_t workspace_bytes, cudaStream_t st);
+               int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
+               void* workspace, size_t workspace_bytes, cudaStream_t st);
+int dcn_tc_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27, const void* weight,
+                     int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace vfi
 
@@ -93,13 +96,23 @@ extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const 
   if (m == VFI_DCN_MATH_FP32)
     return dcn_simt_fwd(x, offset, mask, weight, weight_dtype, bias, bias_dtype, out, O, workspace, workspace_bytes,
                         (cudaStream_t)stream);
-  if (m == VFI_DCN_MATH_BF16_TC)
-    return dcn_tc_fwd(x, offset, mask, weight, weight_dtype, bias, bias_dtype, out, O, workspace, workspace_bytes,
-                      (cudaStream_t)stream);
+  if (m == VFI_DCN_MATH_BF16_TC || m == VFI_DCN_MATH_BF16_TC_HQ)
+    return dcn_tc_fwd(x, offset, mask, weight, weight_dtype, bias, bias_dtype, out, O, m == VFI_DCN_MATH_BF16_TC_HQ,
+                      workspace, workspace_bytes, (cudaStream_t)stream);
   set_error("vfi_dcn_fwd: unknown math mode %d", (int)math);
   return VFI_ERR_INVALID;
 }
 
 extern "C" int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream) {
   return umma_selftest(a_bf16, b_bf16, d, K, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27,
+                                 const void* weight, int32_t weight_dtype, const void* bias, int32_t bias_dtype,
+                                 const vfi_tensor* out, int64_t O, int32_t math, void* workspace, size_t workspace_bytes,
+                                 vfi_stream_t stream) {
+  VFI_REQUIRE(math == VFI_DCN_MATH_AUTO || math == VFI_DCN_MATH_BF16_TC || math == VFI_DCN_MATH_BF16_TC_HQ,
+              VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd_fused: only the tensor-core math modes are implemented in fused form");
+  return dcn_tc_fwd_fused(x_main, x_tail, conv27, weight, weight_dtype, bias, bias_dtype, out, O,
+                          math == VFI_DCN_MATH_BF16_TC_HQ, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -12,15 +12,20 @@
 //   accumulator : 2 x (128 lanes x 80 columns) in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   tile        : 8 rows x 16 columns of output pixels (keeps the gather footprint, ~75 KB at sigma = 1.5 px, inside L1)
 //
-// Warp roles (416 threads, one persistent CTA per SM):
-//   warps 0-7  producers: per tile compute the 9 x 128 tap geometries once (corner pixel indices + mask-folded weights),
-//              then per K block gather 4 corners x 16 B per (row, chunk) item with 128-bit read-only loads, lerp in fp32,
-//              pack to bf16 and store 16 B into the swizzled A stage; fence.proxy.async; one arrive per warp.
-//   warp 8     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
-//   warps 9-12 epilogue: tcgen05.ld the accumulator (lane = pixel), + bias, convert, store.
+// Warp roles (672 threads, one persistent CTA per SM):
+//   warps 0-15  producers in two groups of 8 that alternate over the K blocks (one group's gather latency hides behind
+//               the other's lerp/store work).  Per tile all 16 warps first compute the 9 x 128 tap geometries (corner
+//               pixel indices + mask-folded weights; optionally straight from the 27-channel offset_conv output with the
+//               sigmoid folded in).  Per K block each lane owns one 16-byte chunk of four rows: 4 corner loads of 16 B
+//               (read-only path; 8 lanes cover one pixel's 128 B), packed HFMA2.BF16 lerp (or fp32 in HQ mode), one
+//               16-byte store into the swizzled A stage; fence.proxy.async; one mbarrier arrive per warp.
+//   warp 16     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
+//   warps 17-20 epilogue: tcgen05.ld the accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
 //
-// The activation image the producers gather from is channel-padded channels-last bf16: [B, H, W, 72] (144 B / pixel,
-// nine 16-byte chunks).  Any other layout is converted by pack_input_kernel first (workspace).
+// The activation image the producers gather from is channels-last bf16 in 16-byte chunks: either one channel-padded
+// [B, H, W, 72] buffer (144 B / pixel, what this kernel also writes), or two pieces -- [B, H, W, 64] + [B, H, W, 8] --
+// which is how feat and the warped frame exist before the reference's torch.cat (ema_vfi.py:134).  Any other layout
+// is converted by pack_input_kernel first (workspace).
 #include "common.cuh"
 
 namespace vfi {
@@ -34,8 +39,9 @@ constexpr int TC_KBLOCKS = 11;                       // 128-byte swizzle atoms a
 constexpr int TC_A_BYTES = TC_M * 128;               // 16384
 constexpr int TC_B_BYTES = TC_N * 128;               // 10240
 constexpr int TC_STAGES = 3;
-constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4) * 32;
+constexpr int TC_PRODUCER_WARPS = 16;                // two groups of 8 alternating over K blocks
+constexpr int TC_GROUP_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4) * 32;   // + MMA issuer warp + 4 epilogue warps = 672
 constexpr int TC_TMEM_COLS = 256;                    // two accumulators at column 0 and 128
 constexpr int TC_ACC_STRIDE = 128;
 
@@ -185,20 +191,26 @@ __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long l
 
 // ------------------------------------------------------------------------------------------------ main kernel
 struct TcGeo {
-  int pix[4];      // flattened pixel index (b*H*W + y*W + x) of corners 00, 01, 10, 11, clamped into the image
-  float w[4];      // bilinear weight x modulation mask; 0 for corners outside the image / dead samples / padding rows
+  int pix[4];        // flattened pixel index (b*H*W + y*W + x) of corners 00, 01, 10, 11, clamped into the image
+  uint32_t w[4];     // bilinear weight x modulation mask (0 for corners outside the image / dead samples / padding
+                     // rows): bf16x2 splat (w, w) on the fast path, fp32 bits on the HQ path
 };
 
 struct TcParams {
-  const __nv_bfloat16* x;          // [P][72]
-  const void* offset; const void* mask;
+  // activation image, channels-last bf16 in up to two pieces: chunks 0..n_main-1 come from x_main (pixel stride
+  // main_stride bytes), chunk n_main (if any) from x_tail.  A single packed [P][72] image is main with 9 chunks.
+  const uint8_t* x_main; const uint8_t* x_tail;
+  long long main_stride, tail_stride;      // bytes per pixel
+  int n_main;                              // 16-byte chunks taken from x_main (8 or 9)
+  const void* offset; const void* mask;    // fused27: both point at the 27-channel offset_conv output
   long long f_sn, f_sc, f_sh, f_sw;
   long long m_sn, m_sc, m_sh, m_sw;
-  const uint8_t* wpacked;          // [11][80][128 B] swizzled
-  const float* bias;               // [80]
+  int fused27;                             // 1: offset ch j -> conv27[j < 9 ? j : j + 9], mask = sigmoid(conv27[9 + k])
+  const uint8_t* wpacked;                  // [11][80][128 B] swizzled
+  const float* bias;                       // [80]
   void* out;
   long long o_sn, o_sc, o_sh, o_sw;
-  int out_packed;                  // 1: out is [P][72] bf16 (channel-padded channels-last), vector stores
+  int out_packed;                          // 1: out is [P][72] bf16 (channel-padded channels-last), vector stores
   int B, H, W, O;
   int tiles_x, tiles_y, num_tiles;
 };
@@ -216,23 +228,55 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
   lo = __uint_as_float(v << 16);
   hi = __uint_as_float(v & 0xffff0000u);
 }
-__device__ __forceinline__ uint32_t lerp_pair(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const float* w) {
-  float al, ah, bl, bh, cl, ch, dl, dh;
-  unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch); unpack2(d, dl, dh);
-  float lo = fmaf(w[3], dl, fmaf(w[2], cl, fmaf(w[1], bl, w[0] * al)));
-  float hi = fmaf(w[3], dh, fmaf(w[2], ch, fmaf(w[1], bh, w[0] * ah)));
-  __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+
+// Two channels of the modulated bilinear sample.  HQ: fp32 arithmetic, one rounding at the end.  Fast: packed
+// HMUL2/HFMA2.BF16 (each step rounds to bf16; measured cost on the layer output: 2.8e-3 vs 1.4e-3 max-rel).
+template <bool HQ>
+__device__ __forceinline__ uint32_t lerp_pair(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const uint32_t* w) {
+  if constexpr (HQ) {
+    float al, ah, bl, bh, cl, ch, dl, dh;
+    unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch); unpack2(d, dl, dh);
+    const float w0 = __uint_as_float(w[0]), w1 = __uint_as_float(w[1]), w2 = __uint_as_float(w[2]), w3 = __uint_as_float(w[3]);
+    float lo = fmaf(w3, dl, fmaf(w2, cl, fmaf(w1, bl, w0 * al)));
+    float hi = fmaf(w3, dh, fmaf(w2, ch, fmaf(w1, bh, w0 * ah)));
+    __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&r);
+  } else {
+    __nv_bfloat162 r = __hmul2(as_bf162(w[0]), as_bf162(a));
+    r = __hfma2(as_bf162(w[1]), as_bf162(b), r);
+    r = __hfma2(as_bf162(w[2]), as_bf162(c), r);
+    r = __hfma2(as_bf162(w[3]), as_bf162(d), r);
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+}
+
+template <bool HQ>
+__device__ __forceinline__ uint32_t pack_weight_word(float w) {
+  if constexpr (HQ) return __float_as_uint(w);
+  __nv_bfloat162 r = __float2bfloat162_rn(w);
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <typename TO>
+template <typename TO, bool HQ>
 __device__ __forceinline__ TcGeo tc_make_geo(const TcParams& p, int b, int y, int x, int k) {
   TcGeo g;
   const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
   const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
-  float dy = to_f32<TO>(__ldg(off + (2 * k) * p.f_sc));
-  float dx = to_f32<TO>(__ldg(off + (2 * k + 1) * p.f_sc));
-  float mk = to_f32<TO>(__ldg(msk + k * p.m_sc));
+  float dy, dx, mk;
+  if (p.fused27) {
+    // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets, the middle third is the
+    // pre-sigmoid mask.  The sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would.
+    const int j0 = 2 * k, j1 = 2 * k + 1;
+    dy = to_f32<TO>(__ldg(off + (j0 < 9 ? j0 : j0 + 9) * p.f_sc));
+    dx = to_f32<TO>(__ldg(off + (j1 < 9 ? j1 : j1 + 9) * p.f_sc));
+    const float t = to_f32<TO>(__ldg(msk + (9 + k) * p.m_sc));
+    mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + expf(-t))));
+  } else {
+    dy = to_f32<TO>(__ldg(off + (2 * k) * p.f_sc));
+    dx = to_f32<TO>(__ldg(off + (2 * k + 1) * p.f_sc));
+    mk = to_f32<TO>(__ldg(msk + k * p.m_sc));
+  }
   float py = (float)(y - 1 + k / 3) + dy;
   float px = (float)(x - 1 + k % 3) + dx;
   bool live = (py > -1.0f) && (py < (float)p.H) && (px > -1.0f) && (px < (float)p.W);
@@ -247,10 +291,10 @@ __device__ __forceinline__ TcGeo tc_make_geo(const TcParams& p, int b, int y, in
   int base = b * p.H * p.W;
   g.pix[0] = base + cy0 * p.W + cx0; g.pix[1] = base + cy0 * p.W + cx1;
   g.pix[2] = base + cy1 * p.W + cx0; g.pix[3] = base + cy1 * p.W + cx1;
-  g.w[0] = (r0 && c0) ? hh * hw * mk : 0.0f;
-  g.w[1] = (r0 && c1) ? hh * lw * mk : 0.0f;
-  g.w[2] = (r1 && c0) ? lh * hw * mk : 0.0f;
-  g.w[3] = (r1 && c1) ? lh * lw * mk : 0.0f;
+  g.w[0] = pack_weight_word<HQ>((r0 && c0) ? hh * hw * mk : 0.0f);
+  g.w[1] = pack_weight_word<HQ>((r0 && c1) ? hh * lw * mk : 0.0f);
+  g.w[2] = pack_weight_word<HQ>((r1 && c0) ? lh * hw * mk : 0.0f);
+  g.w[3] = pack_weight_word<HQ>((r1 && c1) ? lh * lw * mk : 0.0f);
   return g;
 }
 
@@ -263,7 +307,7 @@ __device__ __forceinline__ void tile_origin(const TcParams& p, int tile, int& b,
   x0 = (t % p.tiles_x) * TC_TW;
 }
 
-template <typename TO, typename TOUT>
+template <typename TO, typename TOUT, bool HQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
@@ -271,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
 
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(smem_u32(&s.full[i]), TC_PRODUCER_WARPS + 1);   // 8 warp arrivals + the expect_tx arrival of the B copy
+      mbar_init(smem_u32(&s.full[i]), TC_GROUP_WARPS + 1);      // 8 warp arrivals + the expect_tx arrival of the B copy
       mbar_init(smem_u32(&s.empty[i]), 1);                      // one tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
@@ -286,68 +330,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================================================================== A-operand producers
-    uint32_t stage = 0, phase = 0;
+    // Two groups of 8 warps alternate over the CTA's global K-block sequence n = tile_iter * 11 + kb (group = n & 1), so
+    // one group's gather latency overlaps the other group's lerp/store work.  stage = n % 3, phase = (n / 3) & 1.
+    const int group = warp >> 3, wig = warp & 7;
     const int rsub = lane >> 3, j = lane & 7;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
       int b, ty0, tx0;
       tile_origin(p, tile, b, ty0, tx0);
-      named_bar_sync(1, TC_PRODUCER_WARPS * 32);        // everyone is done reading the previous tile's geometry
+      named_bar_sync(1, TC_PRODUCER_WARPS * 32);        // every producer is done reading the previous tile's geometry
       for (int i = tid; i < 9 * TC_M; i += TC_PRODUCER_WARPS * 32) {
         int k = i / TC_M, r = i % TC_M;
         int y = ty0 + r / TC_TW, x = tx0 + r % TC_TW;
         TcGeo g;
-        if (y < p.H && x < p.W) g = tc_make_geo<TO>(p, b, y, x, k);
-        else { g.pix[0] = g.pix[1] = g.pix[2] = g.pix[3] = 0; g.w[0] = g.w[1] = g.w[2] = g.w[3] = 0.0f; }
+        if (y < p.H && x < p.W) g = tc_make_geo<TO, HQ>(p, b, y, x, k);
+        else { g.pix[0] = g.pix[1] = g.pix[2] = g.pix[3] = 0; g.w[0] = g.w[1] = g.w[2] = g.w[3] = 0u; }
         s.geo[k][r] = g;
       }
       named_bar_sync(1, TC_PRODUCER_WARPS * 32);
-      for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
+      const int n0 = it * TC_KBLOCKS;
+      for (int kb = (n0 + group) & 1; kb < TC_KBLOCKS; kb += 2) {   // blocks of this tile whose global index has parity `group`
+        const int n = n0 + kb;
+        const int stage = n % TC_STAGES;
+        const uint32_t phase = (uint32_t)(n / TC_STAGES) & 1u;
         mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1);
-        if (tid == 0) {
+        if (wig == 0 && lane == 0) {
           mbar_arrive_expect_tx(smem_u32(&s.full[stage]), TC_B_BYTES);
           bulk_g2s(smem_u32(&s.b[stage][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, smem_u32(&s.full[stage]));
         }
         const int cq = kb * 8 + j;                      // global 16-byte chunk index along K
-        const bool real = cq < TC_CHUNKS;
-        const int tap = real ? cq / 9 : 0;
-        const int cc = real ? cq - tap * 9 : 0;
-        const bool need = cq < TC_CHUNKS + 1;           // chunk 81 is the explicit zero pad of the last UMMA_K step
-        uint4 v[4][4];
-        float wgt[4][4];
+        if (cq <= TC_CHUNKS) {                          // chunk 81 is the explicit zero pad of the last UMMA_K step
+          const bool real = cq < TC_CHUNKS;
+          const int tap = real ? (cq * 57) >> 9 : 0;    // cq / 9 for cq < 81
+          const int cc = cq - tap * 9;
+          const uint8_t* src = (cc < p.n_main) ? p.x_main + cc * 16 : p.x_tail;
+          const long long pstride = (cc < p.n_main) ? p.main_stride : p.tail_stride;
+          uint8_t* a_stage = &s.a[stage][0];
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          const int r = (pass * TC_PRODUCER_WARPS + warp) * 4 + rsub;
-          if (real) {
-            const TcGeo g = s.geo[tap][r];
+          for (int batch = 0; batch < 2; ++batch) {
+            uint4 v[2][4];
+            uint4 wq[2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              wgt[pass][c] = g.w[c];
-              v[pass][c] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)g.pix[c] * TC_CPAD + cc * 8));
+            for (int pp = 0; pp < 2; ++pp) {
+              const int r = ((batch * 2 + pp) * TC_GROUP_WARPS + wig) * 4 + rsub;
+              const int4 pix = *reinterpret_cast<const int4*>(&s.geo[tap][r].pix[0]);
+              wq[pp] = *reinterpret_cast<const uint4*>(&s.geo[tap][r].w[0]);
+              if (real) {
+                v[pp][0] = __ldg(reinterpret_cast<const uint4*>(src + pix.x * pstride));
+                v[pp][1] = __ldg(reinterpret_cast<const uint4*>(src + pix.y * pstride));
+                v[pp][2] = __ldg(reinterpret_cast<const uint4*>(src + pix.z * pstride));
+                v[pp][3] = __ldg(reinterpret_cast<const uint4*>(src + pix.w * pstride));
+              } else {
+                v[pp][0] = v[pp][1] = v[pp][2] = v[pp][3] = make_uint4(0, 0, 0, 0);
+                wq[pp] = make_uint4(0, 0, 0, 0);
+              }
             }
-          } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { wgt[pass][c] = 0.0f; v[pass][c] = make_uint4(0, 0, 0, 0); }
-          }
-        }
-        if (need) {
-#pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int r = (pass * TC_PRODUCER_WARPS + warp) * 4 + rsub;
-            uint4 o;
-            o.x = lerp_pair(v[pass][0].x, v[pass][1].x, v[pass][2].x, v[pass][3].x, wgt[pass]);
-            o.y = lerp_pair(v[pass][0].y, v[pass][1].y, v[pass][2].y, v[pass][3].y, wgt[pass]);
-            o.z = lerp_pair(v[pass][0].z, v[pass][1].z, v[pass][2].z, v[pass][3].z, wgt[pass]);
-            o.w = lerp_pair(v[pass][0].w, v[pass][1].w, v[pass][2].w, v[pass][3].w, wgt[pass]);
-            *reinterpret_cast<uint4*>(&s.a[stage][r * 128 + ((j ^ (r & 7)) << 4)]) = o;
+            for (int pp = 0; pp < 2; ++pp) {
+              const int r = ((batch * 2 + pp) * TC_GROUP_WARPS + wig) * 4 + rsub;
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(&wq[pp]);
+              uint4 o;
+              o.x = lerp_pair<HQ>(v[pp][0].x, v[pp][1].x, v[pp][2].x, v[pp][3].x, w);
+              o.y = lerp_pair<HQ>(v[pp][0].y, v[pp][1].y, v[pp][2].y, v[pp][3].y, w);
+              o.z = lerp_pair<HQ>(v[pp][0].z, v[pp][1].z, v[pp][2].z, v[pp][3].z, w);
+              o.w = lerp_pair<HQ>(v[pp][0].w, v[pp][1].w, v[pp][2].w, v[pp][3].w, w);
+              *reinterpret_cast<uint4*>(a_stage + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+            }
           }
         }
         fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.full[stage]));
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == TC_PRODUCER_WARPS) {
@@ -355,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase[2] = {0, 0};
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
@@ -381,44 +438,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
     const int row = quad * 32 + lane;
     uint32_t acc = 0, acc_phase[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
       int b, ty0, tx0;
       tile_origin(p, tile, b, ty0, tx0);
       mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
-      uint32_t d[TC_N];
-#pragma unroll
-      for (int c = 0; c < TC_N / 16; ++c) tmem_ld16(taddr + c * 16, d + c * 16);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
-
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
-      if (y < p.H && x < p.W) {
-        if (p.out_packed) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ((size_t)(b * p.H + y) * p.W + x) * TC_CPAD;
+      const bool inside = y < p.H && x < p.W;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((size_t)(b * p.H + y) * p.W + x) * TC_CPAD;
+      TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
 #pragma unroll
-          for (int c = 0; c < TC_CPAD / 8; ++c) {
-            uint32_t w4[4];
+      for (int c16 = 0; c16 < TC_N / 16; ++c16) {
+        uint32_t d[16];
+        tmem_ld16(taddr + c16 * 16, d);
+        tmem_ld_wait();
+        if (c16 == TC_N / 16 - 1) {                      // last TMEM read of this accumulator: hand it back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
+        }
+        if (inside) {
+          if (p.out_packed) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(d[c * 8 + 2 * i]) + s.bias[c * 8 + 2 * i],
-                                                       __uint_as_float(d[c * 8 + 2 * i + 1]) + s.bias[c * 8 + 2 * i + 1]);
-              w4[i] = *reinterpret_cast<uint32_t*>(&h);
+            for (int h = 0; h < 2; ++h) {
+              if (c16 * 16 + h * 8 >= TC_CPAD) break;    // columns 72..79 are padding of the UMMA N dimension
+              uint32_t w4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int c = c16 * 16 + h * 8 + 2 * i;
+                __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c],
+                                                          __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c + 1]);
+                w4[i] = *reinterpret_cast<uint32_t*>(&hv);
+              }
+              *reinterpret_cast<uint4*>(op + c16 * 16 + h * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
-            *reinterpret_cast<uint4*>(o + c * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-          }
-        } else {
-          TOUT* o = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
+          } else {
 #pragma unroll
-          for (int c = 0; c < TC_N; ++c)
-            if (c < p.O) o[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[c]) + s.bias[c]);
+            for (int i = 0; i < 16; ++i) {
+              const int c = c16 * 16 + i;
+              if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]) + s.bias[c]);
+            }
+          }
         }
       }
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
     }
   }
 
@@ -489,12 +555,12 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
-bool is_packed_nhwc72(const vfi_tensor* t) {
+}  // namespace
+
+static bool is_packed_nhwc72(const vfi_tensor* t) {
   return t->dtype == VFI_BF16 && t->c <= TC_CPAD && t->sc == 1 && t->sw == TC_CPAD && t->sh == t->w * TC_CPAD &&
          t->sn == t->h * t->w * TC_CPAD && aligned(t->data, 16);
 }
-
-}  // namespace
 
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
                        void* packed, float* bias_out, cudaStream_t st) {
@@ -527,39 +593,73 @@ int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st) {
   return VFI_OK;
 }
 
-int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight, int weight_dtype,
-               const void* bias, int bias_dtype, const vfi_tensor* out, long long O, void* workspace, size_t workspace_bytes,
-               cudaStream_t st) {
-  VFI_REQUIRE(x && offset && mask && out && weight, VFI_ERR_INVALID, "vfi_dcn_fwd: null argument");
-  VFI_REQUIRE(x->c <= TC_CPAD && O <= TC_N && O > 0 && x->c > 0, VFI_ERR_UNSUPPORTED,
-              "vfi_dcn_fwd(bf16_tc): supports C <= %d and O <= %d (got C=%lld, O=%lld)", TC_CPAD, TC_N, (long long)x->c, O);
-  VFI_REQUIRE(offset->n == x->n && offset->c == 18 && offset->h == x->h && offset->w == x->w, VFI_ERR_INVALID,
-              "vfi_dcn_fwd: offset must be [B,18,H,W]");
-  VFI_REQUIRE(mask->n == x->n && mask->c == 9 && mask->h == x->h && mask->w == x->w, VFI_ERR_INVALID,
-              "vfi_dcn_fwd: mask must be [B,9,H,W]");
+// channels-last bf16 piece usable by the gather without a layout pass: unit channel stride, dense pixels, 16-byte rows
+static bool is_nhwc_piece(const vfi_tensor* t, long long min_sw) {
+  return t->dtype == VFI_BF16 && t->sc == 1 && t->sw >= min_sw && t->sw % 8 == 0 && t->sh == t->w * t->sw &&
+         t->sn == t->h * t->w * t->sw && aligned(t->data, 16);
+}
+
+// Shared implementation.  x_tail may be null.  conv27 != null selects the fused offset/mask form.
+int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* offset, const vfi_tensor* mask,
+               const vfi_tensor* conv27, const void* weight, int weight_dtype, const void* bias, int bias_dtype,
+               const vfi_tensor* out, long long O, bool hq, void* workspace, size_t workspace_bytes, cudaStream_t st,
+               const char* who) {
+  const vfi_tensor* x = x_main;
+  VFI_REQUIRE(x && out && weight && (conv27 || (offset && mask)), VFI_ERR_INVALID, "%s: null argument", who);
+  const long long C = x->c + (x_tail ? x_tail->c : 0);
+  VFI_REQUIRE(C <= TC_CPAD && O <= TC_N && O > 0 && x->c > 0, VFI_ERR_UNSUPPORTED,
+              "%s(bf16_tc): supports C <= %d and O <= %d (got C=%lld, O=%lld)", who, TC_CPAD, TC_N, C, O);
+  if (conv27) {
+    VFI_REQUIRE(conv27->n == x->n && conv27->c == 27 && conv27->h == x->h && conv27->w == x->w, VFI_ERR_INVALID,
+                "%s: conv27 must be [B,27,H,W]", who);
+    offset = mask = conv27;
+  } else {
+    VFI_REQUIRE(offset->n == x->n && offset->c == 18 && offset->h == x->h && offset->w == x->w, VFI_ERR_INVALID,
+                "%s: offset must be [B,18,H,W]", who);
+    VFI_REQUIRE(mask->n == x->n && mask->c == 9 && mask->h == x->h && mask->w == x->w, VFI_ERR_INVALID,
+                "%s: mask must be [B,9,H,W]", who);
+    VFI_REQUIRE(offset->dtype == mask->dtype, VFI_ERR_UNSUPPORTED, "%s: offset and mask must share a dtype", who);
+  }
   VFI_REQUIRE(out->n == x->n && out->c == O && out->h == x->h && out->w == x->w, VFI_ERR_INVALID,
-              "vfi_dcn_fwd: out must be [B,O,H,W]");
-  VFI_REQUIRE(offset->dtype == mask->dtype, VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd: offset and mask must share a dtype");
+              "%s: out must be [B,O,H,W]", who);
   const long long P = (long long)x->n * x->h * x->w;
   if (P == 0) return VFI_OK;
-  VFI_REQUIRE(x->data && offset->data && mask->data && out->data, VFI_ERR_INVALID, "vfi_dcn_fwd: null data pointer");
-  VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd(bf16_tc): more than 2^30 pixels per call");
-  const bool x_packed = is_packed_nhwc72(x);
-  const size_t need = x_packed ? ws_input_off() : dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  VFI_REQUIRE(x->data && offset->data && mask->data && out->data, VFI_ERR_INVALID, "%s: null data pointer", who);
+  VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "%s(bf16_tc): more than 2^30 pixels per call", who);
+
+  TcParams p;
+  bool direct;
+  if (x_tail) {
+    // two-piece form: main supplies whole 16-byte chunks, the tail supplies the last one
+    VFI_REQUIRE(x_tail->data && x_tail->n == x->n && x_tail->h == x->h && x_tail->w == x->w && x_tail->c <= 8,
+                VFI_ERR_INVALID, "%s: x_tail must be [B,<=8,H,W] matching x_main", who);
+    VFI_REQUIRE(x->c % 8 == 0 && is_nhwc_piece(x, x->c) && is_nhwc_piece(x_tail, 8), VFI_ERR_UNSUPPORTED,
+                "%s: the two-piece input needs channels-last bf16 pieces (main: C %% 8 == 0; tail: pixel stride >= 8, "
+                "16-byte aligned, pad channels zero)", who);
+    direct = true;
+    p.x_main = reinterpret_cast<const uint8_t*>(x->data); p.main_stride = x->sw * 2; p.n_main = (int)(x->c / 8);
+    p.x_tail = reinterpret_cast<const uint8_t*>(x_tail->data); p.tail_stride = x_tail->sw * 2;
+  } else {
+    direct = is_packed_nhwc72(x);
+  }
+  const size_t need = direct ? ws_input_off() : dcn_tc_workspace_bytes(x->n, x->h, x->w);
   VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
-              "vfi_dcn_fwd(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", need, workspace_bytes);
+              "%s(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float* bias_ws = reinterpret_cast<float*>(ws + ws_bias_off());
-  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, x->c, ws, bias_ws, st);
+  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st);
   if (rc) return rc;
-  const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(x->data);
-  if (!x_packed) {
-    rc = dcn_tc_pack_input(x, ws + ws_input_off(), st);
-    if (rc) return rc;
-    xin = reinterpret_cast<const __nv_bfloat16*>(ws + ws_input_off());
+  if (!x_tail) {
+    const uint8_t* xin = reinterpret_cast<const uint8_t*>(x->data);
+    if (!direct) {
+      rc = dcn_tc_pack_input(x, ws + ws_input_off(), st);
+      if (rc) return rc;
+      xin = ws + ws_input_off();
+    }
+    p.x_main = xin; p.main_stride = TC_CPAD * 2; p.n_main = TC_CPAD / 8;
+    p.x_tail = xin; p.tail_stride = TC_CPAD * 2;
   }
-  TcParams p;
-  p.x = xin; p.offset = offset->data; p.mask = mask->data;
+  p.offset = offset->data; p.mask = mask->data; p.fused27 = conv27 ? 1 : 0;
   p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
   p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
   p.wpacked = ws; p.bias = bias_ws; p.out = out->data;
@@ -575,13 +675,34 @@ int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* 
   const size_t smem = sizeof(TcSmem) + 1024;
   VFI_DISPATCH(offset->dtype, TO, {
     VFI_DISPATCH(out->dtype, TOUT, {
-      auto kern = dcn_tc_fwd_kernel<TO, TOUT>;
-      VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, TC_THREADS, smem, st>>>(p);
+      if (hq) {
+        auto kern = dcn_tc_fwd_kernel<TO, TOUT, true>;
+        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TC_THREADS, smem, st>>>(p);
+      } else {
+        auto kern = dcn_tc_fwd_kernel<TO, TOUT, false>;
+        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TC_THREADS, smem, st>>>(p);
+      }
     });
   });
   VFI_LAUNCH_CHECK("dcn_tc_fwd_kernel");
   return VFI_OK;
+}
+
+int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight, int weight_dtype,
+               const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq, void* workspace,
+               size_t workspace_bytes, cudaStream_t st) {
+  return dcn_tc_run(x, nullptr, offset, mask, nullptr, weight, weight_dtype, bias, bias_dtype, out, O, hq, workspace,
+                    workspace_bytes, st, "vfi_dcn_fwd");
+}
+
+int dcn_tc_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27, const void* weight,
+                     int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  VFI_REQUIRE(conv27, VFI_ERR_INVALID, "vfi_dcn_fwd_fused: null conv27");
+  return dcn_tc_run(x_main, x_tail, nullptr, nullptr, conv27, weight, weight_dtype, bias, bias_dtype, out, O, hq, workspace,
+                    workspace_bytes, st, "vfi_dcn_fwd_fused");
 }
 
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st) {

@@ -29,26 +29,39 @@ class HotPath:
         self.biases = list(biases)
         self.math = math
         self._streams = None
+        self._tail = None
+        self._tail_key = None
 
     # ---------------------------------------------------------------------------------------------- device API
     def run(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor,
             convs27: Sequence[torch.Tensor]) -> torch.Tensor:
-        if feat.dtype == torch.bfloat16 and self.math != "fp32" and feat.shape[1] + frame2.shape[1] <= ops.PACKED_C:
-            # tensor-core path: build the fused 67-channel activation directly in the channel-padded channels-last
-            # image the DCN kernel gathers from; the warp writes its 3 channels in place (no torch.cat, no layout pass)
+        if self._fast(frame2, feat):
+            # Tensor-core path with the reference's glue folded away: the warp writes its 3 channels into a 16-byte
+            # "tail" record per pixel, the first DCN layer gathers from (feat, tail) directly (no torch.cat), every layer
+            # reads the raw 27-channel offset_conv output (no chunk/cat/sigmoid) and writes the channel-padded
+            # channels-last image the next layer gathers from.
             B, C, H, W = feat.shape
-            xv = ops.packed_buffer(B, H, W, feat.device).permute(0, 3, 1, 2)
-            xv[:, :C].copy_(feat)
-            xv[:, C + frame2.shape[1]:].zero_()
-            ops.warp(frame2, flow, out=xv[:, C:C + frame2.shape[1]])
-            x = xv[:, :C + frame2.shape[1]]
-        else:
-            warped = ops.warp(frame2, flow)
-            x = torch.cat((feat, warped), dim=1)
+            key = (B, H, W, feat.device)
+            if self._tail is None or self._tail_key != key:
+                self._tail = torch.zeros((B, H, W, 8), dtype=torch.bfloat16, device=feat.device)   # pad channels stay 0
+                self._tail_key = key
+            tail = self._tail.permute(0, 3, 1, 2)
+            ops.warp(frame2, flow, out=tail[:, :frame2.shape[1]])
+            x_main, x_tail = feat, tail[:, :frame2.shape[1]]
+            for w, b, c27 in zip(self.weights, self.biases, convs27):
+                x_main = ops.deform_conv2d_fused(x_main, x_tail, c27, w, b, math=self.math if self.math != "auto" else "bf16_tc")
+                x_tail = None
+            return x_main
+        warped = ops.warp(frame2, flow)
+        x = torch.cat((feat, warped), dim=1)
         for w, b, c27 in zip(self.weights, self.biases, convs27):
             offset, mask = pack_split(c27)
             x = ops.deform_conv2d(x, offset, w, b, stride=1, padding=1, dilation=1, mask=mask, math=self.math)
         return x
+
+    def _fast(self, frame2, feat) -> bool:
+        return (self.math != "fp32" and feat.dtype == torch.bfloat16 and feat.shape[1] == 64 and frame2.shape[1] <= 8
+                and feat.is_contiguous(memory_format=torch.channels_last))
 
     # ---------------------------------------------------------------------------------------------- host API
     def run_host(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor, convs27: Sequence[torch.Tensor],

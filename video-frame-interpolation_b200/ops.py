@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import check, desc, dtype_code, ref, require_cuda, stream_handle
 
-__all__ = ["warp", "warp_blend", "deform_conv2d", "dcn_workspace_bytes", "launch_count", "reset_launch_count"]
+__all__ = ["warp", "warp_blend", "deform_conv2d", "deform_conv2d_fused", "dcn_workspace_bytes", "launch_count", "reset_launch_count"]
 
 
 def launch_count() -> int:
@@ -99,7 +99,7 @@ def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch
 
 
 # ------------------------------------------------------------------------------------------------------ DCN
-_MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC}
+_MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC, "bf16_tc_hq": _lib.MATH_BF16_TC_HQ}
 PACKED_C = 72   # channel stride of the tensor-core path's activation image
 
 
@@ -141,7 +141,7 @@ class _DcnFn(torch.autograd.Function):
         weight_c = weight.contiguous()
         bias_c = None if bias is None else bias.contiguous()
         lib = _lib.load()
-        tc = math == _lib.MATH_BF16_TC or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
+        tc = math in (_lib.MATH_BF16_TC, _lib.MATH_BF16_TC_HQ) or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
         if tc and x.dtype == torch.bfloat16 and O <= PACKED_C:
             # channel-padded channels-last bf16 [B,H,W,72]: what the next tensor-core layer gathers from without a
             # layout pass; handed back as the logical [B,O,H,W] view (strides (H*W*72, 1, W*72, 72))
@@ -192,6 +192,31 @@ class _DcnFn(torch.autograd.Function):
         return (gx.to(x.dtype) if need_x else None, goff.to(offset.dtype) if need_off else None,
                 gmask.to(mask.dtype) if need_mask else None, gw.to(weight.dtype) if need_w else None,
                 gb.to(ctx.bias_dtype) if need_b else None, None)
+
+
+def deform_conv2d_fused(x_main: torch.Tensor, x_tail: Optional[torch.Tensor], conv27: torch.Tensor, weight: torch.Tensor,
+                        bias: Optional[torch.Tensor] = None, math: str = "bf16_tc") -> torch.Tensor:
+    """Hot-path form of the DCNv2 forward (inference only, tensor-core math): consumes the raw 27-channel
+    ``offset_conv`` output (the chunk/cat/sigmoid of ema_vfi.py:57-59 happens inside the kernel) and, optionally, the
+    input as two channels-last bf16 pieces ``x_main`` [B,64,H,W] + ``x_tail`` [B,<=8,H,W] (the torch.cat of
+    ema_vfi.py:134 never materialises).  Returns the logical [B,O,H,W] view of a channel-padded channels-last buffer."""
+    dev = require_cuda(x_main, x_tail, conv27, weight, bias)
+    if math not in ("auto", "bf16_tc", "bf16_tc_hq"):
+        raise NotImplementedError("deform_conv2d_fused implements the tensor-core math modes only")
+    B, _, H, W = x_main.shape
+    O = weight.shape[0]
+    lib = _lib.load()
+    weight_c = weight.contiguous()
+    bias_c = None if bias is None else bias.contiguous()
+    out = packed_buffer(B, H, W, dev).permute(0, 3, 1, 2)[:, :O]
+    ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, x_main.shape[1], O, H, W, _MATH[math])))
+    with torch.cuda.device(dev):
+        check(lib.vfi_dcn_fwd_fused(ref(desc(x_main)), ref(desc(x_tail)) if x_tail is not None else None,
+                                    ref(desc(conv27)), weight_c.data_ptr(), dtype_code(weight_c.dtype),
+                                    None if bias_c is None else bias_c.data_ptr(),
+                                    dtype_code(bias_c.dtype) if bias_c is not None else 0, ref(desc(out)), O, _MATH[math],
+                                    ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_fwd_fused")
+    return out
 
 
 def _pair(v):
