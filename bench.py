@@ -202,7 +202,7 @@ def main():
 
     # kernel-level events: every DCN forward launch and the warp launch inside the timed region
     dcn_ev, warp_ev = [], []
-    orig_dcn, orig_warp = vfi_b200.ops.deform_conv2d, vfi_b200.ops.warp
+    orig_dcn, orig_dcn_fused, orig_warp = vfi_b200.ops.deform_conv2d, vfi_b200.ops.deform_conv2d_fused, vfi_b200.ops.warp
     timing = {"on": False}
 
     def timed(fn, bucket):
@@ -218,6 +218,7 @@ def main():
         return wrapper
 
     vfi_b200.ops.deform_conv2d = timed(orig_dcn, dcn_ev)
+    vfi_b200.ops.deform_conv2d_fused = timed(orig_dcn_fused, dcn_ev)
     vfi_b200.ops.warp = timed(orig_warp, warp_ev)
 
     out = None

@@ -99,17 +99,20 @@ int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flow_a, const 
  * mask [B,9,H,W]; weight [O,C,3,3] contiguous; bias [O] or NULL; out [B,O,H,W]. */
 size_t vfi_dcn_workspace_bytes(int64_t B, int64_t C, int64_t O, int64_t H, int64_t W, int32_t math);
 
-/* Packs weight [O,C,3,3] (f32|bf16|f16) into the bf16 B-operand image the tcgen05 kernel bulk-copies into shared
- * memory: 11 K blocks x [80 rows (o, zero padded)] x 128 B, K order q = tap*72 + c (zero padded to 704), each row's
- * eight 16-byte chunks already permuted for the SWIZZLE_128B canonical layout (chunk j of row r stored at j ^ (r & 7)).
- * `packed` needs vfi_dcn_packed_weight_bytes() = 112,640 bytes, 16-byte aligned. */
+/* Tensor-core path operand formats.
+ *  - Activation "planes": channels-last bf16 in two dense buffers, main [B,H,W,64] (128 B per pixel: one aligned cache
+ *    line per bilinear corner) and tail [B,H,W,8] (16 B per pixel: channels 64..71, zero beyond C).
+ *  - Weight image: 11 K blocks x [80 rows (o, zero padded)] x 128 B; K block t < 9 holds the 64 main channels of tap t,
+ *    block 9 the 8-channel tails of taps 0..7, block 10 the tail of tap 8 + zeros; each row's eight 16-byte chunks are
+ *    already permuted for the SWIZZLE_128B canonical layout (chunk j of row r stored at j ^ (r & 7)).
+ *    vfi_dcn_packed_weight_bytes() = 112,640 bytes, 16-byte aligned. */
 size_t vfi_dcn_packed_weight_bytes(void);
 int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
                         vfi_stream_t stream);
 
-/* Converts an activation tensor of any supported layout/dtype into the channel-padded channels-last bf16 image
- * the tcgen05 kernel gathers from: [B,H,W,72] bf16 (channels >= C are zero). */
-int vfi_dcn_pack_input(const vfi_tensor* x, void* packed_nhwc72, vfi_stream_t stream);
+/* Converts an activation tensor of any supported layout/dtype (C <= 72) into planes: main_plane B*H*W*64 bf16,
+ * tail_plane B*H*W*8 bf16. */
+int vfi_dcn_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, vfi_stream_t stream);
 
 int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
                 int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out, int64_t O,
@@ -118,12 +121,15 @@ int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor*
 /* Hot-path form of the forward (tensor-core math only).  Two pieces of glue of the reference are folded in:
  *  - the offset/mask split of ema_vfi.py:57-59: conv27 is the raw [B,27,H,W] offset_conv output; offsets are its
  *    thirds 0 and 2, the mask is sigmoid(third 1), computed in the kernel's geometry stage;
- *  - the torch.cat of ema_vfi.py:134: the input may be given as two channels-last bf16 pieces, x_main [B,64,H,W]
- *    (unit channel stride, dense pixels) and x_tail [B,<=8,H,W] (pixel stride >= 8 elements, pad channels zero);
- *    x_tail may be NULL, in which case x_main is handled exactly as vfi_dcn_fwd handles x. */
+ *  - the torch.cat of ema_vfi.py:134: the input is given as planes, x_main [B,64,H,W] + x_tail [B,<=8,H,W] (dense
+ *    channels-last bf16, pixel strides 64 and 8 elements, pad channels of the tail zero) -- feat and the warped frame
+ *    as they exist before the cat.  x_tail may be NULL, in which case x_main is handled as vfi_dcn_fwd handles x.
+ * Output: planes when out_tail != NULL (out [B,64,H,W], out_tail [B,O-64,H,W]; what the next layer reads directly),
+ * otherwise any strided [B,O,H,W] tensor. */
 int vfi_dcn_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27, const void* weight,
-                      int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out, int64_t O,
-                      int32_t math, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
+                      int32_t weight_dtype, const void* bias, int32_t bias_dtype, const vfi_tensor* out,
+                      const vfi_tensor* out_tail, int64_t O, int32_t math, void* workspace, size_t workspace_bytes,
+                      vfi_stream_t stream);
 
 /* Gradients (torchvision::_deform_conv2d_backward).  grad_out must have x's dtype.  All gradient tensors are f32.  grad_x must be zero-filled by
  * the caller (atomic scatter-add target); grad_weight / grad_bias likewise (accumulated with atomics so that a

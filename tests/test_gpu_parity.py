@@ -286,9 +286,9 @@ def test_dcn_tensor_core_path(B, H, W, sigma):
     out = vfi_b200.deform_conv2d(t["x"], t["offset"], t["weight"], t["bias"], stride=1, padding=1, dilation=1,
                                  mask=t["mask"], math="bf16_tc")
     assert out.shape == (B, 67, H, W) and out.dtype == torch.bfloat16
-    assert out.stride() == (H * W * 72, 1, W * 72, 72)          # channel-padded channels-last view
+    assert out.is_contiguous(memory_format=torch.channels_last)
     assert relerr(out, ref) <= 1e-2
-    # chained: the packed output feeds the next layer without a layout pass, fp32 offsets/mask accepted
+    # chained with fp32 offsets/mask
     out2 = vfi_b200.deform_conv2d(out, cu(z["offset"]), t["weight"], t["bias"], stride=1, padding=1, dilation=1,
                                   mask=cu(z["mask"]), math="bf16_tc")
     ref2 = oracle.dcn_fwd(out.float().cpu().numpy(), z["offset"], z["mask"], zr["weight"], zr["bias"])
@@ -317,17 +317,20 @@ def test_dcn_fused_split_input_and_conv27(math, bar):
     c27 = c27.to(torch.bfloat16)
     w = ((torch.rand(67, 67, 3, 3, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
     b = ((torch.rand(67, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
-    tail = torch.zeros(B, H, W, 8, dtype=torch.bfloat16, device=DEV)
-    tail[..., :3] = tail3.permute(0, 2, 3, 1).to(DEV)
-    out = ops.deform_conv2d_fused(feat.to(DEV).contiguous(memory_format=torch.channels_last),
-                                  tail.permute(0, 3, 1, 2)[:, :3], c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
+    src = ops.Planes(B, H, W, DEV, zero_tail=True)
+    src.main.copy_(feat.permute(0, 2, 3, 1))
+    src.tail[..., :3] = tail3.permute(0, 2, 3, 1).to(DEV)
+    out = ops.deform_conv2d_fused(src.main_nchw, src.tail_nchw(3), c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
     off, m = oracle.pack_split(c27.float().numpy())
     ref = oracle.dcn_fwd(torch.cat([feat, tail3], 1).float().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
-    assert relerr(out, ref) <= bar
-    # single-piece form (the packed output of a previous layer) with conv27
-    out2 = ops.deform_conv2d_fused(out, None, c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
-    ref2 = oracle.dcn_fwd(out.float().cpu().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
-    assert relerr(out2, ref2) <= bar
+    assert relerr(out.to_nchw(), ref) <= bar
+    assert float(out.tail[..., 3:].abs().max()) == 0.0            # pad channels of the tail plane are written as zeros
+    # planes in -> planes out (what layers 2 and 3 of the path do), and a plain NCHW tensor in
+    out2 = ops.deform_conv2d_fused(out.main_nchw, out.tail_nchw(), c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
+    ref2 = oracle.dcn_fwd(out.to_nchw().float().cpu().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
+    assert relerr(out2.to_nchw(), ref2) <= bar
+    out3 = ops.deform_conv2d_fused(torch.cat([feat, tail3], 1).to(DEV), None, c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
+    assert relerr(out3.to_nchw(), ref) <= bar
 
 
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
@@ -353,6 +356,7 @@ def test_hot_path_bf16_tensor_core_vs_fp32_reference_psnr():
     frame2, flow, feat, convs = synthetic_inputs(B, H, W, dtype=torch.bfloat16, device=DEV, seed=5)
     ws, bs = synthetic_weights(dtype=torch.bfloat16, device=DEV)
     out = HotPath(ws, bs, math="bf16_tc").run(frame2, flow, feat.contiguous(memory_format=torch.channels_last), convs)
+    out = out.to_nchw()
     f = lambda t: t.float().cpu().numpy()  # noqa: E731
     x = np.concatenate([f(feat), oracle.warp_fwd(f(frame2), f(flow))], 1)
     for w, b, c in zip(ws, bs, convs):

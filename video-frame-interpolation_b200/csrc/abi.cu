@@ -28,13 +28,13 @@ size_t dcn_tc_packed_weight_bytes();
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
                        void* packed, float* bias_out, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
-int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st);
+int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
                int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
                void* workspace, size_t workspace_bytes, cudaStream_t st);
 int dcn_tc_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27, const void* weight,
-                     int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+                     int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, const vfi_tensor* out_tail,
+                     long long O, bool hq, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace vfi
 
@@ -84,8 +84,8 @@ extern "C" int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int
   return dcn_tc_pack_weight(weight, weight_dtype, nullptr, VFI_F32, O, C, packed, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int vfi_dcn_pack_input(const vfi_tensor* x, void* packed_nhwc72, vfi_stream_t stream) {
-  return dcn_tc_pack_input(x, packed_nhwc72, (cudaStream_t)stream);
+extern "C" int vfi_dcn_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, vfi_stream_t stream) {
+  return dcn_tc_pack_input(x, main_plane, tail_plane, (cudaStream_t)stream);
 }
 
 extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
@@ -109,10 +109,10 @@ extern "C" int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* 
 
 extern "C" int vfi_dcn_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27,
                                  const void* weight, int32_t weight_dtype, const void* bias, int32_t bias_dtype,
-                                 const vfi_tensor* out, int64_t O, int32_t math, void* workspace, size_t workspace_bytes,
-                                 vfi_stream_t stream) {
+                                 const vfi_tensor* out, const vfi_tensor* out_tail, int64_t O, int32_t math,
+                                 void* workspace, size_t workspace_bytes, vfi_stream_t stream) {
   VFI_REQUIRE(math == VFI_DCN_MATH_AUTO || math == VFI_DCN_MATH_BF16_TC || math == VFI_DCN_MATH_BF16_TC_HQ,
               VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd_fused: only the tensor-core math modes are implemented in fused form");
-  return dcn_tc_fwd_fused(x_main, x_tail, conv27, weight, weight_dtype, bias, bias_dtype, out, O,
+  return dcn_tc_fwd_fused(x_main, x_tail, conv27, weight, weight_dtype, bias, bias_dtype, out, out_tail, O,
                           math == VFI_DCN_MATH_BF16_TC_HQ, workspace, workspace_bytes, (cudaStream_t)stream);
 }

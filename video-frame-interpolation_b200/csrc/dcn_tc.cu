@@ -4,9 +4,16 @@
 // torchvision materialises columns[603, P] in HBM (40 GB fp32 at 1080p batch 8) and calls a BLAS GEMM; here the
 // modulated bilinear im2col is the A-operand PRODUCER of the GEMM and never leaves the SM:
 //
-//     D[128 px, 80 o] (TMEM, fp32)  +=  A[128 px, 64 k] (smem, written by 8 gather warps)  x  B[80 o, 64 k]^T (smem, bulk copy)
+//     D[128 px, 80 o] (TMEM, fp32)  +=  A[128 px, 64 k] (smem, written by the gather warps)  x  B[80 o, 64 k]^T (smem, bulk copy)
 //
-//   K ordering  : q = tap * 72 + c  (tap = 3i + j, c < 67 real, 67..71 zero) -> 648, padded to 656 = 41 x UMMA_K(16)
+// Activation layout ("planes"): channels-last bf16 in two dense buffers,
+//     main [B, H, W, 64]  (128 B per pixel = exactly one aligned L1 line per bilinear corner) and
+//     tail [B, H, W,  8]  ( 16 B per pixel: channels 64..66 + zeros; eight pixels share a line).
+// This is how feat (64 ch) and the warped frame (3 ch) exist before the reference's torch.cat (ema_vfi.py:134), and it is
+// what the kernel writes for the next layer.  Any other input layout is converted by pack_input_kernel (workspace).
+//
+//   K ordering  : 11 blocks of 64: block t < 9 = the 64 main channels of tap t (t = 3i + j); block 9 = the 8-channel
+//                 tails of taps 0..7; block 10 = the tail of tap 8 + zero padding (one UMMA_K = 16 step).  656 in all.
 //   A stage     : 128 rows x 128 B, canonical K-major SWIZZLE_128B (16-byte chunk j of row r sits at chunk j ^ (r & 7))
 //   B stage     : 80 rows x 128 B of the pre-swizzled weight image, one cp.async.bulk (UBLKCP) per K block
 //   accumulator : 2 x (128 lanes x 80 columns) in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
@@ -16,26 +23,23 @@
 //   warps 0-15  producers in two groups of 8 that alternate over the K blocks (one group's gather latency hides behind
 //               the other's lerp/store work).  Per tile all 16 warps first compute the 9 x 128 tap geometries (corner
 //               pixel indices + mask-folded weights; optionally straight from the 27-channel offset_conv output with the
-//               sigmoid folded in).  Per K block each lane owns one 16-byte chunk of four rows: 4 corner loads of 16 B
-//               (read-only path; 8 lanes cover one pixel's 128 B), packed HFMA2.BF16 lerp (or fp32 in HQ mode), one
-//               16-byte store into the swizzled A stage; fence.proxy.async; one mbarrier arrive per warp.
+//               sigmoid folded in).  Main blocks: each lane owns one 16-byte chunk of four rows; the 8 lanes of a row
+//               read one aligned 128 B line per corner.  Tail blocks: each lane owns one row, warps split the taps.
+//               4 corner loads of 16 B (read-only path), packed HFMA2.BF16 lerp (fp32 in HQ mode), one 16-byte store
+//               into the swizzled A stage; fence.proxy.async; one mbarrier arrive per warp.
 //   warp 16     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
 //   warps 17-20 epilogue: tcgen05.ld the accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
-//
-// The activation image the producers gather from is channels-last bf16 in 16-byte chunks: either one channel-padded
-// [B, H, W, 72] buffer (144 B / pixel, what this kernel also writes), or two pieces -- [B, H, W, 64] + [B, H, W, 8] --
-// which is how feat and the warped frame exist before the reference's torch.cat (ema_vfi.py:134).  Any other layout
-// is converted by pack_input_kernel first (workspace).
 #include "common.cuh"
 
 namespace vfi {
 
 constexpr int TC_M = 128;
 constexpr int TC_N = 80;
-constexpr int TC_CPAD = 72;
+constexpr int TC_CMAIN = 64;                         // channels in the main plane (8 chunks of 16 B)
+constexpr int TC_CTAIL = 8;                          // channels in the tail plane (1 chunk)
+constexpr int TC_CMAX = TC_CMAIN + TC_CTAIL;         // 72
 constexpr int TC_TH = 8, TC_TW = 16;                 // output tile (rows x cols) = 128 pixels
-constexpr int TC_CHUNKS = 81;                        // real 16-byte K chunks: 9 taps x 9
-constexpr int TC_KBLOCKS = 11;                       // 128-byte swizzle atoms along K (last one: 2 chunks used)
+constexpr int TC_KBLOCKS = 11;                       // 128-byte swizzle atoms along K (9 main + 2 tail)
 constexpr int TC_A_BYTES = TC_M * 128;               // 16384
 constexpr int TC_B_BYTES = TC_N * 128;               // 10240
 constexpr int TC_STAGES = 3;
@@ -48,12 +52,13 @@ constexpr int TC_ACC_STRIDE = 128;
 bool dcn_tc_available() { return true; }
 size_t dcn_tc_packed_weight_bytes() { return (size_t)TC_KBLOCKS * TC_B_BYTES; }   // 112,640
 
-// workspace: [packed weight image | bias f32[80] (512 B) | packed input B*H*W*72 bf16]
+// workspace: [packed weight image | bias f32[80] (512 B) | main plane P*64 bf16 | tail plane P*8 bf16]
 static size_t ws_bias_off() { return dcn_tc_packed_weight_bytes(); }
-static size_t ws_input_off() { return dcn_tc_packed_weight_bytes() + 512; }
+static size_t ws_main_off() { return dcn_tc_packed_weight_bytes() + 512; }
+static size_t ws_tail_off(long long P) { return ws_main_off() + (((size_t)P * TC_CMAIN * 2 + 255) / 256) * 256; }
 size_t dcn_tc_workspace_bytes(long long B, long long H, long long W) {
-  size_t xin = (((size_t)B * H * W * TC_CPAD * 2) + 255) / 256 * 256;
-  return ws_input_off() + xin;
+  const long long P = B * H * W;
+  return ws_tail_off(P) + (((size_t)P * TC_CTAIL * 2 + 255) / 256) * 256;
 }
 
 namespace {
@@ -71,19 +76,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-// Bounded wait: a protocol bug traps (launch failure) after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    if (done) return;
-    if (it == 64) t0 = clock64();
-    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+// Bounded wait.  try_wait suspends the thread in hardware for up to the hinted time, so a waiting role does not burn
+// issue slots (the un-hinted form returns every ~150 cycles; measured: 29% of all executed instructions were spin loops).
+// A protocol bug traps (launch failure) after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done)
+               : "r"(bar), "r"(parity), "r"(hint_ns)
+               : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity, 20000u)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity, 2000u)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -143,15 +155,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ operand packers
+// K index (kb, kk) -> (tap, channel) of the weight it multiplies; channel -1 = zero padding.
+__host__ __device__ inline void tc_k_to_tap_channel(int kb, int kk, int& tap, int& c) {
+  if (kb < 9) { tap = kb; c = kk; }
+  else if (kb == 9) { tap = kk >> 3; c = TC_CMAIN + (kk & 7); }
+  else if (kk < 8) { tap = 8; c = TC_CMAIN + kk; }
+  else { tap = 0; c = -1; }
+}
+
 template <typename TW>
 __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, int bias_dtype, int O, int C,
                                    uint8_t* __restrict__ packed, float* __restrict__ bias_out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < TC_KBLOCKS * TC_N * 64) {
     int kb = idx / (TC_N * 64), o = (idx / 64) % TC_N, kk = idx % 64;
-    int q = kb * 64 + kk, tap = q / TC_CPAD, c = q % TC_CPAD;
+    int tap, c;
+    tc_k_to_tap_channel(kb, kk, tap, c);
     float v = 0.0f;
-    if (o < O && tap < 9 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + tap]);
+    if (o < O && c >= 0 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + tap]);
     size_t off = (size_t)kb * TC_B_BYTES + (size_t)o * 128 + ((((kk >> 3) ^ (o & 7))) << 4) + (kk & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
   }
@@ -166,13 +187,15 @@ __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, i
   }
 }
 
+// Any strided [B,C,H,W] tensor -> main plane [P][64] + tail plane [P][8] (bf16, zero padded).
 template <typename TX>
 __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long long sc, long long sh, long long sw, int B,
-                                  int C, int H, int W, __nv_bfloat16* __restrict__ packed) {
+                                  int C, int H, int W, __nv_bfloat16* __restrict__ main_plane,
+                                  __nv_bfloat16* __restrict__ tail_plane) {
   // one thread per (pixel, 8-channel chunk); lanes run over pixels so NCHW reads coalesce
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long npix = (long long)B * H * W;
-  if (idx >= npix * (TC_CPAD / 8)) return;
+  if (idx >= npix * (TC_CMAX / 8)) return;
   int chunk = (int)(idx / npix);
   long long pix = idx % npix;
   int xx = (int)(pix % W);
@@ -186,39 +209,34 @@ __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long l
     int c = chunk * 8 + i;
     v[i] = __float2bfloat16_rn(c < C ? to_f32<TX>(__ldg(src + c * sc)) : 0.0f);
   }
-  *reinterpret_cast<uint4*>(packed + pix * TC_CPAD + chunk * 8) = *reinterpret_cast<uint4*>(v);
+  __nv_bfloat16* dst = chunk < 8 ? main_plane + pix * TC_CMAIN + chunk * 8 : tail_plane + pix * TC_CTAIL;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(v);
 }
 
 // ------------------------------------------------------------------------------------------------ main kernel
-struct TcGeo {
-  int pix[4];        // flattened pixel index (b*H*W + y*W + x) of corners 00, 01, 10, 11, clamped into the image
-  uint32_t w[4];     // bilinear weight x modulation mask (0 for corners outside the image / dead samples / padding
-                     // rows): bf16x2 splat (w, w) on the fast path, fp32 bits on the HQ path
-};
-
 struct TcParams {
-  // activation image, channels-last bf16 in up to two pieces: chunks 0..n_main-1 come from x_main (pixel stride
-  // main_stride bytes), chunk n_main (if any) from x_tail.  A single packed [P][72] image is main with 9 chunks.
-  const uint8_t* x_main; const uint8_t* x_tail;
-  long long main_stride, tail_stride;      // bytes per pixel
-  int n_main;                              // 16-byte chunks taken from x_main (8 or 9)
-  const void* offset; const void* mask;    // fused27: both point at the 27-channel offset_conv output
+  const uint8_t* x_main; const uint8_t* x_tail;   // planes (see file header)
+  uint32_t main_stride, tail_stride;               // bytes per pixel (128 / 16 for dense planes)
+  const void* offset; const void* mask;            // fused27: both point at the 27-channel offset_conv output
   long long f_sn, f_sc, f_sh, f_sw;
   long long m_sn, m_sc, m_sh, m_sw;
-  int fused27;                             // 1: offset ch j -> conv27[j < 9 ? j : j + 9], mask = sigmoid(conv27[9 + k])
-  const uint8_t* wpacked;                  // [11][80][128 B] swizzled
-  const float* bias;                       // [80]
-  void* out;
-  long long o_sn, o_sc, o_sh, o_sw;
-  int out_packed;                          // 1: out is [P][72] bf16 (channel-padded channels-last), vector stores
+  int fused27;                                     // 1: offset ch j -> conv27[j < 9 ? j : j + 9], mask = sigmoid(conv27[9 + k])
+  const uint8_t* wpacked;                          // [11][80][128 B] swizzled
+  const float* bias;                               // [80]
+  void* out; void* out_tail;                       // out_tail != null: planes out (main [P][64], tail [P][8] bf16)
+  long long o_sn, o_sc, o_sh, o_sw;                // generic strided output otherwise
   int B, H, W, O;
   int tiles_x, tiles_y, num_tiles;
 };
 
+// Tap geometry, one entry per (tap, tile row).  Row 9 of both arrays is all zeros: the zero-padding chunk of the last
+// K block is produced by the ordinary code path with "tap 9".
 struct __align__(1024) TcSmem {
   uint8_t a[TC_STAGES][TC_A_BYTES];
   uint8_t b[TC_STAGES][TC_B_BYTES];
-  TcGeo geo[9][TC_M];
+  int4 geo_pix[10][TC_M];      // flattened pixel index (b*H*W + y*W + x) of corners 00, 01, 10, 11, clamped into the image
+  uint4 geo_w[10][TC_M];       // bilinear weight x modulation mask per corner (0 for corners outside the image, dead
+                               // samples, padding rows): bf16x2 splat (w, w) on the fast path, fp32 bits on the HQ path
   float bias[TC_N];
   unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
@@ -233,22 +251,31 @@ __device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) { return *reinter
 // Two channels of the modulated bilinear sample.  HQ: fp32 arithmetic, one rounding at the end.  Fast: packed
 // HMUL2/HFMA2.BF16 (each step rounds to bf16; measured cost on the layer output: 2.8e-3 vs 1.4e-3 max-rel).
 template <bool HQ>
-__device__ __forceinline__ uint32_t lerp_pair(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const uint32_t* w) {
+__device__ __forceinline__ uint32_t lerp_pair(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const uint4& w) {
   if constexpr (HQ) {
     float al, ah, bl, bh, cl, ch, dl, dh;
     unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch); unpack2(d, dl, dh);
-    const float w0 = __uint_as_float(w[0]), w1 = __uint_as_float(w[1]), w2 = __uint_as_float(w[2]), w3 = __uint_as_float(w[3]);
+    const float w0 = __uint_as_float(w.x), w1 = __uint_as_float(w.y), w2 = __uint_as_float(w.z), w3 = __uint_as_float(w.w);
     float lo = fmaf(w3, dl, fmaf(w2, cl, fmaf(w1, bl, w0 * al)));
     float hi = fmaf(w3, dh, fmaf(w2, ch, fmaf(w1, bh, w0 * ah)));
     __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&r);
   } else {
-    __nv_bfloat162 r = __hmul2(as_bf162(w[0]), as_bf162(a));
-    r = __hfma2(as_bf162(w[1]), as_bf162(b), r);
-    r = __hfma2(as_bf162(w[2]), as_bf162(c), r);
-    r = __hfma2(as_bf162(w[3]), as_bf162(d), r);
+    __nv_bfloat162 r = __hmul2(as_bf162(w.x), as_bf162(a));
+    r = __hfma2(as_bf162(w.y), as_bf162(b), r);
+    r = __hfma2(as_bf162(w.z), as_bf162(c), r);
+    r = __hfma2(as_bf162(w.w), as_bf162(d), r);
     return *reinterpret_cast<uint32_t*>(&r);
   }
+}
+template <bool HQ>
+__device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const uint4& w) {
+  uint4 o;
+  o.x = lerp_pair<HQ>(a.x, b.x, c.x, d.x, w);
+  o.y = lerp_pair<HQ>(a.y, b.y, c.y, d.y, w);
+  o.z = lerp_pair<HQ>(a.z, b.z, c.z, d.z, w);
+  o.w = lerp_pair<HQ>(a.w, b.w, c.w, d.w, w);
+  return o;
 }
 
 template <bool HQ>
@@ -259,8 +286,7 @@ __device__ __forceinline__ uint32_t pack_weight_word(float w) {
 }
 
 template <typename TO, bool HQ>
-__device__ __forceinline__ TcGeo tc_make_geo(const TcParams& p, int b, int y, int x, int k) {
-  TcGeo g;
+__device__ __forceinline__ void tc_make_geo(const TcParams& p, int b, int y, int x, int k, int4& pix, uint4& wq) {
   const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
   const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
   float dy, dx, mk;
@@ -289,13 +315,12 @@ __device__ __forceinline__ TcGeo tc_make_geo(const TcParams& p, int b, int y, in
   int cy0 = min(max(y0, 0), p.H - 1), cy1 = min(max(y0 + 1, 0), p.H - 1);
   int cx0 = min(max(x0, 0), p.W - 1), cx1 = min(max(x0 + 1, 0), p.W - 1);
   int base = b * p.H * p.W;
-  g.pix[0] = base + cy0 * p.W + cx0; g.pix[1] = base + cy0 * p.W + cx1;
-  g.pix[2] = base + cy1 * p.W + cx0; g.pix[3] = base + cy1 * p.W + cx1;
-  g.w[0] = pack_weight_word<HQ>((r0 && c0) ? hh * hw * mk : 0.0f);
-  g.w[1] = pack_weight_word<HQ>((r0 && c1) ? hh * lw * mk : 0.0f);
-  g.w[2] = pack_weight_word<HQ>((r1 && c0) ? lh * hw * mk : 0.0f);
-  g.w[3] = pack_weight_word<HQ>((r1 && c1) ? lh * lw * mk : 0.0f);
-  return g;
+  pix.x = base + cy0 * p.W + cx0; pix.y = base + cy0 * p.W + cx1;
+  pix.z = base + cy1 * p.W + cx0; pix.w = base + cy1 * p.W + cx1;
+  wq.x = pack_weight_word<HQ>((r0 && c0) ? hh * hw * mk : 0.0f);
+  wq.y = pack_weight_word<HQ>((r0 && c1) ? hh * lw * mk : 0.0f);
+  wq.z = pack_weight_word<HQ>((r1 && c0) ? lh * hw * mk : 0.0f);
+  wq.w = pack_weight_word<HQ>((r1 && c1) ? lh * lw * mk : 0.0f);
 }
 
 // tile index -> (batch, top row, left column)
@@ -305,6 +330,10 @@ __device__ __forceinline__ void tile_origin(const TcParams& p, int tile, int& b,
   int t = tile % per_img;
   y0 = (t / p.tiles_x) * TC_TH;
   x0 = (t % p.tiles_x) * TC_TW;
+}
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* base, int pix, uint32_t stride) {
+  return __ldg(reinterpret_cast<const uint4*>(base + (unsigned long long)(unsigned)pix * stride));   // IMAD.WIDE.U32
 }
 
 template <typename TO, typename TOUT, bool HQ>
@@ -326,6 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
   }
   if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
   if (tid < TC_N) s.bias[tid] = p.bias[tid];
+  if (tid < TC_M) { s.geo_pix[9][tid] = make_int4(0, 0, 0, 0); s.geo_w[9][tid] = make_uint4(0, 0, 0, 0); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -337,19 +367,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     // Two groups of 8 warps alternate over the CTA's global K-block sequence n = tile_iter * 11 + kb (group = n & 1), so
     // one group's gather latency overlaps the other group's lerp/store work.  stage = n % 3, phase = (n / 3) & 1.
     const int group = warp >> 3, wig = warp & 7;
+    // main blocks: lane = (row-in-quad rsub, chunk j); a pass covers rows 32*pass + 4*wig + rsub
     const int rsub = lane >> 3, j = lane & 7;
+    const int r_main = 4 * wig + rsub;                                    // + 32 * pass
+    const uint32_t a_off_main = (uint32_t)r_main * 128 + ((uint32_t)(j ^ (r_main & 7)) << 4);   // + 4096 * pass
+    const uint8_t* src_main = p.x_main + j * 16;
+    // tail blocks: lane = row within a 32-row pass
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       int b, ty0, tx0;
       tile_origin(p, tile, b, ty0, tx0);
       named_bar_sync(1, TC_PRODUCER_WARPS * 32);        // every producer is done reading the previous tile's geometry
       for (int i = tid; i < 9 * TC_M; i += TC_PRODUCER_WARPS * 32) {
-        int k = i / TC_M, r = i % TC_M;
-        int y = ty0 + r / TC_TW, x = tx0 + r % TC_TW;
-        TcGeo g;
-        if (y < p.H && x < p.W) g = tc_make_geo<TO, HQ>(p, b, y, x, k);
-        else { g.pix[0] = g.pix[1] = g.pix[2] = g.pix[3] = 0; g.w[0] = g.w[1] = g.w[2] = g.w[3] = 0u; }
-        s.geo[k][r] = g;
+        const int k = i / TC_M, r = i % TC_M;
+        const int y = ty0 + r / TC_TW, x = tx0 + r % TC_TW;
+        int4 pix = make_int4(0, 0, 0, 0);
+        uint4 wq = make_uint4(0, 0, 0, 0);
+        if (y < p.H && x < p.W) tc_make_geo<TO, HQ>(p, b, y, x, k, pix, wq);
+        s.geo_pix[k][r] = pix;
+        s.geo_w[k][r] = wq;
       }
       named_bar_sync(1, TC_PRODUCER_WARPS * 32);
       const int n0 = it * TC_KBLOCKS;
@@ -362,45 +398,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
           mbar_arrive_expect_tx(smem_u32(&s.full[stage]), TC_B_BYTES);
           bulk_g2s(smem_u32(&s.b[stage][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, smem_u32(&s.full[stage]));
         }
-        const int cq = kb * 8 + j;                      // global 16-byte chunk index along K
-        if (cq <= TC_CHUNKS) {                          // chunk 81 is the explicit zero pad of the last UMMA_K step
-          const bool real = cq < TC_CHUNKS;
-          const int tap = real ? (cq * 57) >> 9 : 0;    // cq / 9 for cq < 81
-          const int cc = cq - tap * 9;
-          const uint8_t* src = (cc < p.n_main) ? p.x_main + cc * 16 : p.x_tail;
-          const long long pstride = (cc < p.n_main) ? p.main_stride : p.tail_stride;
-          uint8_t* a_stage = &s.a[stage][0];
+        uint8_t* a_stage = &s.a[stage][0];
+        if (kb < 9) {
+          // ---- the 64 main channels of tap kb: one aligned 128 B line per (row, corner), 8 lanes each
+          const int4* gp = &s.geo_pix[kb][r_main];
+          const uint4* gw = &s.geo_w[kb][r_main];
+          uint8_t* dst = a_stage + a_off_main;
 #pragma unroll
           for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4];
-            uint4 wq[2];
+            uint4 v[2][4], wq[2];
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
-              const int r = ((batch * 2 + pp) * TC_GROUP_WARPS + wig) * 4 + rsub;
-              const int4 pix = *reinterpret_cast<const int4*>(&s.geo[tap][r].pix[0]);
-              wq[pp] = *reinterpret_cast<const uint4*>(&s.geo[tap][r].w[0]);
-              if (real) {
-                v[pp][0] = __ldg(reinterpret_cast<const uint4*>(src + pix.x * pstride));
-                v[pp][1] = __ldg(reinterpret_cast<const uint4*>(src + pix.y * pstride));
-                v[pp][2] = __ldg(reinterpret_cast<const uint4*>(src + pix.z * pstride));
-                v[pp][3] = __ldg(reinterpret_cast<const uint4*>(src + pix.w * pstride));
-              } else {
-                v[pp][0] = v[pp][1] = v[pp][2] = v[pp][3] = make_uint4(0, 0, 0, 0);
-                wq[pp] = make_uint4(0, 0, 0, 0);
-              }
+              const int pass = batch * 2 + pp;
+              const int4 pix = gp[pass * 32];
+              wq[pp] = gw[pass * 32];
+              v[pp][0] = ldg16(src_main, pix.x, p.main_stride);
+              v[pp][1] = ldg16(src_main, pix.y, p.main_stride);
+              v[pp][2] = ldg16(src_main, pix.z, p.main_stride);
+              v[pp][3] = ldg16(src_main, pix.w, p.main_stride);
+            }
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp)
+              *reinterpret_cast<uint4*>(dst + (batch * 2 + pp) * 4096) = lerp_chunk<HQ>(v[pp][0], v[pp][1], v[pp][2], v[pp][3], wq[pp]);
+          }
+        } else if (kb == 9) {
+          // ---- tails of taps 0..7: warp wig owns tap wig (chunk wig), lanes run over rows so neighbouring pixels' 16 B
+          //      tail records coalesce
+          const int tap = wig;
+#pragma unroll
+          for (int batch = 0; batch < 2; ++batch) {
+            uint4 v[2][4], wq[2];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              const int r = (batch * 2 + pp) * 32 + lane;
+              const int4 pix = s.geo_pix[tap][r];
+              wq[pp] = s.geo_w[tap][r];
+              v[pp][0] = ldg16(p.x_tail, pix.x, p.tail_stride);
+              v[pp][1] = ldg16(p.x_tail, pix.y, p.tail_stride);
+              v[pp][2] = ldg16(p.x_tail, pix.z, p.tail_stride);
+              v[pp][3] = ldg16(p.x_tail, pix.w, p.tail_stride);
             }
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
-              const int r = ((batch * 2 + pp) * TC_GROUP_WARPS + wig) * 4 + rsub;
-              const uint32_t* w = reinterpret_cast<const uint32_t*>(&wq[pp]);
-              uint4 o;
-              o.x = lerp_pair<HQ>(v[pp][0].x, v[pp][1].x, v[pp][2].x, v[pp][3].x, w);
-              o.y = lerp_pair<HQ>(v[pp][0].y, v[pp][1].y, v[pp][2].y, v[pp][3].y, w);
-              o.z = lerp_pair<HQ>(v[pp][0].z, v[pp][1].z, v[pp][2].z, v[pp][3].z, w);
-              o.w = lerp_pair<HQ>(v[pp][0].w, v[pp][1].w, v[pp][2].w, v[pp][3].w, w);
-              *reinterpret_cast<uint4*>(a_stage + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+              const int r = (batch * 2 + pp) * 32 + lane;
+              *reinterpret_cast<uint4*>(a_stage + r * 128 + ((tap ^ (r & 7)) << 4)) =
+                  lerp_chunk<HQ>(v[pp][0], v[pp][1], v[pp][2], v[pp][3], wq[pp]);
             }
           }
+        } else if (wig < 4) {
+          // ---- tail of tap 8 (chunk 0) and the zero chunk 1 of the last UMMA_K step: four warps, one row per lane
+          const int r = wig * 32 + lane;
+          const int4 pix = s.geo_pix[8][r];
+          const uint4 wq = s.geo_w[8][r];
+          const uint4 v0 = ldg16(p.x_tail, pix.x, p.tail_stride), v1 = ldg16(p.x_tail, pix.y, p.tail_stride);
+          const uint4 v2 = ldg16(p.x_tail, pix.z, p.tail_stride), v3 = ldg16(p.x_tail, pix.w, p.tail_stride);
+          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk<HQ>(v0, v1, v2, v3, wq);
+          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
         __syncwarp();
@@ -447,7 +500,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
       const bool inside = y < p.H && x < p.W;
-      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((size_t)(b * p.H + y) * p.W + x) * TC_CPAD;
+      const size_t pixel = (size_t)(b * p.H + y) * p.W + x;
+      __nv_bfloat16* om = reinterpret_cast<__nv_bfloat16*>(p.out) + pixel * TC_CMAIN;
+      __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(p.out_tail) + pixel * TC_CTAIL;
       TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
 #pragma unroll
       for (int c16 = 0; c16 < TC_N / 16; ++c16) {
@@ -460,19 +515,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
           if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
         }
         if (inside) {
-          if (p.out_packed) {
+          if (p.out_tail) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (c16 * 16 + h * 8 >= TC_CPAD) break;    // columns 72..79 are padding of the UMMA N dimension
+              const int c0 = c16 * 16 + h * 8;
+              if (c0 >= TC_CMAX) break;                  // columns 72..79 are padding of the UMMA N dimension
               uint32_t w4[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int c = c16 * 16 + h * 8 + 2 * i;
-                __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c],
-                                                          __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c + 1]);
+                __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c0 + 2 * i],
+                                                          __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c0 + 2 * i + 1]);
                 w4[i] = *reinterpret_cast<uint32_t*>(&hv);
               }
-              *reinterpret_cast<uint4*>(op + c16 * 16 + h * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              __nv_bfloat16* dst = c0 < TC_CMAIN ? om + c0 : ot;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
           } else {
 #pragma unroll
@@ -557,16 +613,17 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
 
 }  // namespace
 
-static bool is_packed_nhwc72(const vfi_tensor* t) {
-  return t->dtype == VFI_BF16 && t->c <= TC_CPAD && t->sc == 1 && t->sw == TC_CPAD && t->sh == t->w * TC_CPAD &&
-         t->sn == t->h * t->w * TC_CPAD && aligned(t->data, 16);
+// dense channels-last bf16 plane [B,H,W,C] with a pixel stride of exactly `stride` elements, 16-byte aligned
+static bool is_plane(const vfi_tensor* t, long long stride) {
+  return t->dtype == VFI_BF16 && t->sc == 1 && t->sw == stride && t->sh == t->w * stride && t->sn == t->h * t->w * stride &&
+         aligned(t->data, 16);
 }
 
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
                        void* packed, float* bias_out, cudaStream_t st) {
   VFI_REQUIRE(weight && packed, VFI_ERR_INVALID, "vfi_dcn_pack_weight: null pointer");
-  VFI_REQUIRE(O > 0 && O <= TC_N && C > 0 && C <= TC_CPAD, VFI_ERR_UNSUPPORTED,
-              "vfi_dcn_pack_weight: tensor-core path supports C <= %d, O <= %d (got C=%lld, O=%lld)", TC_CPAD, TC_N, C, O);
+  VFI_REQUIRE(O > 0 && O <= TC_N && C > 0 && C <= TC_CMAX, VFI_ERR_UNSUPPORTED,
+              "vfi_dcn_pack_weight: tensor-core path supports C <= %d, O <= %d (got C=%lld, O=%lld)", TC_CMAX, TC_N, C, O);
   VFI_REQUIRE(aligned(packed, 16), VFI_ERR_INVALID, "vfi_dcn_pack_weight: destination must be 16-byte aligned");
   const int n = TC_KBLOCKS * TC_N * 64;
   VFI_DISPATCH(weight_dtype, TW, {
@@ -577,38 +634,34 @@ int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, i
   return VFI_OK;
 }
 
-int dcn_tc_pack_input(const vfi_tensor* x, void* packed, cudaStream_t st) {
-  VFI_REQUIRE(x && packed, VFI_ERR_INVALID, "vfi_dcn_pack_input: null pointer");
-  VFI_REQUIRE(x->c > 0 && x->c <= TC_CPAD, VFI_ERR_UNSUPPORTED, "vfi_dcn_pack_input: C must be <= %d", TC_CPAD);
-  VFI_REQUIRE(aligned(packed, 16), VFI_ERR_INVALID, "vfi_dcn_pack_input: destination must be 16-byte aligned");
-  long long total = (long long)x->n * x->h * x->w * (TC_CPAD / 8);
+int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st) {
+  VFI_REQUIRE(x && main_plane && tail_plane, VFI_ERR_INVALID, "vfi_dcn_pack_input: null pointer");
+  VFI_REQUIRE(x->c > 0 && x->c <= TC_CMAX, VFI_ERR_UNSUPPORTED, "vfi_dcn_pack_input: C must be <= %d", TC_CMAX);
+  VFI_REQUIRE(aligned(main_plane, 16) && aligned(tail_plane, 16), VFI_ERR_INVALID,
+              "vfi_dcn_pack_input: destinations must be 16-byte aligned");
+  long long total = (long long)x->n * x->h * x->w * (TC_CMAX / 8);
   if (total == 0) return VFI_OK;
   VFI_REQUIRE(x->data, VFI_ERR_INVALID, "vfi_dcn_pack_input: null data pointer");
   VFI_DISPATCH(x->dtype, TX, {
-    pack_input_kernel<TX><<<ceil_div(total, 256), 256, 0, st>>>(reinterpret_cast<const TX*>(x->data), x->sn, x->sc, x->sh,
-                                                               x->sw, (int)x->n, (int)x->c, (int)x->h, (int)x->w,
-                                                               reinterpret_cast<__nv_bfloat16*>(packed));
+    pack_input_kernel<TX><<<ceil_div(total, 256), 256, 0, st>>>(
+        reinterpret_cast<const TX*>(x->data), x->sn, x->sc, x->sh, x->sw, (int)x->n, (int)x->c, (int)x->h, (int)x->w,
+        reinterpret_cast<__nv_bfloat16*>(main_plane), reinterpret_cast<__nv_bfloat16*>(tail_plane));
   });
   VFI_LAUNCH_CHECK("pack_input_kernel");
   return VFI_OK;
 }
 
-// channels-last bf16 piece usable by the gather without a layout pass: unit channel stride, dense pixels, 16-byte rows
-static bool is_nhwc_piece(const vfi_tensor* t, long long min_sw) {
-  return t->dtype == VFI_BF16 && t->sc == 1 && t->sw >= min_sw && t->sw % 8 == 0 && t->sh == t->w * t->sw &&
-         t->sn == t->h * t->w * t->sw && aligned(t->data, 16);
-}
-
-// Shared implementation.  x_tail may be null.  conv27 != null selects the fused offset/mask form.
+// Shared implementation.  x_tail == null: x_main is any [B,C,H,W] tensor (packed into planes in the workspace).
+// x_tail != null: planes in.  conv27 != null selects the fused offset/mask form.  out_tail != null: planes out.
 int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* offset, const vfi_tensor* mask,
                const vfi_tensor* conv27, const void* weight, int weight_dtype, const void* bias, int bias_dtype,
-               const vfi_tensor* out, long long O, bool hq, void* workspace, size_t workspace_bytes, cudaStream_t st,
-               const char* who) {
+               const vfi_tensor* out, const vfi_tensor* out_tail, long long O, bool hq, void* workspace,
+               size_t workspace_bytes, cudaStream_t st, const char* who) {
   const vfi_tensor* x = x_main;
   VFI_REQUIRE(x && out && weight && (conv27 || (offset && mask)), VFI_ERR_INVALID, "%s: null argument", who);
   const long long C = x->c + (x_tail ? x_tail->c : 0);
-  VFI_REQUIRE(C <= TC_CPAD && O <= TC_N && O > 0 && x->c > 0, VFI_ERR_UNSUPPORTED,
-              "%s(bf16_tc): supports C <= %d and O <= %d (got C=%lld, O=%lld)", who, TC_CPAD, TC_N, C, O);
+  VFI_REQUIRE(C <= TC_CMAX && O <= TC_N && O > 0 && x->c > 0, VFI_ERR_UNSUPPORTED,
+              "%s(bf16_tc): supports C <= %d and O <= %d (got C=%lld, O=%lld)", who, TC_CMAX, TC_N, C, O);
   if (conv27) {
     VFI_REQUIRE(conv27->n == x->n && conv27->c == 27 && conv27->h == x->h && conv27->w == x->w, VFI_ERR_INVALID,
                 "%s: conv27 must be [B,27,H,W]", who);
@@ -620,51 +673,55 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
                 "%s: mask must be [B,9,H,W]", who);
     VFI_REQUIRE(offset->dtype == mask->dtype, VFI_ERR_UNSUPPORTED, "%s: offset and mask must share a dtype", who);
   }
-  VFI_REQUIRE(out->n == x->n && out->c == O && out->h == x->h && out->w == x->w, VFI_ERR_INVALID,
-              "%s: out must be [B,O,H,W]", who);
   const long long P = (long long)x->n * x->h * x->w;
   if (P == 0) return VFI_OK;
   VFI_REQUIRE(x->data && offset->data && mask->data && out->data, VFI_ERR_INVALID, "%s: null data pointer", who);
   VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "%s(bf16_tc): more than 2^30 pixels per call", who);
 
   TcParams p;
-  bool direct;
-  if (x_tail) {
-    // two-piece form: main supplies whole 16-byte chunks, the tail supplies the last one
-    VFI_REQUIRE(x_tail->data && x_tail->n == x->n && x_tail->h == x->h && x_tail->w == x->w && x_tail->c <= 8,
-                VFI_ERR_INVALID, "%s: x_tail must be [B,<=8,H,W] matching x_main", who);
-    VFI_REQUIRE(x->c % 8 == 0 && is_nhwc_piece(x, x->c) && is_nhwc_piece(x_tail, 8), VFI_ERR_UNSUPPORTED,
-                "%s: the two-piece input needs channels-last bf16 pieces (main: C %% 8 == 0; tail: pixel stride >= 8, "
-                "16-byte aligned, pad channels zero)", who);
-    direct = true;
-    p.x_main = reinterpret_cast<const uint8_t*>(x->data); p.main_stride = x->sw * 2; p.n_main = (int)(x->c / 8);
-    p.x_tail = reinterpret_cast<const uint8_t*>(x_tail->data); p.tail_stride = x_tail->sw * 2;
+  if (out_tail) {
+    VFI_REQUIRE(O > TC_CMAIN && O <= TC_CMAX && out->c == TC_CMAIN && out_tail->c == O - TC_CMAIN && out_tail->data &&
+                    out->n == x->n && out->h == x->h && out->w == x->w && out_tail->n == x->n && out_tail->h == x->h &&
+                    out_tail->w == x->w && is_plane(out, TC_CMAIN) && is_plane(out_tail, TC_CTAIL),
+                VFI_ERR_UNSUPPORTED,
+                "%s: plane output needs out [B,64,H,W] and out_tail [B,O-64,H,W] as dense channels-last bf16 planes "
+                "(pixel strides 64 and 8 elements)", who);
+    p.out = out->data; p.out_tail = out_tail->data;
+    p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0;
   } else {
-    direct = is_packed_nhwc72(x);
+    VFI_REQUIRE(out->n == x->n && out->c == O && out->h == x->h && out->w == x->w, VFI_ERR_INVALID,
+                "%s: out must be [B,O,H,W]", who);
+    p.out = out->data; p.out_tail = nullptr;
+    p.o_sn = out->sn; p.o_sc = out->sc; p.o_sh = out->sh; p.o_sw = out->sw;
   }
-  const size_t need = direct ? ws_input_off() : dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  if (x_tail) {
+    VFI_REQUIRE(x_tail->data && x->c == TC_CMAIN && x_tail->c <= TC_CTAIL && x_tail->n == x->n && x_tail->h == x->h &&
+                    x_tail->w == x->w && is_plane(x, TC_CMAIN) && is_plane(x_tail, TC_CTAIL),
+                VFI_ERR_UNSUPPORTED,
+                "%s: plane input needs x_main [B,64,H,W] and x_tail [B,<=8,H,W] as dense channels-last bf16 planes "
+                "(pixel strides 64 and 8 elements, pad channels of the tail zero)", who);
+  }
+  const size_t need = x_tail ? ws_main_off() : dcn_tc_workspace_bytes(x->n, x->h, x->w);
   VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
               "%s(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float* bias_ws = reinterpret_cast<float*>(ws + ws_bias_off());
   int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st);
   if (rc) return rc;
-  if (!x_tail) {
-    const uint8_t* xin = reinterpret_cast<const uint8_t*>(x->data);
-    if (!direct) {
-      rc = dcn_tc_pack_input(x, ws + ws_input_off(), st);
-      if (rc) return rc;
-      xin = ws + ws_input_off();
-    }
-    p.x_main = xin; p.main_stride = TC_CPAD * 2; p.n_main = TC_CPAD / 8;
-    p.x_tail = xin; p.tail_stride = TC_CPAD * 2;
+  if (x_tail) {
+    p.x_main = reinterpret_cast<const uint8_t*>(x->data);
+    p.x_tail = reinterpret_cast<const uint8_t*>(x_tail->data);
+  } else {
+    rc = dcn_tc_pack_input(x, ws + ws_main_off(), ws + ws_tail_off(P), st);
+    if (rc) return rc;
+    p.x_main = ws + ws_main_off();
+    p.x_tail = ws + ws_tail_off(P);
   }
+  p.main_stride = TC_CMAIN * 2; p.tail_stride = TC_CTAIL * 2;
   p.offset = offset->data; p.mask = mask->data; p.fused27 = conv27 ? 1 : 0;
   p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
   p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
-  p.wpacked = ws; p.bias = bias_ws; p.out = out->data;
-  p.o_sn = out->sn; p.o_sc = out->sc; p.o_sh = out->sh; p.o_sw = out->sw;
-  p.out_packed = is_packed_nhwc72(out) ? 1 : 0;
+  p.wpacked = ws; p.bias = bias_ws;
   p.B = (int)x->n; p.H = (int)x->h; p.W = (int)x->w; p.O = (int)O;
   p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y;
@@ -673,8 +730,9 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   const size_t smem = sizeof(TcSmem) + 1024;
+  const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
   VFI_DISPATCH(offset->dtype, TO, {
-    VFI_DISPATCH(out->dtype, TOUT, {
+    VFI_DISPATCH(out_dtype, TOUT, {
       if (hq) {
         auto kern = dcn_tc_fwd_kernel<TO, TOUT, true>;
         VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -693,16 +751,16 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight, int weight_dtype,
                const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq, void* workspace,
                size_t workspace_bytes, cudaStream_t st) {
-  return dcn_tc_run(x, nullptr, offset, mask, nullptr, weight, weight_dtype, bias, bias_dtype, out, O, hq, workspace,
-                    workspace_bytes, st, "vfi_dcn_fwd");
+  return dcn_tc_run(x, nullptr, offset, mask, nullptr, weight, weight_dtype, bias, bias_dtype, out, nullptr, O, hq,
+                    workspace, workspace_bytes, st, "vfi_dcn_fwd");
 }
 
 int dcn_tc_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27, const void* weight,
-                     int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                     int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, const vfi_tensor* out_tail,
+                     long long O, bool hq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   VFI_REQUIRE(conv27, VFI_ERR_INVALID, "vfi_dcn_fwd_fused: null conv27");
-  return dcn_tc_run(x_main, x_tail, nullptr, nullptr, conv27, weight, weight_dtype, bias, bias_dtype, out, O, hq, workspace,
-                    workspace_bytes, st, "vfi_dcn_fwd_fused");
+  return dcn_tc_run(x_main, x_tail, nullptr, nullptr, conv27, weight, weight_dtype, bias, bias_dtype, out, out_tail, O, hq,
+                    workspace, workspace_bytes, st, "vfi_dcn_fwd_fused");
 }
 
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st) {

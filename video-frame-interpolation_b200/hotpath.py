@@ -29,29 +29,34 @@ class HotPath:
         self.biases = list(biases)
         self.math = math
         self._streams = None
-        self._tail = None
-        self._tail_key = None
+        self._bufs = None
+        self._bufs_key = None
 
     # ---------------------------------------------------------------------------------------------- device API
     def run(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor,
             convs27: Sequence[torch.Tensor]) -> torch.Tensor:
         if self._fast(frame2, feat):
-            # Tensor-core path with the reference's glue folded away: the warp writes its 3 channels into a 16-byte
-            # "tail" record per pixel, the first DCN layer gathers from (feat, tail) directly (no torch.cat), every layer
-            # reads the raw 27-channel offset_conv output (no chunk/cat/sigmoid) and writes the channel-padded
-            # channels-last image the next layer gathers from.
+            # Tensor-core path with the reference's glue folded away: the warp writes its 3 channels into the 16-byte
+            # tail record of each pixel, the first DCN layer gathers from (feat, tail) directly (no torch.cat), every
+            # layer reads the raw 27-channel offset_conv output (no chunk/cat/sigmoid) and writes the two planes the
+            # next layer gathers from.  Returns ops.Planes (``.to_nchw()`` gives the logical [B,67,H,W] tensor).
             B, C, H, W = feat.shape
             key = (B, H, W, feat.device)
-            if self._tail is None or self._tail_key != key:
-                self._tail = torch.zeros((B, H, W, 8), dtype=torch.bfloat16, device=feat.device)   # pad channels stay 0
-                self._tail_key = key
-            tail = self._tail.permute(0, 3, 1, 2)
-            ops.warp(frame2, flow, out=tail[:, :frame2.shape[1]])
-            x_main, x_tail = feat, tail[:, :frame2.shape[1]]
+            if self._bufs is None or self._bufs_key != key:
+                # ping-pong activation planes, allocated once; tail pad channels of `src` are zeroed once and stay zero
+                self._bufs = (ops.Planes(B, H, W, feat.device, zero_tail=True), ops.Planes(B, H, W, feat.device),
+                              ops.Planes(B, H, W, feat.device))
+                self._bufs_key = key
+            src, ping, pong = self._bufs
+            ops.warp(frame2, flow, out=src.tail_nchw(frame2.shape[1]))
+            math = self.math if self.math != "auto" else "bf16_tc"
+            x_main, x_tail = feat, src.tail_nchw(frame2.shape[1])
+            dst = ping
             for w, b, c27 in zip(self.weights, self.biases, convs27):
-                x_main = ops.deform_conv2d_fused(x_main, x_tail, c27, w, b, math=self.math if self.math != "auto" else "bf16_tc")
-                x_tail = None
-            return x_main
+                y = ops.deform_conv2d_fused(x_main, x_tail, c27, w, b, math=math, out=dst)
+                x_main, x_tail = y.main_nchw, y.tail_nchw()
+                dst = pong if dst is ping else ping
+            return y
         warped = ops.warp(frame2, flow)
         x = torch.cat((feat, warped), dim=1)
         for w, b, c27 in zip(self.weights, self.biases, convs27):
@@ -90,6 +95,8 @@ class HotPath:
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ready)
                 y = self.run(d[0], d[1], d[2], d[3:])
+                if isinstance(y, ops.Planes):
+                    y = y.to_nchw()
                 for t in d:
                     t.record_stream(s_run)
                 done = torch.cuda.Event()

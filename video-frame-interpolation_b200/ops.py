@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import check, desc, dtype_code, ref, require_cuda, stream_handle
 
-__all__ = ["warp", "warp_blend", "deform_conv2d", "deform_conv2d_fused", "dcn_workspace_bytes", "launch_count", "reset_launch_count"]
+__all__ = ["warp", "warp_blend", "deform_conv2d", "deform_conv2d_fused", "Planes", "dcn_workspace_bytes", "launch_count", "reset_launch_count"]
 
 
 def launch_count() -> int:
@@ -100,13 +100,30 @@ def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch
 
 # ------------------------------------------------------------------------------------------------------ DCN
 _MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC, "bf16_tc_hq": _lib.MATH_BF16_TC_HQ}
-PACKED_C = 72   # channel stride of the tensor-core path's activation image
+MAIN_C, TAIL_C = 64, 8   # channels per pixel in the two activation planes of the tensor-core path
 
 
-def packed_buffer(B: int, H: int, W: int, device) -> torch.Tensor:
-    """Uninitialised [B,H,W,72] bf16 buffer.  ``buf.permute(0,3,1,2)[:, :C]`` is the logical NCHW view of a C-channel
-    activation in the layout the tcgen05 DCN kernel reads and writes directly (pad channels must be finite)."""
-    return torch.empty((B, H, W, PACKED_C), dtype=torch.bfloat16, device=device)
+class Planes:
+    """An activation of up to 72 channels in the layout the tcgen05 DCN kernel gathers from and writes: two dense
+    channels-last bf16 buffers, ``main`` [B,H,W,64] (128 B per pixel) and ``tail`` [B,H,W,8] (16 B per pixel, channels
+    64.. and zero padding).  ``main_nchw`` / ``tail_nchw(c)`` are the logical [B,C,H,W] views handed to the C ABI."""
+
+    def __init__(self, B: int, H: int, W: int, device, channels: int = 67, zero_tail: bool = False):
+        self.channels = channels
+        self.main = torch.empty((B, H, W, MAIN_C), dtype=torch.bfloat16, device=device)
+        alloc = torch.zeros if zero_tail else torch.empty
+        self.tail = alloc((B, H, W, TAIL_C), dtype=torch.bfloat16, device=device)
+
+    @property
+    def main_nchw(self) -> torch.Tensor:
+        return self.main.permute(0, 3, 1, 2)
+
+    def tail_nchw(self, c: Optional[int] = None) -> torch.Tensor:
+        return self.tail.permute(0, 3, 1, 2)[:, : (self.channels - MAIN_C if c is None else c)]
+
+    def to_nchw(self) -> torch.Tensor:
+        """Logical [B,channels,H,W] tensor (a copy; for checks and for handing the result to stock PyTorch ops)."""
+        return torch.cat((self.main_nchw, self.tail_nchw()), dim=1)
 
 
 def selftest_umma(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -142,12 +159,9 @@ class _DcnFn(torch.autograd.Function):
         bias_c = None if bias is None else bias.contiguous()
         lib = _lib.load()
         tc = math in (_lib.MATH_BF16_TC, _lib.MATH_BF16_TC_HQ) or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
-        if tc and x.dtype == torch.bfloat16 and O <= PACKED_C:
-            # channel-padded channels-last bf16 [B,H,W,72]: what the next tensor-core layer gathers from without a
-            # layout pass; handed back as the logical [B,O,H,W] view (strides (H*W*72, 1, W*72, 72))
-            out = packed_buffer(B, H, W, dev).permute(0, 3, 1, 2)[:, :O]
-        else:
-            out = torch.empty((B, O, H, W), dtype=x.dtype, device=dev)
+        # tensor-core results of low-precision inputs come back channels_last (what cuDNN wants next); fp32 stays NCHW
+        fmt = torch.channels_last if (tc and x.dtype != torch.float32) else torch.contiguous_format
+        out = torch.empty((B, O, H, W), dtype=x.dtype, device=dev, memory_format=fmt)
         nbytes = int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, math))
         ws = _workspace(dev, nbytes)
         with torch.cuda.device(dev):
@@ -195,27 +209,33 @@ class _DcnFn(torch.autograd.Function):
 
 
 def deform_conv2d_fused(x_main: torch.Tensor, x_tail: Optional[torch.Tensor], conv27: torch.Tensor, weight: torch.Tensor,
-                        bias: Optional[torch.Tensor] = None, math: str = "bf16_tc") -> torch.Tensor:
+                        bias: Optional[torch.Tensor] = None, math: str = "bf16_tc", out: Optional[Planes] = None) -> Planes:
     """Hot-path form of the DCNv2 forward (inference only, tensor-core math): consumes the raw 27-channel
-    ``offset_conv`` output (the chunk/cat/sigmoid of ema_vfi.py:57-59 happens inside the kernel) and, optionally, the
-    input as two channels-last bf16 pieces ``x_main`` [B,64,H,W] + ``x_tail`` [B,<=8,H,W] (the torch.cat of
-    ema_vfi.py:134 never materialises).  Returns the logical [B,O,H,W] view of a channel-padded channels-last buffer."""
+    ``offset_conv`` output (the chunk/cat/sigmoid of ema_vfi.py:57-59 happens inside the kernel) and the input as
+    planes -- ``x_main`` [B,64,H,W] + ``x_tail`` [B,<=8,H,W], channels-last bf16, i.e. feat and the warped frame before
+    the torch.cat of ema_vfi.py:134, or the :class:`Planes` a previous layer produced.  ``x_tail=None``: ``x_main`` is
+    any [B,C,H,W] tensor.  Returns :class:`Planes` (what the next layer reads without a layout pass)."""
     dev = require_cuda(x_main, x_tail, conv27, weight, bias)
     if math not in ("auto", "bf16_tc", "bf16_tc_hq"):
         raise NotImplementedError("deform_conv2d_fused implements the tensor-core math modes only")
     B, _, H, W = x_main.shape
     O = weight.shape[0]
+    if not (MAIN_C < O <= MAIN_C + TAIL_C):
+        raise NotImplementedError("deform_conv2d_fused writes planes: 64 < O <= 72")
     lib = _lib.load()
     weight_c = weight.contiguous()
     bias_c = None if bias is None else bias.contiguous()
-    out = packed_buffer(B, H, W, dev).permute(0, 3, 1, 2)[:, :O]
-    ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, x_main.shape[1], O, H, W, _MATH[math])))
+    if out is None:
+        out = Planes(B, H, W, dev, channels=O)
+    ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, x_main.shape[1], O, H, W, _MATH[math]))
+                    if x_tail is None else int(lib.vfi_dcn_packed_weight_bytes()) + 512)
     with torch.cuda.device(dev):
         check(lib.vfi_dcn_fwd_fused(ref(desc(x_main)), ref(desc(x_tail)) if x_tail is not None else None,
                                     ref(desc(conv27)), weight_c.data_ptr(), dtype_code(weight_c.dtype),
                                     None if bias_c is None else bias_c.data_ptr(),
-                                    dtype_code(bias_c.dtype) if bias_c is not None else 0, ref(desc(out)), O, _MATH[math],
-                                    ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_fwd_fused")
+                                    dtype_code(bias_c.dtype) if bias_c is not None else 0, ref(desc(out.main_nchw)),
+                                    ref(desc(out.tail_nchw(O - MAIN_C))), O, _MATH[math], ws.data_ptr(), ws.numel(),
+                                    stream_handle(dev)), "vfi_dcn_fwd_fused")
     return out
 
 
