@@ -19,16 +19,18 @@
 //   accumulator : 2 x (128 lanes x 80 columns) in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   tile        : 8 rows x 16 columns of output pixels (keeps the gather footprint, ~75 KB at sigma = 1.5 px, inside L1)
 //
-// Warp roles (672 threads, one persistent CTA per SM):
-//   warps 0-15  producers in two groups of 8 that alternate over the K blocks (one group's gather latency hides behind
-//               the other's lerp/store work).  Per tile all 16 warps first compute the 9 x 128 tap geometries (corner
-//               pixel indices + mask-folded weights; optionally straight from the 27-channel offset_conv output with the
-//               sigmoid folded in).  Main blocks: each lane owns one 16-byte chunk of four rows; the 8 lanes of a row
-//               read one aligned 128 B line per corner.  Tail blocks: each lane owns one row, warps split the taps.
-//               4 corner loads of 16 B (read-only path), packed HFMA2.BF16 lerp (fp32 in HQ mode), one 16-byte store
-//               into the swizzled A stage; fence.proxy.async; one mbarrier arrive per warp.
-//   warp 16     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
-//   warps 17-20 epilogue: tcgen05.ld the accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
+// Warp roles (928 threads, one persistent CTA per SM, a contiguous run of tiles per CTA):
+//   warps 0-23  producers in three groups of 8; group g produces the K blocks n with n % 3 == g into pipeline stage g, so
+//               three blocks are being gathered at once and one group's load latency hides behind the others' lerp/store
+//               work.  Main blocks: each lane owns one 16-byte chunk of four rows; the 8 lanes of a row read one aligned
+//               128 B line per corner.  Tail blocks: each lane owns one row, warps split the taps.  4 corner loads of
+//               16 B (read-only path), packed HFMA2.BF16 lerp (fp32 in HQ mode), one 16-byte store into the swizzled A
+//               stage; fence.proxy.async; one mbarrier arrive per warp.
+//   warp 24     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
+//   warps 25-28 geometry + epilogue: compute tile i+1's 9 x 128 tap geometries (corner pixel index + mask-folded weights;
+//               optionally straight from the 27-channel offset_conv output with the sigmoid folded in) into the other
+//               half of a double buffer and prefetch its footprint into L2 while the producers gather tile i; then
+//               tcgen05.ld tile i's accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
 #include "common.cuh"
 
 namespace vfi {
@@ -43,9 +45,11 @@ constexpr int TC_KBLOCKS = 11;                       // 128-byte swizzle atoms a
 constexpr int TC_A_BYTES = TC_M * 128;               // 16384
 constexpr int TC_B_BYTES = TC_N * 128;               // 10240
 constexpr int TC_STAGES = 3;
-constexpr int TC_PRODUCER_WARPS = 16;                // two groups of 8 alternating over K blocks
+constexpr int TC_GROUPS = 3;                         // producer groups; group g fills stage g (K blocks n with n % 3 == g)
 constexpr int TC_GROUP_WARPS = 8;
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4) * 32;   // + MMA issuer warp + 4 epilogue warps = 672
+constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;   // 24
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4) * 32;   // + MMA issuer warp + 4 geometry/epilogue warps = 928
+static_assert(TC_GROUPS == TC_STAGES, "each producer group owns one pipeline stage");
 constexpr int TC_TMEM_COLS = 256;                    // two accumulators at column 0 and 128
 constexpr int TC_ACC_STRIDE = 128;
 
@@ -101,9 +105,6 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted in bytes on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -229,16 +230,24 @@ struct TcParams {
   int tiles_x, tiles_y, num_tiles;
 };
 
-// Tap geometry, one entry per (tap, tile row).  Row 9 of both arrays is all zeros: the zero-padding chunk of the last
-// K block is produced by the ordinary code path with "tap 9".
+// Tap geometry, one entry per (tap, tile row), double buffered across tiles: the four epilogue warps compute tile
+// i+1's entries while the producers gather tile i.  Row 9 of every buffer is all zeros: the zero-padding chunk of the
+// last K block is produced by the ordinary code path with "tap 9".
+//   pixf : bits 0..29 flattened pixel index (b*H*W + y*W + x) of corner 00 clamped into the image; bit 30: corner 01 is
+//          one pixel to the right (else same pixel); bit 31: corners 10/11 are one row below (else same row)
+//   w    : bilinear weight x modulation mask of corners 00, 01, 10, 11 (0 for corners outside the image, dead samples and
+//          padding rows): two bf16x2 words on the fast path, four fp32 words on the HQ path
+template <bool HQ> struct TcGeoW { using type = uint2; };
+template <> struct TcGeoW<true> { using type = uint4; };
+
+template <bool HQ>
 struct __align__(1024) TcSmem {
   uint8_t a[TC_STAGES][TC_A_BYTES];
   uint8_t b[TC_STAGES][TC_B_BYTES];
-  int4 geo_pix[10][TC_M];      // flattened pixel index (b*H*W + y*W + x) of corners 00, 01, 10, 11, clamped into the image
-  uint4 geo_w[10][TC_M];       // bilinear weight x modulation mask per corner (0 for corners outside the image, dead
-                               // samples, padding rows): bf16x2 splat (w, w) on the fast path, fp32 bits on the HQ path
+  uint32_t geo_pix[2][10][TC_M];
+  typename TcGeoW<HQ>::type geo_w[2][10][TC_M];
   float bias[TC_N];
-  unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
+  unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], geo_full[2], geo_empty[2];
   uint32_t tmem_base;
 };
 
@@ -248,79 +257,60 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
 }
 __device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
 
-// Two channels of the modulated bilinear sample.  HQ: fp32 arithmetic, one rounding at the end.  Fast: packed
-// HMUL2/HFMA2.BF16 (each step rounds to bf16; measured cost on the layer output: 2.8e-3 vs 1.4e-3 max-rel).
-template <bool HQ>
-__device__ __forceinline__ uint32_t lerp_pair(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const uint4& w) {
-  if constexpr (HQ) {
+// One 16-byte chunk (8 channels) of the modulated bilinear sample from its four corner chunks.
+// Fast: packed HMUL2/HFMA2.BF16 (every step rounds to bf16; measured cost on the layer output: 2.8e-3 vs 1.4e-3
+// max-rel).  HQ: fp32 arithmetic, one rounding at the end.
+__device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const uint2& w) {
+  const __nv_bfloat162 w0 = as_bf162(__byte_perm(w.x, 0, 0x1010)), w1 = as_bf162(__byte_perm(w.x, 0, 0x3232));
+  const __nv_bfloat162 w2 = as_bf162(__byte_perm(w.y, 0, 0x1010)), w3 = as_bf162(__byte_perm(w.y, 0, 0x3232));
+  auto f = [&](uint32_t va, uint32_t vb, uint32_t vc, uint32_t vd) {
+    __nv_bfloat162 r = __hmul2(w0, as_bf162(va));
+    r = __hfma2(w1, as_bf162(vb), r);
+    r = __hfma2(w2, as_bf162(vc), r);
+    r = __hfma2(w3, as_bf162(vd), r);
+    return *reinterpret_cast<uint32_t*>(&r);
+  };
+  return make_uint4(f(a.x, b.x, c.x, d.x), f(a.y, b.y, c.y, d.y), f(a.z, b.z, c.z, d.z), f(a.w, b.w, c.w, d.w));
+}
+__device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const uint4& w) {
+  const float w0 = __uint_as_float(w.x), w1 = __uint_as_float(w.y), w2 = __uint_as_float(w.z), w3 = __uint_as_float(w.w);
+  auto f = [&](uint32_t va, uint32_t vb, uint32_t vc, uint32_t vd) {
     float al, ah, bl, bh, cl, ch, dl, dh;
-    unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch); unpack2(d, dl, dh);
-    const float w0 = __uint_as_float(w.x), w1 = __uint_as_float(w.y), w2 = __uint_as_float(w.z), w3 = __uint_as_float(w.w);
+    unpack2(va, al, ah); unpack2(vb, bl, bh); unpack2(vc, cl, ch); unpack2(vd, dl, dh);
     float lo = fmaf(w3, dl, fmaf(w2, cl, fmaf(w1, bl, w0 * al)));
     float hi = fmaf(w3, dh, fmaf(w2, ch, fmaf(w1, bh, w0 * ah)));
     __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&r);
-  } else {
-    __nv_bfloat162 r = __hmul2(as_bf162(w.x), as_bf162(a));
-    r = __hfma2(as_bf162(w.y), as_bf162(b), r);
-    r = __hfma2(as_bf162(w.z), as_bf162(c), r);
-    r = __hfma2(as_bf162(w.w), as_bf162(d), r);
-    return *reinterpret_cast<uint32_t*>(&r);
-  }
-}
-template <bool HQ>
-__device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const uint4& w) {
-  uint4 o;
-  o.x = lerp_pair<HQ>(a.x, b.x, c.x, d.x, w);
-  o.y = lerp_pair<HQ>(a.y, b.y, c.y, d.y, w);
-  o.z = lerp_pair<HQ>(a.z, b.z, c.z, d.z, w);
-  o.w = lerp_pair<HQ>(a.w, b.w, c.w, d.w, w);
-  return o;
+  };
+  return make_uint4(f(a.x, b.x, c.x, d.x), f(a.y, b.y, c.y, d.y), f(a.z, b.z, c.z, d.z), f(a.w, b.w, c.w, d.w));
 }
 
-template <bool HQ>
-__device__ __forceinline__ uint32_t pack_weight_word(float w) {
-  if constexpr (HQ) return __float_as_uint(w);
-  __nv_bfloat162 r = __float2bfloat162_rn(w);
-  return *reinterpret_cast<uint32_t*>(&r);
+__device__ __forceinline__ void store_geo_w(uint2& dst, float w0, float w1, float w2, float w3) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(w0, w1), b = __floats2bfloat162_rn(w2, w3);
+  dst = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+__device__ __forceinline__ void store_geo_w(uint4& dst, float w0, float w1, float w2, float w3) {
+  dst = make_uint4(__float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), __float_as_uint(w3));
 }
 
-template <typename TO, bool HQ>
-__device__ __forceinline__ void tc_make_geo(const TcParams& p, int b, int y, int x, int k, int4& pix, uint4& wq) {
-  const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
-  const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
-  float dy, dx, mk;
-  if (p.fused27) {
-    // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets, the middle third is the
-    // pre-sigmoid mask.  The sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would.
-    const int j0 = 2 * k, j1 = 2 * k + 1;
-    dy = to_f32<TO>(__ldg(off + (j0 < 9 ? j0 : j0 + 9) * p.f_sc));
-    dx = to_f32<TO>(__ldg(off + (j1 < 9 ? j1 : j1 + 9) * p.f_sc));
-    const float t = to_f32<TO>(__ldg(msk + (9 + k) * p.m_sc));
-    mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + expf(-t))));
-  } else {
-    dy = to_f32<TO>(__ldg(off + (2 * k) * p.f_sc));
-    dx = to_f32<TO>(__ldg(off + (2 * k + 1) * p.f_sc));
-    mk = to_f32<TO>(__ldg(msk + k * p.m_sc));
-  }
+// Sampling geometry of tap k at output pixel (y, x) from its offsets (dy, dx) and modulation mk.
+template <typename GW>
+__device__ __forceinline__ void tc_geo_entry(int H, int W, int base, int y, int x, int k, float dy, float dx, float mk,
+                                             uint32_t& pixf, GW& wq) {
   float py = (float)(y - 1 + k / 3) + dy;
   float px = (float)(x - 1 + k % 3) + dx;
-  bool live = (py > -1.0f) && (py < (float)p.H) && (px > -1.0f) && (px < (float)p.W);
+  const bool live = (py > -1.0f) && (py < (float)H) && (px > -1.0f) && (px < (float)W);
   if (!live) { py = -2.0f; px = -2.0f; mk = 0.0f; }
-  float fy = floorf(py), fx = floorf(px);
-  int y0 = (int)fy, x0 = (int)fx;
-  float lh = py - fy, lw = px - fx, hh = 1.0f - lh, hw = 1.0f - lw;
-  bool r0 = (unsigned)y0 < (unsigned)p.H, r1 = (unsigned)(y0 + 1) < (unsigned)p.H;
-  bool c0 = (unsigned)x0 < (unsigned)p.W, c1 = (unsigned)(x0 + 1) < (unsigned)p.W;
-  int cy0 = min(max(y0, 0), p.H - 1), cy1 = min(max(y0 + 1, 0), p.H - 1);
-  int cx0 = min(max(x0, 0), p.W - 1), cx1 = min(max(x0 + 1, 0), p.W - 1);
-  int base = b * p.H * p.W;
-  pix.x = base + cy0 * p.W + cx0; pix.y = base + cy0 * p.W + cx1;
-  pix.z = base + cy1 * p.W + cx0; pix.w = base + cy1 * p.W + cx1;
-  wq.x = pack_weight_word<HQ>((r0 && c0) ? hh * hw * mk : 0.0f);
-  wq.y = pack_weight_word<HQ>((r0 && c1) ? hh * lw * mk : 0.0f);
-  wq.z = pack_weight_word<HQ>((r1 && c0) ? lh * hw * mk : 0.0f);
-  wq.w = pack_weight_word<HQ>((r1 && c1) ? lh * lw * mk : 0.0f);
+  const float fy = floorf(py), fx = floorf(px);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const float lh = py - fy, lw = px - fx, hh = 1.0f - lh, hw = 1.0f - lw;
+  const bool r0 = (unsigned)y0 < (unsigned)H, r1 = (unsigned)(y0 + 1) < (unsigned)H;
+  const bool c0 = (unsigned)x0 < (unsigned)W, c1 = (unsigned)(x0 + 1) < (unsigned)W;
+  const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+  const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+  pixf = (uint32_t)(base + cy0 * W + cx0) | ((uint32_t)(cx1 - cx0) << 30) | ((uint32_t)(cy1 - cy0) << 31);
+  store_geo_w(wq, (r0 && c0) ? hh * hw * mk : 0.0f, (r0 && c1) ? hh * lw * mk : 0.0f, (r1 && c0) ? lh * hw * mk : 0.0f,
+              (r1 && c1) ? lh * lw * mk : 0.0f);
 }
 
 // tile index -> (batch, top row, left column)
@@ -332,14 +322,22 @@ __device__ __forceinline__ void tile_origin(const TcParams& p, int tile, int& b,
   x0 = (t % p.tiles_x) * TC_TW;
 }
 
-__device__ __forceinline__ uint4 ldg16(const uint8_t* base, int pix, uint32_t stride) {
-  return __ldg(reinterpret_cast<const uint4*>(base + (unsigned long long)(unsigned)pix * stride));   // IMAD.WIDE.U32
+// The four corner chunks of one (row, tap) item.  `base` already includes the lane's chunk offset.
+__device__ __forceinline__ void gather4(const uint8_t* base, uint32_t stride, uint32_t row_stride, uint32_t pixf, uint4* v) {
+  const uint8_t* a00 = base + (unsigned long long)(pixf & 0x3fffffffu) * stride;      // IMAD.WIDE.U32
+  const uint32_t dx = (pixf & 0x40000000u) ? stride : 0u;
+  const uint32_t dy = (pixf & 0x80000000u) ? row_stride : 0u;
+  const uint8_t* a10 = a00 + dy;
+  v[0] = __ldg(reinterpret_cast<const uint4*>(a00));
+  v[1] = __ldg(reinterpret_cast<const uint4*>(a00 + dx));
+  v[2] = __ldg(reinterpret_cast<const uint4*>(a10));
+  v[3] = __ldg(reinterpret_cast<const uint4*>(a10 + dx));
 }
-
 template <typename TO, typename TOUT, bool HQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParams p) {
+  using GW = typename TcGeoW<HQ>::type;
   extern __shared__ uint8_t smem_raw[];
-  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
+  TcSmem<HQ>& s = *reinterpret_cast<TcSmem<HQ>*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -350,76 +348,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
       mbar_init(smem_u32(&s.acc_empty[i]), 4);                  // four epilogue warps
+      mbar_init(smem_u32(&s.geo_full[i]), 4);                   // four geometry (= epilogue) warps
+      mbar_init(smem_u32(&s.geo_empty[i]), TC_PRODUCER_WARPS);  // every producer warp
     }
     fence_barrier_init();
   }
   if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
   if (tid < TC_N) s.bias[tid] = p.bias[tid];
-  if (tid < TC_M) { s.geo_pix[9][tid] = make_int4(0, 0, 0, 0); s.geo_w[9][tid] = make_uint4(0, 0, 0, 0); }
+  if (tid < 2 * TC_M) { s.geo_pix[tid >> 7][9][tid & 127] = 0u; s.geo_w[tid >> 7][9][tid & 127] = GW{}; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Contiguous run of tiles per CTA (raster order): consecutive tiles are horizontal neighbours, so roughly half of a
+  // tile's gather footprint is still in this SM's L1 from the previous tile.
+  const int tiles_base = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;
+  const int my_tiles = tiles_base + ((int)blockIdx.x < tiles_rem ? 1 : 0);
+  const int tile0 = (int)blockIdx.x * tiles_base + min((int)blockIdx.x, tiles_rem);
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================================================================== A-operand producers
-    // Two groups of 8 warps alternate over the CTA's global K-block sequence n = tile_iter * 11 + kb (group = n & 1), so
-    // one group's gather latency overlaps the other group's lerp/store work.  stage = n % 3, phase = (n / 3) & 1.
+    // Three groups of 8 warps rotate over the CTA's global K-block sequence n = tile_iter * 11 + kb: group g produces the
+    // blocks with n % 3 == g into stage g (phase = (n / 3) & 1), so up to three K blocks are being gathered at once and
+    // one group's load latency hides behind the others' lerp/store work.
     const int group = warp >> 3, wig = warp & 7;
-    // main blocks: lane = (row-in-quad rsub, chunk j); a pass covers rows 32*pass + 4*wig + rsub
+    // main blocks: lane = (row-in-quad rsub, chunk j); pass q covers rows 32*q + 4*wig + rsub
     const int rsub = lane >> 3, j = lane & 7;
-    const int r_main = 4 * wig + rsub;                                    // + 32 * pass
+    const int r_main = 4 * wig + rsub;
     const uint32_t a_off_main = (uint32_t)r_main * 128 + ((uint32_t)(j ^ (r_main & 7)) << 4);   // + 4096 * pass
     const uint8_t* src_main = p.x_main + j * 16;
-    // tail blocks: lane = row within a 32-row pass
+    const uint32_t main_row = p.main_stride * (uint32_t)p.W, tail_row = p.tail_stride * (uint32_t)p.W;
+    uint8_t* a_stage = &s.a[group][0];
+    const uint32_t full_bar = smem_u32(&s.full[group]), empty_bar = smem_u32(&s.empty[group]);
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      int b, ty0, tx0;
-      tile_origin(p, tile, b, ty0, tx0);
-      named_bar_sync(1, TC_PRODUCER_WARPS * 32);        // every producer is done reading the previous tile's geometry
-      for (int i = tid; i < 9 * TC_M; i += TC_PRODUCER_WARPS * 32) {
-        const int k = i / TC_M, r = i % TC_M;
-        const int y = ty0 + r / TC_TW, x = tx0 + r % TC_TW;
-        int4 pix = make_int4(0, 0, 0, 0);
-        uint4 wq = make_uint4(0, 0, 0, 0);
-        if (y < p.H && x < p.W) tc_make_geo<TO, HQ>(p, b, y, x, k, pix, wq);
-        s.geo_pix[k][r] = pix;
-        s.geo_w[k][r] = wq;
-      }
-      named_bar_sync(1, TC_PRODUCER_WARPS * 32);
+      const int gb = it & 1;
+      mbar_wait(smem_u32(&s.geo_full[gb]), (uint32_t)(it >> 1) & 1u);      // this tile's geometry has been written
       const int n0 = it * TC_KBLOCKS;
-      for (int kb = (n0 + group) & 1; kb < TC_KBLOCKS; kb += 2) {   // blocks of this tile whose global index has parity `group`
-        const int n = n0 + kb;
-        const int stage = n % TC_STAGES;
-        const uint32_t phase = (uint32_t)(n / TC_STAGES) & 1u;
-        mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1);
+      int kb = group - n0 % TC_GROUPS;
+      if (kb < 0) kb += TC_GROUPS;
+      for (; kb < TC_KBLOCKS; kb += TC_GROUPS) {        // blocks of this tile with (n0 + kb) % 3 == group
+        const uint32_t phase = (uint32_t)((n0 + kb) / TC_STAGES) & 1u;
+        mbar_wait(empty_bar, phase ^ 1);
         if (wig == 0 && lane == 0) {
-          mbar_arrive_expect_tx(smem_u32(&s.full[stage]), TC_B_BYTES);
-          bulk_g2s(smem_u32(&s.b[stage][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, smem_u32(&s.full[stage]));
+          mbar_arrive_expect_tx(full_bar, TC_B_BYTES);
+          bulk_g2s(smem_u32(&s.b[group][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, full_bar);
         }
-        uint8_t* a_stage = &s.a[stage][0];
         if (kb < 9) {
           // ---- the 64 main channels of tap kb: one aligned 128 B line per (row, corner), 8 lanes each
-          const int4* gp = &s.geo_pix[kb][r_main];
-          const uint4* gw = &s.geo_w[kb][r_main];
-          uint8_t* dst = a_stage + a_off_main;
+          const uint32_t* gp = &s.geo_pix[gb][kb][r_main];
+          const GW* gw = &s.geo_w[gb][kb][r_main];
 #pragma unroll
           for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4], wq[2];
+            uint4 v[2][4];
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-              const int pass = batch * 2 + pp;
-              const int4 pix = gp[pass * 32];
-              wq[pp] = gw[pass * 32];
-              v[pp][0] = ldg16(src_main, pix.x, p.main_stride);
-              v[pp][1] = ldg16(src_main, pix.y, p.main_stride);
-              v[pp][2] = ldg16(src_main, pix.z, p.main_stride);
-              v[pp][3] = ldg16(src_main, pix.w, p.main_stride);
-            }
+            for (int q = 0; q < 2; ++q) gather4(src_main, p.main_stride, main_row, gp[(batch * 2 + q) * 32], v[q]);
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp)
-              *reinterpret_cast<uint4*>(dst + (batch * 2 + pp) * 4096) = lerp_chunk<HQ>(v[pp][0], v[pp][1], v[pp][2], v[pp][3], wq[pp]);
+            for (int q = 0; q < 2; ++q)
+              *reinterpret_cast<uint4*>(a_stage + a_off_main + (batch * 2 + q) * 4096) =
+                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], gw[(batch * 2 + q) * 32]);
           }
         } else if (kb == 9) {
           // ---- tails of taps 0..7: warp wig owns tap wig (chunk wig), lanes run over rows so neighbouring pixels' 16 B
@@ -427,38 +413,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
           const int tap = wig;
 #pragma unroll
           for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4], wq[2];
+            uint4 v[2][4];
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-              const int r = (batch * 2 + pp) * 32 + lane;
-              const int4 pix = s.geo_pix[tap][r];
-              wq[pp] = s.geo_w[tap][r];
-              v[pp][0] = ldg16(p.x_tail, pix.x, p.tail_stride);
-              v[pp][1] = ldg16(p.x_tail, pix.y, p.tail_stride);
-              v[pp][2] = ldg16(p.x_tail, pix.z, p.tail_stride);
-              v[pp][3] = ldg16(p.x_tail, pix.w, p.tail_stride);
-            }
+            for (int q = 0; q < 2; ++q)
+              gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][tap][(batch * 2 + q) * 32 + lane], v[q]);
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-              const int r = (batch * 2 + pp) * 32 + lane;
+            for (int q = 0; q < 2; ++q) {
+              const int r = (batch * 2 + q) * 32 + lane;
               *reinterpret_cast<uint4*>(a_stage + r * 128 + ((tap ^ (r & 7)) << 4)) =
-                  lerp_chunk<HQ>(v[pp][0], v[pp][1], v[pp][2], v[pp][3], wq[pp]);
+                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], s.geo_w[gb][tap][r]);
             }
           }
         } else if (wig < 4) {
           // ---- tail of tap 8 (chunk 0) and the zero chunk 1 of the last UMMA_K step: four warps, one row per lane
           const int r = wig * 32 + lane;
-          const int4 pix = s.geo_pix[8][r];
-          const uint4 wq = s.geo_w[8][r];
-          const uint4 v0 = ldg16(p.x_tail, pix.x, p.tail_stride), v1 = ldg16(p.x_tail, pix.y, p.tail_stride);
-          const uint4 v2 = ldg16(p.x_tail, pix.z, p.tail_stride), v3 = ldg16(p.x_tail, pix.w, p.tail_stride);
-          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk<HQ>(v0, v1, v2, v3, wq);
+          uint4 v[4];
+          gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][8][r], v);
+          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk(v[0], v[1], v[2], v[3], s.geo_w[gb][8][r]);
           *reinterpret_cast<uint4*>(a_stage + r * 128 + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.full[stage]));
+        if (lane == 0) mbar_arrive(full_bar);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s.geo_empty[gb]));   // this warp no longer reads geometry buffer gb
     }
   } else if (warp == TC_PRODUCER_WARPS) {
     // =========================================================================== MMA issuer (one lane)
@@ -487,14 +466,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     }
     __syncwarp();
   } else {
-    // =========================================================================== epilogue
+    // =========================================================================== geometry + epilogue (4 warps)
     const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
-    const int row = quad * 32 + lane;
+    const int row = quad * 32 + lane;                    // tile row = TMEM lane = geometry row of this thread
     uint32_t acc = 0, acc_phase[2] = {0, 0};
-    for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+
+    // geometry of tile index `it` (this CTA's numbering) into buffer it & 1: this thread's row, all 9 taps
+    auto make_geometry = [&](int it) {
+      const int gb = it & 1;
+      mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old contents
       int b, ty0, tx0;
-      tile_origin(p, tile, b, ty0, tx0);
+      tile_origin(p, tile0 + it, b, ty0, tx0);
+      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
+      {
+        // pull the tile's nominal gather footprint (tile + 2 px halo: 12 x 20 pixels) towards L2 while the producers are
+        // still busy with the previous tile, so that their compulsory L1 misses find the lines in L2, not in DRAM
+        const int fy = ty0 - 2 + row / 20, fx = tx0 - 2 + row % 20;
+        const int fy2 = ty0 - 2 + (row + 128) / 20, fx2 = tx0 - 2 + (row + 128) % 20;
+        if (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x_main + (size_t)((b * p.H + fy) * p.W + fx) * p.main_stride));
+        if (row + 128 < 240 && fy2 >= 0 && fy2 < p.H && fx2 >= 0 && fx2 < p.W)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x_main + (size_t)((b * p.H + fy2) * p.W + fx2) * p.main_stride));
+      }
+      if (y < p.H && x < p.W) {
+        const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
+        const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
+        const int base = b * p.H * p.W;
+#pragma unroll
+        for (int k0 = 0; k0 < 9; k0 += 3) {              // three taps at a time: nine loads in flight, few registers
+          TO rdy[3], rdx[3], rmk[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = k0 + i, j0 = 2 * k, j1 = 2 * k + 1;
+            if (p.fused27) {
+              // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets (tap k uses channels 2k and
+              // 2k+1 of their concatenation), the middle third is the pre-sigmoid mask
+              rdy[i] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * p.f_sc);
+              rdx[i] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * p.f_sc);
+              rmk[i] = __ldg(msk + (9 + k) * p.m_sc);
+            } else {
+              rdy[i] = __ldg(off + j0 * p.f_sc);
+              rdx[i] = __ldg(off + j1 * p.f_sc);
+              rmk[i] = __ldg(msk + k * p.m_sc);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = k0 + i;
+            float mk = to_f32<TO>(rmk[i]);
+            // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
+            if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
+            uint32_t pixf;
+            GW wq;
+            tc_geo_entry<GW>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[i]), to_f32<TO>(rdx[i]), mk, pixf, wq);
+            s.geo_pix[gb][k][row] = pixf;
+            s.geo_w[gb][k][row] = wq;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { s.geo_pix[gb][k][row] = 0u; s.geo_w[gb][k][row] = GW{}; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
+    };
+
+    if (my_tiles > 0) make_geometry(0);
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) make_geometry(it + 1);      // overlaps the producers' work on tile `it`
+      int b, ty0, tx0;
+      tile_origin(p, tile0 + it, b, ty0, tx0);
       mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
@@ -729,7 +770,7 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   VFI_CUDA(cudaGetDevice(&dev));
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  const size_t smem = sizeof(TcSmem) + 1024;
+  const size_t smem = (hq ? sizeof(TcSmem<true>) : sizeof(TcSmem<false>)) + 1024;
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
   VFI_DISPATCH(offset->dtype, TO, {
     VFI_DISPATCH(out_dtype, TOUT, {
