@@ -106,6 +106,23 @@ def test_warp_strided_and_channels_last_inputs():
     assert maxabs(out2, oracle.warp_fwd(src[..., :63].numpy(), flow[..., :63].numpy())) <= 1e-5
 
 
+def test_warp_into_tail_plane_records():
+    """bf16 warp written straight into the 16-byte tail records the tensor-core DCN gathers from (no torch.cat)."""
+    from vfi_b200 import ops
+
+    g = torch.Generator().manual_seed(15)
+    src = torch.randn(2, 3, 40, 64, generator=g).to(torch.bfloat16)
+    flow = (5 * torch.randn(2, 2, 40, 64, generator=g)).to(torch.bfloat16)
+    ref = oracle.warp_fwd(src.float().numpy(), flow.float().numpy())
+    pl = ops.Planes(2, 40, 64, DEV)
+    pl.tail.fill_(7.0)                                            # garbage: the kernel must overwrite pad channels with 0
+    out = vfi_b200.warp(src.to(DEV), flow.to(DEV), out=pl.tail_nchw(3))
+    assert out.data_ptr() == pl.tail.data_ptr()
+    assert relerr(pl.tail_nchw(3), ref) <= 1e-2
+    assert float(pl.tail[..., 3:].abs().max()) == 0.0
+    assert maxabs(pl.tail_nchw(3), vfi_b200.warp(src.to(DEV), flow.to(DEV))) == 0.0   # same values as the planar kernel
+
+
 def test_warp_empty_batch_and_errors():
     out = vfi_b200.warp(torch.zeros(0, 3, 8, 8, device=DEV), torch.zeros(0, 2, 8, 8, device=DEV))
     assert out.shape == (0, 3, 8, 8)

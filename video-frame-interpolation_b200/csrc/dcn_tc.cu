@@ -19,7 +19,7 @@
 //   accumulator : 2 x (128 lanes x 80 columns) in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 //   tile        : 8 rows x 16 columns of output pixels (keeps the gather footprint, ~75 KB at sigma = 1.5 px, inside L1)
 //
-// Warp roles (928 threads, one persistent CTA per SM, a contiguous run of tiles per CTA):
+// Warp roles (928 threads, one persistent CTA per SM, tiles dealt round-robin):
 //   warps 0-23  producers in three groups of 8; group g produces the K blocks n with n % 3 == g into pipeline stage g, so
 //               three blocks are being gathered at once and one group's load latency hides behind the others' lerp/store
 //               work.  Main blocks: each lane owns one 16-byte chunk of four rows; the 8 lanes of a row read one aligned
@@ -360,11 +360,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
-  // Contiguous run of tiles per CTA (raster order): consecutive tiles are horizontal neighbours, so roughly half of a
-  // tile's gather footprint is still in this SM's L1 from the previous tile.
-  const int tiles_base = p.num_tiles / (int)gridDim.x, tiles_rem = p.num_tiles % (int)gridDim.x;
-  const int my_tiles = tiles_base + ((int)blockIdx.x < tiles_rem ? 1 : 0);
-  const int tile0 = (int)blockIdx.x * tiles_base + min((int)blockIdx.x, tiles_rem);
+  // Tiles are dealt round-robin: at any moment the 148 CTAs work on 148 neighbouring tiles, so the halo lines two tiles
+  // share are fetched from DRAM once and found in L2 by the neighbour.  (A contiguous run per CTA was measured: no L1
+  // gain, +70% DRAM reads because a tile row's halo is evicted from L2 before the CTA comes back one tile row later.)
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================================================================== A-operand producers
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
       const int gb = it & 1;
       mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old contents
       int b, ty0, tx0;
-      tile_origin(p, tile0 + it, b, ty0, tx0);
+      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
       {
         // pull the tile's nominal gather footprint (tile + 2 px halo: 12 x 20 pixels) towards L2 while the producers are
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     for (int it = 0; it < my_tiles; ++it) {
       if (it + 1 < my_tiles) make_geometry(it + 1);      // overlaps the producers' work on tile `it`
       int b, ty0, tx0;
-      tile_origin(p, tile0 + it, b, ty0, tx0);
+      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;

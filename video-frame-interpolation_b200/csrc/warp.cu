@@ -144,6 +144,55 @@ __global__ void __launch_bounds__(256) warp_fwd_kernel(const WarpParams p) {
   }
 }
 
+// Record output: out is a channels-last bf16 "tail plane" (unit channel stride, 8 elements = 16 B per pixel, dense
+// rows), i.e. the tail input of the tensor-core DCN kernel.  One thread = 4 consecutive pixels: two 8-byte flow loads,
+// 4 x C x 4 independent gathers in flight, four 16-byte record stores (channels >= C written as zeros, so the buffer needs
+// no pre-clearing).  Removes the torch.cat of ema_vfi.py:134 without paying for partial-sector writes.
+template <typename TF, int CT>
+__global__ void __launch_bounds__(256) warp_fwd_rec_kernel(const WarpParams p) {
+  const int Wv = p.W / 4;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)p.B * p.H * Wv;
+  if (idx >= total) return;
+  int xv = (int)(idx % Wv);
+  long long t = idx / Wv;
+  int y = (int)(t % p.H);
+  int b = (int)(t / p.H);
+  int x = xv * 4;
+  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + y * p.f_sh + x;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.src) + b * p.s_sn;
+  float fx[4], fy[4];
+  if constexpr (sizeof(TF) == 4) {
+    float4 a = __ldcs(reinterpret_cast<const float4*>(fl));
+    float4 c = __ldcs(reinterpret_cast<const float4*>(fl + p.f_sc));
+    fx[0] = a.x; fx[1] = a.y; fx[2] = a.z; fx[3] = a.w;
+    fy[0] = c.x; fy[1] = c.y; fy[2] = c.z; fy[3] = c.w;
+  } else {
+    uint2 a = __ldcs(reinterpret_cast<const uint2*>(fl));
+    uint2 c = __ldcs(reinterpret_cast<const uint2*>(fl + p.f_sc));
+    const TF* ap = reinterpret_cast<const TF*>(&a);
+    const TF* cp = reinterpret_cast<const TF*>(&c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fx[i] = to_f32<TF>(ap[i]); fy[i] = to_f32<TF>(cp[i]); }
+  }
+  Corners cr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cr[i] = locate(x + i, y, fx[i], fy[i], p.ax, p.ay, p.H, p.W, p.s_sh, p.s_sw);
+  float r[4][CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i][c] = sample<__nv_bfloat16>(src + c * p.s_sc, cr[i]);
+  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __align__(16) __nv_bfloat16 rec[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rec[c] = __float2bfloat16_rn(c < CT ? r[i][c < CT ? c : 0] : 0.0f);
+    __stcs(o + i, *reinterpret_cast<uint4*>(rec));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ blend (W3)
 struct BlendParams {
   WarpParams a;          // src_a / flow_a / out
@@ -303,6 +352,16 @@ extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const
   WarpParams p = make_params(src, flow, out, flags);
   bool vec4 = rows_vec4(flow) && rows_vec4(out);
   cudaStream_t st = (cudaStream_t)stream;
+  // tail-plane record output (see warp_fwd_rec_kernel): [B,H,W,8] bf16 records, C = 3
+  if (src->dtype == VFI_BF16 && src->c == 3 && out->sc == 1 && out->sw == 8 && out->sh == out->w * 8 && out->sn % 8 == 0 &&
+      aligned(out->data, 16) && rows_vec4(flow)) {
+    long long total = (long long)p.B * p.H * (p.W / 4);
+    int blocks = ceil_div(total, 256);
+    if (flow->dtype == VFI_F32) warp_fwd_rec_kernel<float, 3><<<blocks, 256, 0, st>>>(p);
+    else warp_fwd_rec_kernel<__nv_bfloat16, 3><<<blocks, 256, 0, st>>>(p);
+    VFI_LAUNCH_CHECK("warp_fwd_rec_kernel");
+    return VFI_OK;
+  }
   VFI_DISPATCH(src->dtype, TS, {
     if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, vec4, st); }
     else { rc = launch_fwd<TS, TS>(p, vec4, st); }
