@@ -90,8 +90,8 @@ static inline warp_tap warp_locate(int x, int y, float fx, float fy, int H, int 
   float iy = sample_coord(y, fy, H);
   /* Positions further than a few pixels outside the frame (or NaN) touch no valid corner; pin them to a
    * fixed out-of-bounds spot so the float->int cast below is always defined. */
-  if (!(ix >= -4.0f && ix <= (float)W + 4.0f)) ix = -4.0f;
-  if (!(iy >= -4.0f && iy <= (float)H + 4.0f)) iy = -4.0f;
+  if (!(ix >= -4.0f)) ix = -4.0f; else if (ix > (float)W + 4.0f) ix = (float)W + 4.0f;
+  if (!(iy >= -4.0f)) iy = -4.0f; else if (iy > (float)H + 4.0f) iy = (float)H + 4.0f;
   float fx0 = floorf(ix), fy0 = floorf(iy);
   t.x0 = (int)fx0;
   t.y0 = (int)fy0;

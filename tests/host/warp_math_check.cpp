@@ -22,7 +22,7 @@ static float ref_coord(int pix, float disp, long long size) {
   t = t / 2.0f;
   volatile float i = t * (float)(size - 1);
   float hi = (float)size + 4.0f;
-  return (i >= -4.0f && i <= hi) ? (float)i : -4.0f;
+  float r = i; if (!(r >= -4.0f)) r = -4.0f; if (r > hi) r = hi; return r;
 }
 
 int main(int argc, char** argv) {

@@ -5,9 +5,10 @@
 // thread derives its coordinates from its index, replays the normalise/un-normalise round trip bit-exactly
 // (warp_math.h) and gathers the four corners straight from the source planes.
 //
-// HBM-bound: algorithmic traffic is (C_in + 2 + C_out) elements per pixel (32 B/px fp32, 16 B/px bf16, C = 3).
-// The vectorised kernel moves flow and output as 128-bit (fp32) / 64-bit (bf16) accesses, four pixels per thread;
+// HBM-bound by design: algorithmic traffic is (C_in + 2 + C_out) elements per pixel (32 B/px fp32, 16 B/px bf16, C = 3);
 // the corner gathers go through the read-only path and hit L1/L2 for everything but the compulsory first touch.
+#include <type_traits>
+
 #include "common.cuh"
 #include "warp_math.h"
 
@@ -25,47 +26,47 @@ struct WarpParams {
   WarpAxis ax, ay;
 };
 
-// Everything a pixel needs to know about where it samples.
+// Everything a pixel needs to know about where it samples.  Plane offsets are 32-bit (checked on the host); a corner
+// outside the frame has offset -1 and is not loaded (zeros padding).
 struct Corners {
-  int off00, off01, off10, off11;   // element offsets inside one source plane (clamped, always in range)
+  int off00, off01, off10, off11;   // element offsets inside one source plane, -1 = corner outside the frame
   float w00, w01, w10, w11;         // nw, ne, sw, se weights
-  bool v00, v01, v10, v11;          // corner lies inside the frame
   float wx0, wx1, wy0, wy1;
-  int x0, y0;                       // unclamped north-west corner
+  int x0, y0;                       // north-west corner (may lie outside)
 };
 
 __device__ __forceinline__ Corners locate(int x, int y, float fx, float fy, const WarpAxis& ax, const WarpAxis& ay,
-                                          int H, int W, long long sh, long long sw) {
+                                          int H, int W, int sh, int sw) {
   Corners c;
-  float ix = vfi_warp_coord(x, fx, ax);
-  float iy = vfi_warp_coord(y, fy, ay);
-  float x0f = floorf(ix), y0f = floorf(iy);
-  int x0 = (int)x0f, y0 = (int)y0f;
+  const float ix = vfi_warp_coord(x, fx, ax);
+  const float iy = vfi_warp_coord(y, fy, ay);
+  const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);      // floor; positions are pinned to [-4, size + 4]
+  const float x0f = (float)x0, y0f = (float)y0;
   c.x0 = x0; c.y0 = y0;
   c.wx1 = ix - x0f;
   c.wx0 = (x0f + 1.0f) - ix;
   c.wy1 = iy - y0f;
   c.wy0 = (y0f + 1.0f) - iy;
-  bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
-  bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
-  int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
-  int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
-  c.off00 = (int)(cy0 * sh + cx0 * sw);
-  c.off01 = (int)(cy0 * sh + cx1 * sw);
-  c.off10 = (int)(cy1 * sh + cx0 * sw);
-  c.off11 = (int)(cy1 * sh + cx1 * sw);
-  c.v00 = vx0 && vy0; c.v01 = vx1 && vy0; c.v10 = vx0 && vy1; c.v11 = vx1 && vy1;
+  const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+  const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+  const int r0 = y0 * sh, r1 = r0 + sh, c0 = x0 * sw, c1 = c0 + sw;
+  c.off00 = (vx0 && vy0) ? r0 + c0 : -1;
+  c.off01 = (vx1 && vy0) ? r0 + c1 : -1;
+  c.off10 = (vx0 && vy1) ? r1 + c0 : -1;
+  c.off11 = (vx1 && vy1) ? r1 + c1 : -1;
   c.w00 = c.wx0 * c.wy0; c.w01 = c.wx1 * c.wy0; c.w10 = c.wx0 * c.wy1; c.w11 = c.wx1 * c.wy1;
   return c;
 }
 
 template <typename TS>
+__device__ __forceinline__ float corner(const TS* plane, int off) {
+  return off >= 0 ? ldg_f32(plane + (unsigned)off) : 0.0f;   // predicated load: outside corners contribute nothing
+}
+
+template <typename TS>
 __device__ __forceinline__ float sample(const TS* plane, const Corners& c) {
-  // predicated loads: an out-of-frame corner contributes nothing (zeros padding), as in aten::grid_sampler_2d
-  float a = c.v00 ? ldg_f32(plane + c.off00) : 0.0f;
-  float b = c.v01 ? ldg_f32(plane + c.off01) : 0.0f;
-  float d = c.v10 ? ldg_f32(plane + c.off10) : 0.0f;
-  float e = c.v11 ? ldg_f32(plane + c.off11) : 0.0f;
+  const float a = corner(plane, c.off00), b = corner(plane, c.off01);
+  const float d = corner(plane, c.off10), e = corner(plane, c.off11);
   float acc = a * c.w00;
   acc = fmaf(b, c.w01, acc);
   acc = fmaf(d, c.w10, acc);
@@ -74,122 +75,66 @@ __device__ __forceinline__ float sample(const TS* plane, const Corners& c) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// One thread = VEC consecutive pixels of one row.  VEC = 4 requires unit W-stride and 4-element alignment of flow
-// and out rows (checked on the host); VEC = 1 is the fully strided path.  CT = compile-time channel count (0 = any).
-template <typename TS, typename TF, int VEC, int CT>
-__global__ void __launch_bounds__(256) warp_fwd_kernel(const WarpParams p) {
-  const int Wv = (p.W + VEC - 1) / VEC;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)p.B * p.H * Wv;
-  if (idx >= total) return;
-  int xv = (int)(idx % Wv);
-  long long t = idx / Wv;
-  int y = (int)(t % p.H);
-  int b = (int)(t / p.H);
-  int x = xv * VEC;
+// Thread mapping: lanes are CONSECUTIVE pixels of one row, so every one of the 4 x C corner gathers of a warp lands in
+// one or two 128-byte lines (smooth flow) instead of the 3+ lines a 4-pixels-per-thread mapping touches; the LSU replays
+// a multi-line request at ~2 cycles per line, which is what bounded the first version (0.23 ms for bf16 and fp32 alike).
+// Instruction-level parallelism comes from PPT pixels per thread spaced one block apart (x, x + 256): all 2 x 4 x C
+// gathers of a thread are independent and in flight together.  grid = (ceil(W / 512), H, B).
+// REC = true: out is a channels-last bf16 "tail plane" (unit channel stride, 8 elements = 16 B per pixel) -- the tail
+// input of the tensor-core DCN kernel; channels >= C are written as zeros (no pre-clearing, no torch.cat).
+constexpr int WARP_BLOCK = 256;
+constexpr int WARP_PPT = 2;
+
+template <typename TS, typename TF, int CT, bool REC>
+__global__ void __launch_bounds__(WARP_BLOCK) warp_fwd_kernel(const WarpParams p) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x0 = blockIdx.x * (WARP_BLOCK * WARP_PPT) + threadIdx.x;
   const int C = CT ? CT : p.C;
-
-  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
+  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + y * p.f_sh;
+  const TF* fl_y = fl + p.f_sc;
   const TS* src = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
-  TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
+  TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + y * p.o_sh;
+  const int f_sw = (int)p.f_sw, o_sw = (int)p.o_sw, s_sh = (int)p.s_sh, s_sw = (int)p.s_sw;   // 32-bit inner strides
 
-  float fx[VEC], fy[VEC];
-  if constexpr (VEC == 4) {
-    if constexpr (sizeof(TF) == 4) {
-      float4 a = __ldcs(reinterpret_cast<const float4*>(fl));
-      float4 c = __ldcs(reinterpret_cast<const float4*>(fl + p.f_sc));
-      fx[0] = a.x; fx[1] = a.y; fx[2] = a.z; fx[3] = a.w;
-      fy[0] = c.x; fy[1] = c.y; fy[2] = c.z; fy[3] = c.w;
-    } else {
-      uint2 a = __ldcs(reinterpret_cast<const uint2*>(fl));
-      uint2 c = __ldcs(reinterpret_cast<const uint2*>(fl + p.f_sc));
-      const TF* ap = reinterpret_cast<const TF*>(&a);
-      const TF* cp = reinterpret_cast<const TF*>(&c);
+  Corners cr[WARP_PPT];
+  bool ok[WARP_PPT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { fx[i] = to_f32<TF>(ap[i]); fy[i] = to_f32<TF>(cp[i]); }
+  for (int i = 0; i < WARP_PPT; ++i) {
+    const int x = x0 + i * WARP_BLOCK;
+    ok[i] = x < p.W;
+    const int xs = ok[i] ? x : 0;
+    const float fx = to_f32<TF>(__ldcs(fl + xs * f_sw)), fy = to_f32<TF>(__ldcs(fl_y + xs * f_sw));
+    cr[i] = locate(xs, y, fx, fy, p.ax, p.ay, p.H, p.W, s_sh, s_sw);
+  }
+  if constexpr (REC) {
+    float r[WARP_PPT][CT ? CT : 1];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+      for (int i = 0; i < WARP_PPT; ++i) r[i][c] = sample<TS>(src + c * p.s_sc, cr[i]);
+#pragma unroll
+    for (int i = 0; i < WARP_PPT; ++i) {
+      if (!ok[i]) continue;
+      __align__(16) __nv_bfloat16 rec[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rec[c] = __float2bfloat16_rn(c < CT ? r[i][c < CT ? c : 0] : 0.0f);
+      __stcs(reinterpret_cast<uint4*>(out + (x0 + i * WARP_BLOCK) * o_sw), *reinterpret_cast<uint4*>(rec));
     }
   } else {
-    fx[0] = to_f32<TF>(fl[0]);
-    fy[0] = to_f32<TF>(fl[p.f_sc]);
-  }
-
-  Corners cr[VEC];
+    auto do_channel = [&](int c) {
+      float r[WARP_PPT];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) cr[i] = locate(x + i, y, fx[i], fy[i], p.ax, p.ay, p.H, p.W, p.s_sh, p.s_sw);
-
-  auto do_channel = [&](int cc) {
-    const TS* plane = src + cc * p.s_sc;
-    float r[VEC];
+      for (int i = 0; i < WARP_PPT; ++i) r[i] = sample<TS>(src + c * p.s_sc, cr[i]);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) r[i] = sample<TS>(plane, cr[i]);
-    TS* o = out + cc * p.o_sc;
-    if constexpr (VEC == 4) {
-      if constexpr (sizeof(TS) == 4) {
-        __stcs(reinterpret_cast<float4*>(o), make_float4(r[0], r[1], r[2], r[3]));
-      } else {
-        TS v[4];
+      for (int i = 0; i < WARP_PPT; ++i)
+        if (ok[i]) __stcs(out + c * p.o_sc + (x0 + i * WARP_BLOCK) * o_sw, from_f32<TS>(r[i]));
+    };
+    if constexpr (CT > 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = from_f32<TS>(r[i]);
-        __stcs(reinterpret_cast<uint2*>(o), *reinterpret_cast<uint2*>(v));
-      }
+      for (int c = 0; c < CT; ++c) do_channel(c);
     } else {
-      o[0] = from_f32<TS>(r[0]);
+      for (int c = 0; c < C; ++c) do_channel(c);
     }
-  };
-  if constexpr (CT > 0) {
-#pragma unroll
-    for (int c = 0; c < CT; ++c) do_channel(c);
-  } else {
-    for (int c = 0; c < C; ++c) do_channel(c);
-  }
-}
-
-// Record output: out is a channels-last bf16 "tail plane" (unit channel stride, 8 elements = 16 B per pixel, dense
-// rows), i.e. the tail input of the tensor-core DCN kernel.  One thread = 4 consecutive pixels: two 8-byte flow loads,
-// 4 x C x 4 independent gathers in flight, four 16-byte record stores (channels >= C written as zeros, so the buffer needs
-// no pre-clearing).  Removes the torch.cat of ema_vfi.py:134 without paying for partial-sector writes.
-template <typename TF, int CT>
-__global__ void __launch_bounds__(256) warp_fwd_rec_kernel(const WarpParams p) {
-  const int Wv = p.W / 4;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)p.B * p.H * Wv;
-  if (idx >= total) return;
-  int xv = (int)(idx % Wv);
-  long long t = idx / Wv;
-  int y = (int)(t % p.H);
-  int b = (int)(t / p.H);
-  int x = xv * 4;
-  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + y * p.f_sh + x;
-  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.src) + b * p.s_sn;
-  float fx[4], fy[4];
-  if constexpr (sizeof(TF) == 4) {
-    float4 a = __ldcs(reinterpret_cast<const float4*>(fl));
-    float4 c = __ldcs(reinterpret_cast<const float4*>(fl + p.f_sc));
-    fx[0] = a.x; fx[1] = a.y; fx[2] = a.z; fx[3] = a.w;
-    fy[0] = c.x; fy[1] = c.y; fy[2] = c.z; fy[3] = c.w;
-  } else {
-    uint2 a = __ldcs(reinterpret_cast<const uint2*>(fl));
-    uint2 c = __ldcs(reinterpret_cast<const uint2*>(fl + p.f_sc));
-    const TF* ap = reinterpret_cast<const TF*>(&a);
-    const TF* cp = reinterpret_cast<const TF*>(&c);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { fx[i] = to_f32<TF>(ap[i]); fy[i] = to_f32<TF>(cp[i]); }
-  }
-  Corners cr[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) cr[i] = locate(x + i, y, fx[i], fy[i], p.ax, p.ay, p.H, p.W, p.s_sh, p.s_sw);
-  float r[4][CT];
-#pragma unroll
-  for (int c = 0; c < CT; ++c)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[i][c] = sample<__nv_bfloat16>(src + c * p.s_sc, cr[i]);
-  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __align__(16) __nv_bfloat16 rec[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) rec[c] = __float2bfloat16_rn(c < CT ? r[i][c < CT ? c : 0] : 0.0f);
-    __stcs(o + i, *reinterpret_cast<uint4*>(rec));
   }
 }
 
@@ -216,8 +161,8 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const BlendParams q) {
   int b = (int)(t / p.H);
   const TF* fa = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
   const TF* fb = reinterpret_cast<const TF*>(q.flow_b) + b * q.g_sn + y * q.g_sh + x * q.g_sw;
-  Corners ca = locate(x, y, to_f32<TF>(fa[0]), to_f32<TF>(fa[p.f_sc]), p.ax, p.ay, p.H, p.W, p.s_sh, p.s_sw);
-  Corners cb = locate(x, y, to_f32<TF>(fb[0]), to_f32<TF>(fb[q.g_sc]), p.ax, p.ay, p.H, p.W, q.b_sh, q.b_sw);
+  Corners ca = locate(x, y, to_f32<TF>(fa[0]), to_f32<TF>(fa[p.f_sc]), p.ax, p.ay, p.H, p.W, (int)p.s_sh, (int)p.s_sw);
+  Corners cb = locate(x, y, to_f32<TF>(fb[0]), to_f32<TF>(fb[q.g_sc]), p.ax, p.ay, p.H, p.W, (int)q.b_sh, (int)q.b_sw);
   float m = to_f32<TS>(reinterpret_cast<const TS*>(q.m)[b * q.m_sn + y * q.m_sh + x * q.m_sw]);
   float m1 = 1.0f - m;
   const TS* sa = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
@@ -253,27 +198,25 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const WarpBwdParams q) {
   int y = (int)(t % p.H);
   int b = (int)(t / p.H);
   const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
-  Corners c = locate(x, y, to_f32<TF>(fl[0]), to_f32<TF>(fl[p.f_sc]), p.ax, p.ay, p.H, p.W, p.s_sh, p.s_sw);
+  Corners c = locate(x, y, to_f32<TF>(fl[0]), to_f32<TF>(fl[p.f_sc]), p.ax, p.ay, p.H, p.W, (int)p.s_sh, (int)p.s_sw);
   const TS* src = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
   const TG* go = reinterpret_cast<const TG*>(q.gout) + b * q.go_sn + y * q.go_sh + x * q.go_sw;
   float gix = 0.0f, giy = 0.0f;
   for (int ch = 0; ch < p.C; ++ch) {
     const TS* plane = src + ch * p.s_sc;
     float g = to_f32<TG>(__ldg(go + ch * q.go_sc));
-    float nw = c.v00 ? ldg_f32(plane + c.off00) : 0.0f;
-    float ne = c.v01 ? ldg_f32(plane + c.off01) : 0.0f;
-    float sw = c.v10 ? ldg_f32(plane + c.off10) : 0.0f;
-    float se = c.v11 ? ldg_f32(plane + c.off11) : 0.0f;
+    float nw = corner(plane, c.off00), ne = corner(plane, c.off01);
+    float sw = corner(plane, c.off10), se = corner(plane, c.off11);
     gix += ((ne - nw) * c.wy0 + (se - sw) * c.wy1) * g;
     giy += ((sw - nw) * c.wx0 + (se - ne) * c.wx1) * g;
     if (q.gsrc) {
       // same pixel geometry as src but addressed with grad_src's own strides
       float* gs = q.gsrc + b * q.gs_sn + ch * q.gs_sc;
       const int x0 = c.x0, y0 = c.y0;
-      if (c.v00) atomicAdd(gs + y0 * q.gs_sh + x0 * q.gs_sw, g * c.w00);
-      if (c.v01) atomicAdd(gs + y0 * q.gs_sh + (x0 + 1) * q.gs_sw, g * c.w01);
-      if (c.v10) atomicAdd(gs + (y0 + 1) * q.gs_sh + x0 * q.gs_sw, g * c.w10);
-      if (c.v11) atomicAdd(gs + (y0 + 1) * q.gs_sh + (x0 + 1) * q.gs_sw, g * c.w11);
+      if (c.off00 >= 0) atomicAdd(gs + y0 * q.gs_sh + x0 * q.gs_sw, g * c.w00);
+      if (c.off01 >= 0) atomicAdd(gs + y0 * q.gs_sh + (x0 + 1) * q.gs_sw, g * c.w01);
+      if (c.off10 >= 0) atomicAdd(gs + (y0 + 1) * q.gs_sh + x0 * q.gs_sw, g * c.w10);
+      if (c.off11 >= 0) atomicAdd(gs + (y0 + 1) * q.gs_sh + (x0 + 1) * q.gs_sw, g * c.w11);
     }
   }
   // d(grid)/d(flow): aten scales by (size-1)/2, autograd of "2.0 * v / denom" divides by denom and doubles.
@@ -316,24 +259,18 @@ WarpParams make_params(const vfi_tensor* src, const vfi_tensor* flow, const vfi_
   return p;
 }
 
-bool rows_vec4(const vfi_tensor* t) {
-  size_t es = dtype_size(t->dtype);
-  return t->sw == 1 && t->w % 4 == 0 && t->sh % 4 == 0 && t->sc % 4 == 0 && t->sn % 4 == 0 && aligned(t->data, 4 * es);
-}
-
 template <typename TS, typename TF>
-int launch_fwd(const WarpParams& p, bool vec4, cudaStream_t st) {
-  if (vec4) {
-    long long total = (long long)p.B * p.H * (p.W / 4);
-    int blocks = ceil_div(total, 256);
-    if (p.C == 3) warp_fwd_kernel<TS, TF, 4, 3><<<blocks, 256, 0, st>>>(p);
-    else warp_fwd_kernel<TS, TF, 4, 0><<<blocks, 256, 0, st>>>(p);
-  } else {
-    long long total = (long long)p.B * p.H * p.W;
-    int blocks = ceil_div(total, 256);
-    if (p.C == 3) warp_fwd_kernel<TS, TF, 1, 3><<<blocks, 256, 0, st>>>(p);
-    else warp_fwd_kernel<TS, TF, 1, 0><<<blocks, 256, 0, st>>>(p);
+int launch_fwd(const WarpParams& p, bool rec, cudaStream_t st) {
+  dim3 grid(ceil_div(p.W, WARP_BLOCK * WARP_PPT), p.H, p.B);
+  if constexpr (std::is_same<TS, __nv_bfloat16>::value) {
+    if (rec) {
+      warp_fwd_kernel<TS, TF, 3, true><<<grid, WARP_BLOCK, 0, st>>>(p);
+      VFI_LAUNCH_CHECK("warp_fwd_kernel<rec>");
+      return VFI_OK;
+    }
   }
+  if (p.C == 3) warp_fwd_kernel<TS, TF, 3, false><<<grid, WARP_BLOCK, 0, st>>>(p);
+  else warp_fwd_kernel<TS, TF, 0, false><<<grid, WARP_BLOCK, 0, st>>>(p);
   VFI_LAUNCH_CHECK("warp_fwd_kernel");
   return VFI_OK;
 }
@@ -349,22 +286,15 @@ extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const
   if (rc) return rc;
   if (src->n == 0 || src->c == 0 || src->h == 0 || src->w == 0) return VFI_OK;
   VFI_REQUIRE((long long)src->n * src->h * src->w < (1LL << 40), VFI_ERR_UNSUPPORTED, "vfi_warp_fwd: too many pixels");
+  VFI_REQUIRE(src->h <= 65535 && src->n <= 65535, VFI_ERR_UNSUPPORTED, "vfi_warp_fwd: H and B must be <= 65535");
   WarpParams p = make_params(src, flow, out, flags);
-  bool vec4 = rows_vec4(flow) && rows_vec4(out);
   cudaStream_t st = (cudaStream_t)stream;
-  // tail-plane record output (see warp_fwd_rec_kernel): [B,H,W,8] bf16 records, C = 3
-  if (src->dtype == VFI_BF16 && src->c == 3 && out->sc == 1 && out->sw == 8 && out->sh == out->w * 8 && out->sn % 8 == 0 &&
-      aligned(out->data, 16) && rows_vec4(flow)) {
-    long long total = (long long)p.B * p.H * (p.W / 4);
-    int blocks = ceil_div(total, 256);
-    if (flow->dtype == VFI_F32) warp_fwd_rec_kernel<float, 3><<<blocks, 256, 0, st>>>(p);
-    else warp_fwd_rec_kernel<__nv_bfloat16, 3><<<blocks, 256, 0, st>>>(p);
-    VFI_LAUNCH_CHECK("warp_fwd_rec_kernel");
-    return VFI_OK;
-  }
+  // tail-plane record output: [B,H,W,8] bf16 records holding C = 3 channels + zeros
+  const bool rec = src->dtype == VFI_BF16 && src->c == 3 && out->sc == 1 && out->sw == 8 && out->sh % 8 == 0 &&
+                   out->sn % 8 == 0 && aligned(out->data, 16);
   VFI_DISPATCH(src->dtype, TS, {
-    if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, vec4, st); }
-    else { rc = launch_fwd<TS, TS>(p, vec4, st); }
+    if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, rec, st); }
+    else { rc = launch_fwd<TS, TS>(p, rec, st); }
   });
   return rc;
 }
@@ -411,7 +341,6 @@ extern "C" int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, c
               "vfi_warp_bwd: flow dtype must be f32 or the dtype of src");
   VFI_REQUIRE((src->h - 1) * llabs(src->sh) + (src->w - 1) * llabs(src->sw) < 2147483647LL, VFI_ERR_UNSUPPORTED,
               "vfi_warp_bwd: one source plane must span < 2^31 elements");
-  int rc = VFI_OK;
   VFI_REQUIRE(same_shape(grad_flow, flow) && grad_flow->dtype == VFI_F32 && (empty_b || grad_flow->data), VFI_ERR_INVALID,
               "vfi_warp_bwd: grad_flow must be f32 [B,2,H,W]");
   if (grad_src) {

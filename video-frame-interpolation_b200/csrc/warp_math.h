@@ -72,6 +72,7 @@ VFI_HD float vfi_warp_coord(int pix, float disp, const WarpAxis& ax) {
   float t = VFI_ADD(g, 1.0f);
   t = VFI_MUL(t, 0.5f);  // division by 2 is exact
   float i = VFI_MUL(t, ax.size_m1);
-  // far outside / NaN: pin to a spot whose four corners are all out of bounds (keeps float->int defined)
-  return (i >= -4.0f && i <= ax.hi) ? i : -4.0f;
+  // far outside / NaN: pin into [-4, size + 4], where all four corners are still out of bounds (keeps float->int
+  // defined; fmaxf/fminf return the non-NaN operand, so NaN lands on -4)
+  return fminf(fmaxf(i, -4.0f), ax.hi);
 }
