@@ -31,6 +31,8 @@
 //               optionally straight from the 27-channel offset_conv output with the sigmoid folded in) into the other
 //               half of a double buffer and prefetch its footprint into L2 while the producers gather tile i; then
 //               tcgen05.ld tile i's accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vfi {
@@ -593,6 +595,353 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
   }
 }
 
+// ------------------------------------------------------------------------------------------------ v5: staged source
+// Same GEMM, same pipeline, but the producers gather from SHARED MEMORY: for every tile a 16 x 22 pixel box of the
+// activation planes (the tile, the 3x3 reach and a halo of 3 rows / 2 columns) is brought in by 1-D bulk copies
+// (cp.async.bulk, one per box row and plane, issued a full tile ahead by a dedicated lane and double buffered).  Why: the
+// L1-resident gather of v4 is bound by its compulsory misses -- all nine taps walk the same ~500 lines, so the first
+// K blocks of every tile wait on L2 while 24 warps sit in long-scoreboard stalls (ncu: LSU data pipe 78 % busy, an
+// L1-hit LDG.128 alone sustains 110 B/cycle/SM in scripts/microbench/l1_gather.cu).  With the box in shared memory every
+// gather is a 30-cycle LDS.128 at 127 B/cycle/SM, and the HBM/L2 -> SM traffic is one streaming pass done by the TMA engine.
+// Samples whose corners fall outside the box (|offset| > 3 rows or > 2 columns beyond the 3x3 reach; ~2 % at sigma = 1.5 px)
+// take the v4 global-memory path lane by lane.  Image borders need no zero fill: the geometry clamps corner coordinates
+// into the image (zero weight), so only in-image pixels are ever read and only the in-image part of a box is copied.
+constexpr int V5_BOX_H = 16, V5_BOX_W = 22, V5_BOX_PX = V5_BOX_H * V5_BOX_W;      // 352 pixels
+constexpr int V5_BOX_TOP = 4, V5_BOX_LEFT = 3;                                       // box origin = tile origin - (4, 3)
+constexpr int V5_THREADS = (TC_PRODUCER_WARPS + 1 + 4 + 1) * 32;                     // + one copy-issuing warp = 960
+constexpr uint32_t V5_INSIDE = 0x80000000u;
+// Box index of the tile's own first pixel: always inside the image and always copied.  Zero-weight entries (dead samples,
+// padding rows, the zero K chunk) point here so that they never multiply 0 by uninitialised shared memory (0 * NaN).
+constexpr uint32_t V5_SAFE = V5_BOX_TOP * V5_BOX_W + V5_BOX_LEFT;
+
+struct __align__(1024) TcSmem5 {
+  uint8_t a[TC_STAGES][TC_A_BYTES];
+  uint8_t b[TC_STAGES][TC_B_BYTES];
+  uint8_t src_main[2][V5_BOX_PX * TC_CMAIN * 2];       // 2 x 45,056 B
+  uint8_t src_tail[2][V5_BOX_PX * TC_CTAIL * 2];       // 2 x  5,632 B
+  uint32_t geo_pix[2][10][TC_M];                       // as in v4 (global pixel index + corner step flags)
+  uint32_t geo_box[2][10][TC_M];                       // bit 31: all four corners are inside the staged box; low bits: box pixel index
+  uint2 geo_w[2][10][TC_M];
+  float bias[TC_N];
+  unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], geo_full[2], geo_empty[2], src_full[2],
+      src_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint4 lds16(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+
+template <typename TO, typename TOUT>
+__global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  TcSmem5& s = *reinterpret_cast<TcSmem5*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int W_MMA = TC_PRODUCER_WARPS, W_COPY = TC_PRODUCER_WARPS + 5;   // warps 25..28: geometry + epilogue
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(smem_u32(&s.full[i]), TC_GROUP_WARPS + 1);
+      mbar_init(smem_u32(&s.empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s.acc_full[i]), 1);
+      mbar_init(smem_u32(&s.acc_empty[i]), 4);
+      mbar_init(smem_u32(&s.geo_full[i]), 4);
+      mbar_init(smem_u32(&s.geo_empty[i]), TC_PRODUCER_WARPS);
+      mbar_init(smem_u32(&s.src_full[i]), 1);                   // the copy lane's expect_tx arrival (+ the bytes)
+      mbar_init(smem_u32(&s.src_empty[i]), TC_PRODUCER_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
+  if (tid < TC_N) s.bias[tid] = p.bias[tid];
+  if (tid < 2 * TC_M) {
+    s.geo_pix[tid >> 7][9][tid & 127] = 0u;
+    s.geo_box[tid >> 7][9][tid & 127] = V5_INSIDE | V5_SAFE;
+    s.geo_w[tid >> 7][9][tid & 127] = make_uint2(0u, 0u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =========================================================================== A-operand producers
+    const int group = warp >> 3, wig = warp & 7;
+    const int rsub = lane >> 3, j = lane & 7;
+    const int r_main = 4 * wig + rsub;
+    const uint32_t a_off_main = (uint32_t)r_main * 128 + ((uint32_t)(j ^ (r_main & 7)) << 4);
+    const uint8_t* gsrc_main = p.x_main + j * 16;
+    const uint32_t main_row = p.main_stride * (uint32_t)p.W, tail_row = p.tail_stride * (uint32_t)p.W;
+    uint8_t* a_stage = &s.a[group][0];
+    const uint32_t full_bar = smem_u32(&s.full[group]), empty_bar = smem_u32(&s.empty[group]);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int gb = it & 1;
+      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(smem_u32(&s.geo_full[gb]), tphase);      // this tile's geometry has been written
+      mbar_wait(smem_u32(&s.src_full[gb]), tphase);      // this tile's source box has landed in shared memory
+      const uint32_t box_main = smem_u32(&s.src_main[gb][0]) + j * 16, box_tail = smem_u32(&s.src_tail[gb][0]);
+      const int n0 = it * TC_KBLOCKS;
+      int kb = group - n0 % TC_GROUPS;
+      if (kb < 0) kb += TC_GROUPS;
+      for (; kb < TC_KBLOCKS; kb += TC_GROUPS) {
+        const uint32_t phase = (uint32_t)((n0 + kb) / TC_STAGES) & 1u;
+        mbar_wait(empty_bar, phase ^ 1);
+        if (wig == 0 && lane == 0) {
+          mbar_arrive_expect_tx(full_bar, TC_B_BYTES);
+          bulk_g2s(smem_u32(&s.b[group][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, full_bar);
+        }
+        if (kb < 9) {
+          // ---- the 64 main channels of tap kb: 8 lanes read one pixel's 128 B from the staged box
+          const uint32_t* gx = &s.geo_box[gb][kb][r_main];
+          const uint32_t* gp = &s.geo_pix[gb][kb][r_main];
+          const uint2* gw = &s.geo_w[gb][kb][r_main];
+#pragma unroll
+          for (int batch = 0; batch < 2; ++batch) {
+            uint4 v[2][4];
+            uint32_t bx[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              bx[q] = gx[(batch * 2 + q) * 32];
+              const uint32_t a00 = box_main + (bx[q] & 0xffffu) * (TC_CMAIN * 2);
+              const uint32_t dx = (bx[q] & 0x10000u) ? TC_CMAIN * 2 : 0u, dy = (bx[q] & 0x20000u) ? V5_BOX_W * TC_CMAIN * 2 : 0u;
+              v[q][0] = lds16(a00); v[q][1] = lds16(a00 + dx); v[q][2] = lds16(a00 + dy); v[q][3] = lds16(a00 + dy + dx);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)     // rare: a corner of this row lies outside the box -> global memory (v4 path)
+              if (!(bx[q] & V5_INSIDE)) gather4(gsrc_main, p.main_stride, main_row, gp[(batch * 2 + q) * 32], v[q]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              *reinterpret_cast<uint4*>(a_stage + a_off_main + (batch * 2 + q) * 4096) =
+                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], gw[(batch * 2 + q) * 32]);
+          }
+        } else if (kb == 9) {
+          // ---- tails of taps 0..7: warp wig owns tap wig (chunk wig), lane = row
+          const int tap = wig;
+#pragma unroll
+          for (int batch = 0; batch < 2; ++batch) {
+            uint4 v[2][4];
+            uint32_t bx[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int r = (batch * 2 + q) * 32 + lane;
+              bx[q] = s.geo_box[gb][tap][r];
+              const uint32_t a00 = box_tail + (bx[q] & 0xffffu) * (TC_CTAIL * 2);
+              const uint32_t dx = (bx[q] & 0x10000u) ? TC_CTAIL * 2 : 0u, dy = (bx[q] & 0x20000u) ? V5_BOX_W * TC_CTAIL * 2 : 0u;
+              v[q][0] = lds16(a00); v[q][1] = lds16(a00 + dx); v[q][2] = lds16(a00 + dy); v[q][3] = lds16(a00 + dy + dx);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              if (!(bx[q] & V5_INSIDE))
+                gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][tap][(batch * 2 + q) * 32 + lane], v[q]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int r = (batch * 2 + q) * 32 + lane;
+              *reinterpret_cast<uint4*>(a_stage + r * 128 + ((tap ^ (r & 7)) << 4)) =
+                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], s.geo_w[gb][tap][r]);
+            }
+          }
+        } else if (wig < 4) {
+          // ---- tail of tap 8 (chunk 0) and the zero chunk 1 of the last UMMA_K step
+          const int r = wig * 32 + lane;
+          uint4 v[4];
+          const uint32_t bx = s.geo_box[gb][8][r];
+          const uint32_t a00 = box_tail + (bx & 0xffffu) * (TC_CTAIL * 2);
+          const uint32_t dx = (bx & 0x10000u) ? TC_CTAIL * 2 : 0u, dy = (bx & 0x20000u) ? V5_BOX_W * TC_CTAIL * 2 : 0u;
+          v[0] = lds16(a00); v[1] = lds16(a00 + dx); v[2] = lds16(a00 + dy); v[3] = lds16(a00 + dy + dx);
+          if (!(bx & V5_INSIDE)) gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][8][r], v);
+          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk(v[0], v[1], v[2], v[3], s.geo_w[gb][8][r]);
+          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar);
+      }
+      __syncwarp();
+      if (lane == 0) {                                   // this warp no longer reads geometry / source buffer gb
+        mbar_arrive(smem_u32(&s.geo_empty[gb]));
+        mbar_arrive(smem_u32(&s.src_empty[gb]));
+      }
+    }
+  } else if (warp == W_MMA) {
+    // =========================================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase[2] = {0, 0};
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
+        for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
+          mbar_wait(smem_u32(&s.full[stage]), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[stage][0]));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[stage][0]));
+          const int nk = (kb == TC_KBLOCKS - 1) ? 1 : 4;
+          for (int k = 0; k < nk; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&s.empty[stage]));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&s.acc_full[acc]));
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_COPY) {
+    // =========================================================================== source-box copies (one lane)
+    if (lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int sb = it & 1;
+        mbar_wait(smem_u32(&s.src_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old box
+        int b, ty0, tx0;
+        tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+        const int by0 = ty0 - V5_BOX_TOP, bx0 = tx0 - V5_BOX_LEFT;
+        const int ya = max(by0, 0), yb = min(by0 + V5_BOX_H, p.H), xa = max(bx0, 0), xb = min(bx0 + V5_BOX_W, p.W);
+        const uint32_t ncol = (uint32_t)(xb - xa), nrow = (uint32_t)(yb - ya);
+        const uint32_t bar = smem_u32(&s.src_full[sb]);
+        mbar_arrive_expect_tx(bar, nrow * ncol * (TC_CMAIN + TC_CTAIL) * 2);
+        for (int y = ya; y < yb; ++y) {
+          const size_t gpix = (size_t)(b * p.H + y) * p.W + xa;
+          const uint32_t bpix = (uint32_t)((y - by0) * V5_BOX_W + (xa - bx0));
+          bulk_g2s(smem_u32(&s.src_main[sb][0]) + bpix * (TC_CMAIN * 2), p.x_main + gpix * p.main_stride, ncol * TC_CMAIN * 2, bar);
+          bulk_g2s(smem_u32(&s.src_tail[sb][0]) + bpix * (TC_CTAIL * 2), p.x_tail + gpix * p.tail_stride, ncol * TC_CTAIL * 2, bar);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================== geometry + epilogue (4 warps)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t acc = 0, acc_phase[2] = {0, 0};
+
+    auto make_geometry = [&](int it) {
+      const int gb = it & 1;
+      mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      int b, ty0, tx0;
+      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
+      const int by0 = ty0 - V5_BOX_TOP, bx0 = tx0 - V5_BOX_LEFT;
+      if (y < p.H && x < p.W) {
+        const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
+        const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
+        const int base = b * p.H * p.W;
+#pragma unroll
+        for (int k0 = 0; k0 < 9; k0 += 3) {
+          TO rdy[3], rdx[3], rmk[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = k0 + i, j0 = 2 * k, j1 = 2 * k + 1;
+            if (p.fused27) {
+              rdy[i] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * p.f_sc);
+              rdx[i] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * p.f_sc);
+              rmk[i] = __ldg(msk + (9 + k) * p.m_sc);
+            } else {
+              rdy[i] = __ldg(off + j0 * p.f_sc);
+              rdx[i] = __ldg(off + j1 * p.f_sc);
+              rmk[i] = __ldg(msk + k * p.m_sc);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = k0 + i;
+            float mk = to_f32<TO>(rmk[i]);
+            if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
+            uint32_t pixf;
+            uint2 wq;
+            tc_geo_entry<uint2>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[i]), to_f32<TO>(rdx[i]), mk, pixf, wq);
+            // position of the (clamped) corner 00 inside the staged box; the step flags are those of pixf
+            const int pix00 = (int)(pixf & 0x3fffffffu) - base;
+            const int cy = pix00 / p.W, cx = pix00 - cy * p.W;
+            const int sx = (int)((pixf >> 30) & 1u), sy = (int)(pixf >> 31);
+            const int ry = cy - by0, rx = cx - bx0;
+            const bool dead = (wq.x | wq.y) == 0u;                       // all four weights are (+)0: value irrelevant
+            const bool in = ry >= 0 && ry + sy < V5_BOX_H && rx >= 0 && rx + sx < V5_BOX_W;
+            uint32_t box = (in && !dead) ? (uint32_t)(ry * V5_BOX_W + rx) | ((uint32_t)sx << 16) | ((uint32_t)sy << 17) : V5_SAFE;
+            if (in || dead) box |= V5_INSIDE;
+            s.geo_pix[gb][k][row] = pixf;
+            s.geo_box[gb][k][row] = box;
+            s.geo_w[gb][k][row] = wq;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          s.geo_pix[gb][k][row] = 0u; s.geo_box[gb][k][row] = V5_INSIDE | V5_SAFE; s.geo_w[gb][k][row] = make_uint2(0u, 0u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
+    };
+
+    if (my_tiles > 0) make_geometry(0);
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) make_geometry(it + 1);
+      int b, ty0, tx0;
+      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+      mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
+      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
+      const bool inside = y < p.H && x < p.W;
+      const size_t pixel = (size_t)(b * p.H + y) * p.W + x;
+      __nv_bfloat16* om = reinterpret_cast<__nv_bfloat16*>(p.out) + pixel * TC_CMAIN;
+      __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(p.out_tail) + pixel * TC_CTAIL;
+      TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
+#pragma unroll
+      for (int c16 = 0; c16 < TC_N / 16; ++c16) {
+        uint32_t d[16];
+        tmem_ld16(taddr + c16 * 16, d);
+        tmem_ld_wait();
+        if (c16 == TC_N / 16 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
+        }
+        if (inside) {
+          if (p.out_tail) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = c16 * 16 + h * 8;
+              if (c0 >= TC_CMAX) break;
+              uint32_t w4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c0 + 2 * i],
+                                                          __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c0 + 2 * i + 1]);
+                w4[i] = *reinterpret_cast<uint32_t*>(&hv);
+              }
+              __nv_bfloat16* dst = c0 < TC_CMAIN ? om + c0 : ot;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c16 * 16 + i;
+              if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]) + s.bias[c]);
+            }
+          }
+        }
+      }
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ UMMA self test
 // D[128, 80] = A[128, K] * Bm[80, K]^T with A, Bm row-major bf16 in global memory, K a multiple of 64.  Uses exactly
 // the descriptor / swizzle / tcgen05 helpers of the kernel above, serialised (one stage, block barriers), so that a
@@ -770,8 +1119,22 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   VFI_CUDA(cudaGetDevice(&dev));
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  const size_t smem = (hq ? sizeof(TcSmem<true>) : sizeof(TcSmem<false>)) + 1024;
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
+  static const bool force_v4 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '4'; }();
+  if (!hq && !force_v4) {
+    // v5: source box staged in shared memory (fast-path arithmetic only; the HQ geometry does not fit next to the boxes)
+    const size_t smem5 = sizeof(TcSmem5) + 1024;
+    VFI_DISPATCH(offset->dtype, TO, {
+      VFI_DISPATCH(out_dtype, TOUT, {
+        auto kern = dcn_tc5_fwd_kernel<TO, TOUT>;
+        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+        kern<<<grid, V5_THREADS, smem5, st>>>(p);
+      });
+    });
+    VFI_LAUNCH_CHECK("dcn_tc5_fwd_kernel");
+    return VFI_OK;
+  }
+  const size_t smem = (hq ? sizeof(TcSmem<true>) : sizeof(TcSmem<false>)) + 1024;
   VFI_DISPATCH(offset->dtype, TO, {
     VFI_DISPATCH(out_dtype, TOUT, {
       if (hq) {
