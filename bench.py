@@ -162,11 +162,14 @@ def main():
     ap.add_argument("--impl", default="vfi_b200", choices=["vfi_b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "bf16_tc"])
+    ap.add_argument("--dcn-kernel", default="", choices=["", "v4", "v5"], help="A/B switch for the tcgen05 DCN kernel variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.dcn_kernel:
+        os.environ["VFI_DCN_KERNEL"] = args.dcn_kernel      # read once by libvfi_b200 at the first DCN launch
     B, H, W, flow_sigma, off_sigma, desc = WORKLOADS[args.workload]
 
     if args.impl == "reference":

@@ -147,6 +147,10 @@ int vfi_dcn_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vf
  * serialised; exercises exactly the shared-memory descriptors, swizzle, tcgen05.mma/commit/ld and TMEM allocation the
  * DCN kernel uses, so a wrong DCN result can be attributed to the tensor-core plumbing or to the gather. */
 int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream);
+/* With VFI_DCN_DEBUG=1 in the environment the staged tcgen05 DCN kernel records, per CTA and warp, the cycles spent in
+ * each of its pipeline waits; this copies `count` u64 counters ([cta][32 warps][8]) of the last launch to host memory
+ * (synchronises the device). */
+int vfi_debug_read(uint64_t* host_dst, size_t count);
 
 #ifdef __cplusplus
 }

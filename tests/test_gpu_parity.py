@@ -350,6 +350,46 @@ def test_dcn_fused_split_input_and_conv27(math, bar):
     assert relerr(out3.to_nchw(), ref) <= bar
 
 
+def test_dcn_staged_variant_matches_default_kernel():
+    """VFI_DCN_KERNEL=v5 (source box staged in shared memory, global fallback for far offsets) in a fresh process: must
+    give bit-identical planes to the default kernel -- same arithmetic, different data path -- including the fallback
+    path (sigma = 6 px) and image borders."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from vfi_b200 import ops
+g = torch.Generator().manual_seed(77)
+B, H, W = 2, 45, 83
+feat = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+src = ops.Planes(B, H, W, 'cuda', zero_tail=True)
+src.tail[..., :3] = torch.randn(B, H, W, 3, generator=g).to(torch.bfloat16).cuda()
+c27 = torch.randn(B, 27, H, W, generator=g)
+c27[:, :9] *= 6.0
+c27[:, 18:] *= 6.0
+c27 = c27.to(torch.bfloat16).cuda()
+w = ((torch.rand(67, 67, 3, 3, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16).cuda()
+b = (torch.randn(67, generator=g) * 0.01).to(torch.bfloat16).cuda()
+y = ops.deform_conv2d_fused(feat, src.tail_nchw(3), c27, w, b).to_nchw()
+torch.save(y.cpu(), sys.argv[1])
+""" % str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    import tempfile
+
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for variant in ("v4", "v5"):
+            path = os.path.join(d, variant + ".pt")
+            env = dict(os.environ, VFI_DCN_KERNEL=variant)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(torch.load(path))
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
     """Full 1080p frame: tcgen05 result against this library's fp32 parity kernel on the same bf16-rounded inputs."""
     g = torch.Generator(device=DEV).manual_seed(41)

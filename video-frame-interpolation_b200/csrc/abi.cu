@@ -28,6 +28,7 @@ size_t dcn_tc_packed_weight_bytes();
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
                        void* packed, float* bias_out, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
+unsigned long long* dcn_tc_debug_buffer();
 int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
                int weight_dtype, const void* bias, int bias_dtype, const vfi_tensor* out, long long O, bool hq,
@@ -115,4 +116,11 @@ extern "C" int vfi_dcn_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_t
               VFI_ERR_UNSUPPORTED, "vfi_dcn_fwd_fused: only the tensor-core math modes are implemented in fused form");
   return dcn_tc_fwd_fused(x_main, x_tail, conv27, weight, weight_dtype, bias, bias_dtype, out, out_tail, O,
                           math == VFI_DCN_MATH_BF16_TC_HQ, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_debug_read(uint64_t* host_dst, size_t count) {
+  unsigned long long* b = dcn_tc_debug_buffer();
+  VFI_REQUIRE(b && host_dst, VFI_ERR_UNSUPPORTED, "vfi_debug_read: set VFI_DCN_DEBUG=1 before the first DCN launch");
+  VFI_CUDA(cudaMemcpy(host_dst, b, (count < 256 * 32 * 8 ? count : 256 * 32 * 8) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return VFI_OK;
 }

@@ -96,12 +96,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uin
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity, 20000u)) {
+    __nanosleep(128);                                   // the hinted try_wait still returns early: do not burn issue slots
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity, 2000u)) return;
   mbar_wait_slow(bar, parity);
+}
+// mbar_wait that adds the cycles spent waiting to `acc` (only used when the debug buffer is enabled)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -230,6 +238,7 @@ struct TcParams {
   long long o_sn, o_sc, o_sh, o_sw;                // generic strided output otherwise
   int B, H, W, O;
   int tiles_x, tiles_y, num_tiles;
+  unsigned long long* debug;                       // optional [grid][32 warps][8] cycle counters (VFI_DCN_DEBUG), else null
 };
 
 // Tap geometry, one entry per (tap, tile row), double buffered across tiles: the four epilogue warps compute tile
@@ -491,39 +500,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x_main + (size_t)((b * p.H + fy2) * p.W + fx2) * p.main_stride));
       }
       if (y < p.H && x < p.W) {
+        // all 27 offset / mask values of this pixel are requested before the first one is used (one DRAM round trip)
+        const int f_sc = (int)p.f_sc, m_sc = (int)p.m_sc;
         const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
         const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
         const int base = b * p.H * p.W;
+        TO rdy[9], rdx[9], rmk[9];
 #pragma unroll
-        for (int k0 = 0; k0 < 9; k0 += 3) {              // three taps at a time: nine loads in flight, few registers
-          TO rdy[3], rdx[3], rmk[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int k = k0 + i, j0 = 2 * k, j1 = 2 * k + 1;
-            if (p.fused27) {
-              // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets (tap k uses channels 2k and
-              // 2k+1 of their concatenation), the middle third is the pre-sigmoid mask
-              rdy[i] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * p.f_sc);
-              rdx[i] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * p.f_sc);
-              rmk[i] = __ldg(msk + (9 + k) * p.m_sc);
-            } else {
-              rdy[i] = __ldg(off + j0 * p.f_sc);
-              rdx[i] = __ldg(off + j1 * p.f_sc);
-              rmk[i] = __ldg(msk + k * p.m_sc);
-            }
+        for (int k = 0; k < 9; ++k) {
+          const int j0 = 2 * k, j1 = 2 * k + 1;
+          if (p.fused27) {
+            // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets (tap k uses channels 2k and
+            // 2k+1 of their concatenation), the middle third is the pre-sigmoid mask
+            rdy[k] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
+            rdx[k] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
+            rmk[k] = __ldg(msk + (9 + k) * m_sc);
+          } else {
+            rdy[k] = __ldg(off + j0 * f_sc);
+            rdx[k] = __ldg(off + j1 * f_sc);
+            rmk[k] = __ldg(msk + k * m_sc);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int k = k0 + i;
-            float mk = to_f32<TO>(rmk[i]);
-            // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
-            if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
-            uint32_t pixf;
-            GW wq;
-            tc_geo_entry<GW>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[i]), to_f32<TO>(rdx[i]), mk, pixf, wq);
-            s.geo_pix[gb][k][row] = pixf;
-            s.geo_w[gb][k][row] = wq;
-          }
+        for (int k = 0; k < 9; ++k) {
+          float mk = to_f32<TO>(rmk[k]);
+          // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
+          if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
+          uint32_t pixf;
+          GW wq;
+          tc_geo_entry<GW>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[k]), to_f32<TO>(rdx[k]), mk, pixf, wq);
+          s.geo_pix[gb][k][row] = pixf;
+          s.geo_w[gb][k][row] = wq;
         }
       } else {
 #pragma unroll
@@ -669,6 +676,9 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
   const uint32_t tmem_base = s.tmem_base;
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
+  const bool dbg = p.debug != nullptr;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;              // cycles spent in this role's waits (debug only)
+  const long long t_begin = clock64();
 
   if (warp < TC_PRODUCER_WARPS) {
     // =========================================================================== A-operand producers
@@ -683,19 +693,24 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(smem_u32(&s.geo_full[gb]), tphase);      // this tile's geometry has been written
-      mbar_wait(smem_u32(&s.src_full[gb]), tphase);      // this tile's source box has landed in shared memory
+      mbar_wait_t(smem_u32(&s.geo_full[gb]), tphase, dbg, w0);      // this tile's geometry has been written
+      mbar_wait_t(smem_u32(&s.src_full[gb]), tphase, dbg, w1);      // this tile's source box has landed in shared memory
       const uint32_t box_main = smem_u32(&s.src_main[gb][0]) + j * 16, box_tail = smem_u32(&s.src_tail[gb][0]);
       const int n0 = it * TC_KBLOCKS;
       int kb = group - n0 % TC_GROUPS;
       if (kb < 0) kb += TC_GROUPS;
       for (; kb < TC_KBLOCKS; kb += TC_GROUPS) {
         const uint32_t phase = (uint32_t)((n0 + kb) / TC_STAGES) & 1u;
-        mbar_wait(empty_bar, phase ^ 1);
-        if (wig == 0 && lane == 0) {
-          mbar_arrive_expect_tx(full_bar, TC_B_BYTES);
-          bulk_g2s(smem_u32(&s.b[group][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, full_bar);
-        }
+        // The stage buffer is only needed when the first lerp result is stored: the gathers of the first batch are
+        // issued BEFORE waiting for the tensor core to release the stage, so the MMA + commit latency of this group's
+        // previous block overlaps with shared-memory load latency instead of adding to it.
+        auto acquire_stage = [&]() {
+          mbar_wait_t(empty_bar, phase ^ 1, dbg, w2);
+          if (wig == 0 && lane == 0) {
+            mbar_arrive_expect_tx(full_bar, TC_B_BYTES);
+            bulk_g2s(smem_u32(&s.b[group][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, full_bar);
+          }
+        };
         if (kb < 9) {
           // ---- the 64 main channels of tap kb: 8 lanes read one pixel's 128 B from the staged box
           const uint32_t* gx = &s.geo_box[gb][kb][r_main];
@@ -715,6 +730,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
 #pragma unroll
             for (int q = 0; q < 2; ++q)     // rare: a corner of this row lies outside the box -> global memory (v4 path)
               if (!(bx[q] & V5_INSIDE)) gather4(gsrc_main, p.main_stride, main_row, gp[(batch * 2 + q) * 32], v[q]);
+            if (batch == 0) acquire_stage();
 #pragma unroll
             for (int q = 0; q < 2; ++q)
               *reinterpret_cast<uint4*>(a_stage + a_off_main + (batch * 2 + q) * 4096) =
@@ -723,6 +739,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
         } else if (kb == 9) {
           // ---- tails of taps 0..7: warp wig owns tap wig (chunk wig), lane = row
           const int tap = wig;
+          acquire_stage();
 #pragma unroll
           for (int batch = 0; batch < 2; ++batch) {
             uint4 v[2][4];
@@ -746,7 +763,9 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
                   lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], s.geo_w[gb][tap][r]);
             }
           }
-        } else if (wig < 4) {
+        } else {
+          acquire_stage();
+          if (wig < 4) {
           // ---- tail of tap 8 (chunk 0) and the zero chunk 1 of the last UMMA_K step
           const int r = wig * 32 + lane;
           uint4 v[4];
@@ -757,6 +776,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
           if (!(bx & V5_INSIDE)) gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][8][r], v);
           *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk(v[0], v[1], v[2], v[3], s.geo_w[gb][8][r]);
           *reinterpret_cast<uint4*>(a_stage + r * 128 + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -774,11 +794,11 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
       constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase[2] = {0, 0};
       for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);
+        mbar_wait_t(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1, dbg, w0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
         for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
-          mbar_wait(smem_u32(&s.full[stage]), phase);
+          mbar_wait_t(smem_u32(&s.full[stage]), phase, dbg, w1);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[stage][0]));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[stage][0]));
@@ -798,7 +818,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
     if (lane == 0) {
       for (int it = 0; it < my_tiles; ++it) {
         const int sb = it & 1;
-        mbar_wait(smem_u32(&s.src_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old box
+        mbar_wait_t(smem_u32(&s.src_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, dbg, w0);   // producers are done with the old box
         int b, ty0, tx0;
         tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
         const int by0 = ty0 - V5_BOX_TOP, bx0 = tx0 - V5_BOX_LEFT;
@@ -823,52 +843,51 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
 
     auto make_geometry = [&](int it) {
       const int gb = it & 1;
-      mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      mbar_wait_t(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, dbg, w0);
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
       const int by0 = ty0 - V5_BOX_TOP, bx0 = tx0 - V5_BOX_LEFT;
       if (y < p.H && x < p.W) {
+        // all 27 offset / mask values of this pixel are requested before the first one is used: one DRAM round trip per
+        // tile instead of three (the producers were waiting 12 % of their time for this stage)
+        const int f_sc = (int)p.f_sc, m_sc = (int)p.m_sc;
         const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
         const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
         const int base = b * p.H * p.W;
+        TO rdy[9], rdx[9], rmk[9];
 #pragma unroll
-        for (int k0 = 0; k0 < 9; k0 += 3) {
-          TO rdy[3], rdx[3], rmk[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int k = k0 + i, j0 = 2 * k, j1 = 2 * k + 1;
-            if (p.fused27) {
-              rdy[i] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * p.f_sc);
-              rdx[i] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * p.f_sc);
-              rmk[i] = __ldg(msk + (9 + k) * p.m_sc);
-            } else {
-              rdy[i] = __ldg(off + j0 * p.f_sc);
-              rdx[i] = __ldg(off + j1 * p.f_sc);
-              rmk[i] = __ldg(msk + k * p.m_sc);
-            }
+        for (int k = 0; k < 9; ++k) {
+          const int j0 = 2 * k, j1 = 2 * k + 1;
+          if (p.fused27) {
+            rdy[k] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
+            rdx[k] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
+            rmk[k] = __ldg(msk + (9 + k) * m_sc);
+          } else {
+            rdy[k] = __ldg(off + j0 * f_sc);
+            rdx[k] = __ldg(off + j1 * f_sc);
+            rmk[k] = __ldg(msk + k * m_sc);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int k = k0 + i;
-            float mk = to_f32<TO>(rmk[i]);
-            if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
-            uint32_t pixf;
-            uint2 wq;
-            tc_geo_entry<uint2>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[i]), to_f32<TO>(rdx[i]), mk, pixf, wq);
-            // position of the (clamped) corner 00 inside the staged box; the step flags are those of pixf
-            const int pix00 = (int)(pixf & 0x3fffffffu) - base;
-            const int cy = pix00 / p.W, cx = pix00 - cy * p.W;
-            const int sx = (int)((pixf >> 30) & 1u), sy = (int)(pixf >> 31);
-            const int ry = cy - by0, rx = cx - bx0;
-            const bool dead = (wq.x | wq.y) == 0u;                       // all four weights are (+)0: value irrelevant
-            const bool in = ry >= 0 && ry + sy < V5_BOX_H && rx >= 0 && rx + sx < V5_BOX_W;
-            uint32_t box = (in && !dead) ? (uint32_t)(ry * V5_BOX_W + rx) | ((uint32_t)sx << 16) | ((uint32_t)sy << 17) : V5_SAFE;
-            if (in || dead) box |= V5_INSIDE;
-            s.geo_pix[gb][k][row] = pixf;
-            s.geo_box[gb][k][row] = box;
-            s.geo_w[gb][k][row] = wq;
-          }
+        for (int k = 0; k < 9; ++k) {
+          float mk = to_f32<TO>(rmk[k]);
+          if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
+          uint32_t pixf;
+          uint2 wq;
+          tc_geo_entry<uint2>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[k]), to_f32<TO>(rdx[k]), mk, pixf, wq);
+          // position of the (clamped) corner 00 inside the staged box; the step flags are those of pixf
+          const int pix00 = (int)(pixf & 0x3fffffffu) - base;
+          const int cy = pix00 / p.W, cx = pix00 - cy * p.W;
+          const int sx = (int)((pixf >> 30) & 1u), sy = (int)(pixf >> 31);
+          const int ry = cy - by0, rx = cx - bx0;
+          const bool dead = (wq.x | wq.y) == 0u;                       // all four weights are (+)0: value irrelevant
+          const bool in = ry >= 0 && ry + sy < V5_BOX_H && rx >= 0 && rx + sx < V5_BOX_W;
+          uint32_t box = (in && !dead) ? (uint32_t)(ry * V5_BOX_W + rx) | ((uint32_t)sx << 16) | ((uint32_t)sy << 17) : V5_SAFE;
+          if (in || dead) box |= V5_INSIDE;
+          s.geo_pix[gb][k][row] = pixf;
+          s.geo_box[gb][k][row] = box;
+          s.geo_w[gb][k][row] = wq;
         }
       } else {
 #pragma unroll
@@ -885,7 +904,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
       if (it + 1 < my_tiles) make_geometry(it + 1);
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
+      mbar_wait_t(smem_u32(&s.acc_full[acc]), acc_phase[acc], dbg, w1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
@@ -934,6 +953,10 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
     }
   }
 
+  if (dbg && lane == 0) {
+    unsigned long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
+    d[0] = (unsigned long long)(clock64() - t_begin); d[1] = w0; d[2] = w1; d[3] = w2; d[4] = w3; d[5] = my_tiles;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) {
@@ -1003,6 +1026,17 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
 
 }  // namespace
 
+// VFI_DCN_DEBUG=1: per-warp wait-cycle counters of the last v5 launch, [256 CTAs][32 warps][8] u64 (diagnostics only).
+unsigned long long* dcn_tc_debug_buffer() {
+  static unsigned long long* buf = [] {
+    unsigned long long* b = nullptr;
+    const char* e = getenv("VFI_DCN_DEBUG");
+    if (e && e[0] == '1' && cudaMalloc(&b, 256 * 32 * 8 * sizeof(unsigned long long)) != cudaSuccess) b = nullptr;
+    return b;
+  }();
+  return buf;
+}
+
 // dense channels-last bf16 plane [B,H,W,C] with a pixel stride of exactly `stride` elements, 16-byte aligned
 static bool is_plane(const vfi_tensor* t, long long stride) {
   return t->dtype == VFI_BF16 && t->sc == 1 && t->sw == stride && t->sh == t->w * stride && t->sn == t->h * t->w * stride &&
@@ -1067,6 +1101,8 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   if (P == 0) return VFI_OK;
   VFI_REQUIRE(x->data && offset->data && mask->data && out->data, VFI_ERR_INVALID, "%s: null data pointer", who);
   VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "%s(bf16_tc): more than 2^30 pixels per call", who);
+  VFI_REQUIRE(27 * llabs(offset->sc) < 2147483647LL && 27 * llabs(mask->sc) < 2147483647LL, VFI_ERR_UNSUPPORTED,
+              "%s(bf16_tc): offset/mask channel stride too large for 32-bit indexing", who);
 
   TcParams p;
   if (out_tail) {
@@ -1115,13 +1151,17 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   p.B = (int)x->n; p.H = (int)x->h; p.W = (int)x->w; p.O = (int)O;
   p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y;
+  p.debug = dcn_tc_debug_buffer();
   int dev = 0, sms = 148;
   VFI_CUDA(cudaGetDevice(&dev));
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
-  static const bool force_v4 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '4'; }();
-  if (!hq && !force_v4) {
+  // Kernel variant.  Default: v4 (gathers through L1).  VFI_DCN_KERNEL=v5 selects the variant that stages each tile's
+  // source box in shared memory; measured 7.56 vs 7.27 ms per layer at cfg2 -- both are limited by shared-memory/L1
+  // bandwidth shared between the gathers and the tensor core's own operand reads, not by where the gather hits.
+  static const bool use_v5 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '5'; }();
+  if (!hq && use_v5) {
     // v5: source box staged in shared memory (fast-path arithmetic only; the HQ geometry does not fit next to the boxes)
     const size_t smem5 = sizeof(TcSmem5) + 1024;
     VFI_DISPATCH(offset->dtype, TO, {
