@@ -39,6 +39,12 @@ FLOP_PER_PX = 2 * 603 * 67          # one DCNv2 layer, algorithmic (SURVEY.md se
 WARP_BYTES_PER_PX_BF16 = (3 + 2 + 3) * 2
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the hot kernels from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    f = ROOT / "profiles" / "traffic.json"
+    return json.loads(f.read_text()) if f.exists() else {}
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -301,6 +307,7 @@ def main():
         return
 
     pk = peaks()
+    tr = measured_traffic() if args.workload == "cfg2" else {}
     dcn_tflops = P * FLOP_PER_PX / (dcn_ms * 1e-3) / 1e12
     warp_gbs = P * WARP_BYTES_PER_PX_BF16 / (warp_ms * 1e-3) / 1e9
     line = {
@@ -314,13 +321,13 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "DCNv2 forward (one launch per layer, 3 per step)",
                      "achieved": dcn_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                     "frac": dcn_tflops / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+                     "frac": dcn_tflops / pk["tensor_sustained"], "traffic": tr.get("dcn_tc_fwd_kernel"), "peak_source": pk["source"] + " sustained bf16",
                      "frac_of_burst_peak": dcn_tflops / pk["tensor_burst"], "ms_per_launch": dcn_ms,
                      "algorithmic_flop_per_launch": P * FLOP_PER_PX},
         "roofline_warp": {"bound": "hbm", "kernel": "warp_fwd (planar NCHW bf16 in/out, timed alone, 20 launches)",
                           "achieved": P * WARP_BYTES_PER_PX_BF16 / (planar_ms["bf16"] * 1e-3) / 1e9, "peak": pk["hbm"],
                           "unit": "GB/s", "frac": P * WARP_BYTES_PER_PX_BF16 / (planar_ms["bf16"] * 1e-3) / 1e9 / pk["hbm"],
-                          "traffic": None, "ms_per_launch": planar_ms["bf16"],
+                          "traffic": tr.get("warp_fwd_kernel_bf16_planar"), "ms_per_launch": planar_ms["bf16"],
                           "algorithmic_bytes_per_launch": P * WARP_BYTES_PER_PX_BF16, "peak_source": pk["source"],
                           "f32": {"ms_per_launch": planar_ms["f32"],
                                   "achieved": 2 * P * WARP_BYTES_PER_PX_BF16 / (planar_ms["f32"] * 1e-3) / 1e9,

@@ -2,6 +2,7 @@
 import os, sys
 os.environ["VFI_DCN_DEBUG"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ['VFI_DCN_KERNEL'] = 'v5'
 import numpy as np, torch, ctypes
 import vfi_b200
 from vfi_b200 import ops, _lib
@@ -23,7 +24,7 @@ def show(name, warps, labels):
     tot = x[..., 0].mean()
     print(f"{name:10s} total {tot/1e3:8.1f} kcyc  " + "  ".join(f"{l} {x[..., i+1].mean()/tot*100:5.1f}%" for i, l in enumerate(labels)))
 show("producers", list(range(24)), ["geo_full", "src_full", "stage_empty"])
-show("mma", [24], ["acc_empty", "stage_full"])
+show("mma", [24], ["acc_empty", "stage_full", "mma_issue", "commit"])
 show("epilogue", [25, 26, 27, 28], ["geo_empty", "acc_full"])
 show("copy", [29], ["src_empty"])
 print("tiles per CTA", d[:, 0, 5].mean(), " cycles per tile", d[:, 0, 0].mean() / d[:, 0, 5].mean())

@@ -50,7 +50,7 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_GROUPS = 3;                         // producer groups; group g fills stage g (K blocks n with n % 3 == g)
 constexpr int TC_GROUP_WARPS = 8;
 constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;   // 24
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4) * 32;   // + MMA issuer warp + 4 geometry/epilogue warps = 928
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4 + 1) * 32;   // + MMA issuer, 4 geometry/epilogue, 1 loader warp = 960
 static_assert(TC_GROUPS == TC_STAGES, "each producer group owns one pipeline stage");
 constexpr int TC_TMEM_COLS = 256;                    // two accumulators at column 0 and 128
 constexpr int TC_ACC_STRIDE = 128;
@@ -251,14 +251,22 @@ struct TcParams {
 template <bool HQ> struct TcGeoW { using type = uint2; };
 template <> struct TcGeoW<true> { using type = uint4; };
 
+// Operand rings are decoupled: A (written by the gather warps over ~1k cycles) has one more slot than there are producer
+// groups, so a group never waits for the tensor core to finish ITS previous block (measured: 26 % of producer time with
+// one slot per group); B (a 10 KB bulk copy per K block, the same 11 blocks for every tile) has its own 3-slot ring fed by
+// a dedicated lane.
+template <bool HQ> struct TcRing { static constexpr int A = 4, B = 3; };
+template <> struct TcRing<true> { static constexpr int A = 3, B = 3; };   // the fp32 geometry weights need the room
+
 template <bool HQ>
 struct __align__(1024) TcSmem {
-  uint8_t a[TC_STAGES][TC_A_BYTES];
-  uint8_t b[TC_STAGES][TC_B_BYTES];
+  uint8_t a[TcRing<HQ>::A][TC_A_BYTES];
+  uint8_t b[TcRing<HQ>::B][TC_B_BYTES];
   uint32_t geo_pix[2][10][TC_M];
   typename TcGeoW<HQ>::type geo_w[2][10][TC_M];
   float bias[TC_N];
-  unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], geo_full[2], geo_empty[2];
+  unsigned long long a_full[TcRing<HQ>::A], a_empty[TcRing<HQ>::A], b_full[TcRing<HQ>::B], b_empty[TcRing<HQ>::B];
+  unsigned long long acc_full[2], acc_empty[2], geo_full[2], geo_empty[2];
   uint32_t tmem_base;
 };
 
@@ -347,14 +355,20 @@ __device__ __forceinline__ void gather4(const uint8_t* base, uint32_t stride, ui
 template <typename TO, typename TOUT, bool HQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParams p) {
   using GW = typename TcGeoW<HQ>::type;
+  constexpr int NA = TcRing<HQ>::A, NB = TcRing<HQ>::B;
+  constexpr int W_MMA = TC_PRODUCER_WARPS, W_LOAD = TC_PRODUCER_WARPS + 5;   // warps 25..28: geometry + epilogue
   extern __shared__ uint8_t smem_raw[];
   TcSmem<HQ>& s = *reinterpret_cast<TcSmem<HQ>*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(smem_u32(&s.full[i]), TC_GROUP_WARPS + 1);      // 8 warp arrivals + the expect_tx arrival of the B copy
-      mbar_init(smem_u32(&s.empty[i]), 1);                      // one tcgen05.commit
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(smem_u32(&s.a_full[i]), TC_GROUP_WARPS);        // the 8 warps of the producing group
+      mbar_init(smem_u32(&s.a_empty[i]), 1);                    // one tcgen05.commit
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(smem_u32(&s.b_full[i]), 1);                     // the loader's expect_tx arrival (+ the bytes)
+      mbar_init(smem_u32(&s.b_empty[i]), 1);                    // one tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
@@ -364,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     }
     fence_barrier_init();
   }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
+  if (warp == W_MMA) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
   if (tid < TC_N) s.bias[tid] = p.bias[tid];
   if (tid < 2 * TC_M) { s.geo_pix[tid >> 7][9][tid & 127] = 0u; s.geo_w[tid >> 7][9][tid & 127] = GW{}; }
   tc_fence_before();
@@ -389,8 +403,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
     const uint32_t a_off_main = (uint32_t)r_main * 128 + ((uint32_t)(j ^ (r_main & 7)) << 4);   // + 4096 * pass
     const uint8_t* src_main = p.x_main + j * 16;
     const uint32_t main_row = p.main_stride * (uint32_t)p.W, tail_row = p.tail_stride * (uint32_t)p.W;
-    uint8_t* a_stage = &s.a[group][0];
-    const uint32_t full_bar = smem_u32(&s.full[group]), empty_bar = smem_u32(&s.empty[group]);
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       mbar_wait(smem_u32(&s.geo_full[gb]), (uint32_t)(it >> 1) & 1u);      // this tile's geometry has been written
@@ -398,12 +410,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
       int kb = group - n0 % TC_GROUPS;
       if (kb < 0) kb += TC_GROUPS;
       for (; kb < TC_KBLOCKS; kb += TC_GROUPS) {        // blocks of this tile with (n0 + kb) % 3 == group
-        const uint32_t phase = (uint32_t)((n0 + kb) / TC_STAGES) & 1u;
-        mbar_wait(empty_bar, phase ^ 1);
-        if (wig == 0 && lane == 0) {
-          mbar_arrive_expect_tx(full_bar, TC_B_BYTES);
-          bulk_g2s(smem_u32(&s.b[group][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, full_bar);
-        }
+        const int n = n0 + kb, sa = n % NA;
+        uint8_t* a_stage = &s.a[sa][0];
+        const uint32_t full_bar = smem_u32(&s.a_full[sa]);
+        mbar_wait(smem_u32(&s.a_empty[sa]), ((uint32_t)(n / NA) & 1u) ^ 1u);
         if (kb < 9) {
           // ---- the 64 main channels of tap kb: one aligned 128 B line per (row, corner), 8 lanes each
           const uint32_t* gp = &s.geo_pix[gb][kb][r_main];
@@ -450,29 +460,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s.geo_empty[gb]));   // this warp no longer reads geometry buffer gb
     }
-  } else if (warp == TC_PRODUCER_WARPS) {
+  } else if (warp == W_MMA) {
     // =========================================================================== MMA issuer (one lane)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase[2] = {0, 0};
+      uint32_t acc = 0, acc_phase[2] = {0, 0};
+      int n = 0;                                         // global K-block counter of this CTA
       for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
-        for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
-          mbar_wait(smem_u32(&s.full[stage]), phase);
+        for (int kb = 0; kb < TC_KBLOCKS; ++kb, ++n) {
+          const int sa = n % NA, sb = n % NB;
+          mbar_wait(smem_u32(&s.b_full[sb]), (uint32_t)(n / NB) & 1u);
+          mbar_wait(smem_u32(&s.a_full[sa]), (uint32_t)(n / NA) & 1u);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[stage][0]));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[stage][0]));
+          const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[sa][0]));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[sb][0]));
           const int nk = (kb == TC_KBLOCKS - 1) ? 1 : 4;
           for (int k = 0; k < nk; ++k)                   // +32 B along K inside the 128 B swizzle atom = +2 encoded
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(smem_u32(&s.empty[stage]));        // stage reusable once these MMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(smem_u32(&s.a_empty[sa]));         // both slots reusable once these MMAs have read them
+          umma_commit(smem_u32(&s.b_empty[sb]));
         }
         umma_commit(smem_u32(&s.acc_full[acc]));         // accumulator complete
         acc_phase[acc] ^= 1;
         acc ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_LOAD) {
+    // =========================================================================== weight-block loader (one lane)
+    if (lane == 0) {
+      const int total = my_tiles * TC_KBLOCKS;
+      int kb = 0;
+      for (int n = 0; n < total; ++n) {
+        const int sb = n % NB;
+        mbar_wait(smem_u32(&s.b_empty[sb]), ((uint32_t)(n / NB) & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&s.b_full[sb]);
+        mbar_arrive_expect_tx(bar, TC_B_BYTES);
+        bulk_g2s(smem_u32(&s.b[sb][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, bar);
+        if (++kb == TC_KBLOCKS) kb = 0;
       }
     }
     __syncwarp();
@@ -596,7 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_PRODUCER_WARPS) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
@@ -799,12 +827,15 @@ __global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcPara
         const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
         for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
           mbar_wait_t(smem_u32(&s.full[stage]), phase, dbg, w1);
+          const long long ti0 = dbg ? clock64() : 0;
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[stage][0]));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[stage][0]));
           const int nk = (kb == TC_KBLOCKS - 1) ? 1 : 4;
           for (int k = 0; k < nk; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          const long long ti1 = dbg ? clock64() : 0;
           umma_commit(smem_u32(&s.empty[stage]));
+          if (dbg) { w2 += ti1 - ti0; w3 += clock64() - ti1; }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&s.acc_full[acc]));
@@ -1158,8 +1189,10 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
   // Kernel variant.  Default: v4 (gathers through L1).  VFI_DCN_KERNEL=v5 selects the variant that stages each tile's
-  // source box in shared memory; measured 7.56 vs 7.27 ms per layer at cfg2 -- both are limited by shared-memory/L1
-  // bandwidth shared between the gathers and the tensor core's own operand reads, not by where the gather hits.
+  // source box in shared memory; measured 7.56 vs 7.03 ms per layer at cfg2.  Both are limited by the SM's L1/shared-memory
+  // array bandwidth, which the gathers, the A-stage stores, the bulk copies and the tensor core's own operand reads share
+  // (per-role counters, VFI_DCN_DEBUG: issuing one tcgen05.mma takes ~190 cycles because its smem operand reads queue
+  // behind the LSU traffic), not by where the gather hits.
   static const bool use_v5 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '5'; }();
   if (!hq && use_v5) {
     // v5: source box staged in shared memory (fast-path arithmetic only; the HQ geometry does not fit next to the boxes)
