@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--impl", default="vfi_b200", choices=["vfi_b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "bf16_tc"])
-    ap.add_argument("--dcn-kernel", default="", choices=["", "v4", "v5"], help="A/B switch for the tcgen05 DCN kernel variant")
+    ap.add_argument("--dcn-kernel", default="", choices=["", "v4", "v6"], help="A/B switch for the tcgen05 DCN kernel variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")

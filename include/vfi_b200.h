@@ -147,6 +147,11 @@ int vfi_dcn_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vf
  * serialised; exercises exactly the shared-memory descriptors, swizzle, tcgen05.mma/commit/ld and TMEM allocation the
  * DCN kernel uses, so a wrong DCN result can be attributed to the tensor-core plumbing or to the gather. */
 int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream);
+/* D[128,80] = 2 * A[128,64] * B[80,64]^T with the A operand written to TENSOR MEMORY (once by tcgen05.st.16x256b with the
+ * thread <-> (lane, column) mapping the v6 DCN producers use, once by tcgen05.st.32x32b) and consumed by the A-from-TMEM
+ * form of tcgen05.mma.  raw [128][32] u32 receives the TMEM image of the first copy (K elements 2c, 2c+1 of row r at
+ * raw[r][c]) so a wrong mapping can be decoded on the host. */
+int vfi_selftest_umma_ts(const void* a_bf16, const void* b_bf16, float* d, uint32_t* raw, vfi_stream_t stream);
 /* With VFI_DCN_DEBUG=1 in the environment the staged tcgen05 DCN kernel records, per CTA and warp, the cycles spent in
  * each of its pipeline waits; this copies `count` u64 counters ([cta][32 warps][8]) of the last launch to host memory
  * (synchronises the device). */

@@ -350,10 +350,27 @@ def test_dcn_fused_split_input_and_conv27(math, bar):
     assert relerr(out3.to_nchw(), ref) <= bar
 
 
-def test_dcn_staged_variant_matches_default_kernel():
-    """VFI_DCN_KERNEL=v5 (source box staged in shared memory, global fallback for far offsets) in a fresh process: must
-    give bit-identical planes to the default kernel -- same arithmetic, different data path -- including the fallback
-    path (sigma = 6 px) and image borders."""
+def test_umma_ts_selftest_matches_matmul():
+    """The plumbing v6 adds: A written to tensor memory by tcgen05.st (16x256b with the producers' thread mapping, and
+    32x32b) and consumed by the A-from-TMEM MMA form.  The raw TMEM image must be A itself (row r = lane r, 32-bit column c
+    = K elements 2c, 2c+1)."""
+    from vfi_b200 import ops
+
+    g = torch.Generator().manual_seed(22)
+    a = torch.randn(128, 64, generator=g).to(torch.bfloat16).to(DEV)
+    b = torch.randn(80, 64, generator=g).to(torch.bfloat16).to(DEV)
+    d, raw = ops.selftest_umma_ts(a, b)
+    want_raw = a.contiguous().view(torch.int32).reshape(128, 32)
+    assert torch.equal(raw, want_raw), "tcgen05.st.16x256b thread <-> (lane, column) mapping differs from the one assumed"
+    ref = 2.0 * (a.float() @ b.float().t())
+    assert maxabs(d, ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_dcn_kernel_variants_agree():
+    """VFI_DCN_KERNEL=v4 (gather through L1 into a shared-memory A ring) against the default v6 (A in tensor memory,
+    source box staged in shared memory) in fresh processes: same blend arithmetic, different K order inside the tensor
+    core, so outputs may differ by one bf16 rounding.  sigma = 6 px exercises v6's out-of-box global path, 45 x 83 its
+    partial tiles and image borders."""
     import os
     import subprocess
     import sys
@@ -380,14 +397,15 @@ torch.save(y.cpu(), sys.argv[1])
 
     outs = []
     with tempfile.TemporaryDirectory() as d:
-        for variant in ("v4", "v5"):
+        for variant in ("v4", "v6"):
             path = os.path.join(d, variant + ".pt")
             env = dict(os.environ, VFI_DCN_KERNEL=variant)
             r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, r.stderr[-2000:]
-            outs.append(torch.load(path))
-    assert torch.isfinite(outs[0].float()).all()
-    assert torch.equal(outs[0], outs[1])
+            outs.append(torch.load(path).float())
+    assert torch.isfinite(outs[0]).all() and torch.isfinite(outs[1]).all()
+    assert relerr(outs[1], outs[0]) <= 5e-3                       # one bf16 ulp of the largest value
+    assert float((outs[0] != outs[1]).float().mean()) <= 0.05
 
 
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():

@@ -26,7 +26,8 @@ bool dcn_tc_available();
 size_t dcn_tc_workspace_bytes(long long B, long long H, long long W);
 size_t dcn_tc_packed_weight_bytes();
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
-                       void* packed, float* bias_out, cudaStream_t st);
+                       void* packed, float* bias_out, cudaStream_t st, int variant);
+int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 unsigned long long* dcn_tc_debug_buffer();
 int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
@@ -82,7 +83,7 @@ extern "C" size_t vfi_dcn_packed_weight_bytes(void) { return dcn_tc_packed_weigh
 
 extern "C" int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
                                    vfi_stream_t stream) {
-  return dcn_tc_pack_weight(weight, weight_dtype, nullptr, VFI_F32, O, C, packed, nullptr, (cudaStream_t)stream);
+  return dcn_tc_pack_weight(weight, weight_dtype, nullptr, VFI_F32, O, C, packed, nullptr, (cudaStream_t)stream, 4);
 }
 
 extern "C" int vfi_dcn_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, vfi_stream_t stream) {
@@ -106,6 +107,10 @@ extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const 
 
 extern "C" int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream) {
   return umma_selftest(a_bf16, b_bf16, d, K, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_selftest_umma_ts(const void* a_bf16, const void* b_bf16, float* d, uint32_t* raw, vfi_stream_t stream) {
+  return umma_ts_selftest(a_bf16, b_bf16, d, raw, (cudaStream_t)stream);
 }
 
 extern "C" int vfi_dcn_fwd_fused(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* conv27,

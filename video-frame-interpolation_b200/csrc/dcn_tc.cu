@@ -174,14 +174,18 @@ __host__ __device__ inline void tc_k_to_tap_channel(int kb, int kk, int& tap, in
   else { tap = 0; c = -1; }
 }
 
+__host__ __device__ inline void v6_k_to_tap_channel(int kb, int kk, int& tap, int& c);   // dcn_tc6.cuh
+
+// variant 4: the K order of the v4 kernel (11 blocks); variant 6: that of v6 (10 blocks, block 10 left zero)
 template <typename TW>
 __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, int bias_dtype, int O, int C,
-                                   uint8_t* __restrict__ packed, float* __restrict__ bias_out) {
+                                   uint8_t* __restrict__ packed, float* __restrict__ bias_out, int variant) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < TC_KBLOCKS * TC_N * 64) {
     int kb = idx / (TC_N * 64), o = (idx / 64) % TC_N, kk = idx % 64;
     int tap, c;
-    tc_k_to_tap_channel(kb, kk, tap, c);
+    if (variant == 6) v6_k_to_tap_channel(kb, kk, tap, c);
+    else tc_k_to_tap_channel(kb, kk, tap, c);
     float v = 0.0f;
     if (o < O && c >= 0 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + tap]);
     size_t off = (size_t)kb * TC_B_BYTES + (size_t)o * 128 + ((((kk >> 3) ^ (o & 7))) << 4) + (kk & 7) * 2;
@@ -630,371 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
   }
 }
 
-// ------------------------------------------------------------------------------------------------ v5: staged source
-// Same GEMM, same pipeline, but the producers gather from SHARED MEMORY: for every tile a 16 x 22 pixel box of the
-// activation planes (the tile, the 3x3 reach and a halo of 3 rows / 2 columns) is brought in by 1-D bulk copies
-// (cp.async.bulk, one per box row and plane, issued a full tile ahead by a dedicated lane and double buffered).  Why: the
-// L1-resident gather of v4 is bound by its compulsory misses -- all nine taps walk the same ~500 lines, so the first
-// K blocks of every tile wait on L2 while 24 warps sit in long-scoreboard stalls (ncu: LSU data pipe 78 % busy, an
-// L1-hit LDG.128 alone sustains 110 B/cycle/SM in scripts/microbench/l1_gather.cu).  With the box in shared memory every
-// gather is a 30-cycle LDS.128 at 127 B/cycle/SM, and the HBM/L2 -> SM traffic is one streaming pass done by the TMA engine.
-// Samples whose corners fall outside the box (|offset| > 3 rows or > 2 columns beyond the 3x3 reach; ~2 % at sigma = 1.5 px)
-// take the v4 global-memory path lane by lane.  Image borders need no zero fill: the geometry clamps corner coordinates
-// into the image (zero weight), so only in-image pixels are ever read and only the in-image part of a box is copied.
-constexpr int V5_BOX_H = 16, V5_BOX_W = 22, V5_BOX_PX = V5_BOX_H * V5_BOX_W;      // 352 pixels
-constexpr int V5_BOX_TOP = 4, V5_BOX_LEFT = 3;                                       // box origin = tile origin - (4, 3)
-constexpr int V5_THREADS = (TC_PRODUCER_WARPS + 1 + 4 + 1) * 32;                     // + one copy-issuing warp = 960
-constexpr uint32_t V5_INSIDE = 0x80000000u;
-// Box index of the tile's own first pixel: always inside the image and always copied.  Zero-weight entries (dead samples,
-// padding rows, the zero K chunk) point here so that they never multiply 0 by uninitialised shared memory (0 * NaN).
-constexpr uint32_t V5_SAFE = V5_BOX_TOP * V5_BOX_W + V5_BOX_LEFT;
-
-struct __align__(1024) TcSmem5 {
-  uint8_t a[TC_STAGES][TC_A_BYTES];
-  uint8_t b[TC_STAGES][TC_B_BYTES];
-  uint8_t src_main[2][V5_BOX_PX * TC_CMAIN * 2];       // 2 x 45,056 B
-  uint8_t src_tail[2][V5_BOX_PX * TC_CTAIL * 2];       // 2 x  5,632 B
-  uint32_t geo_pix[2][10][TC_M];                       // as in v4 (global pixel index + corner step flags)
-  uint32_t geo_box[2][10][TC_M];                       // bit 31: all four corners are inside the staged box; low bits: box pixel index
-  uint2 geo_w[2][10][TC_M];
-  float bias[TC_N];
-  unsigned long long full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], geo_full[2], geo_empty[2], src_full[2],
-      src_empty[2];
-  uint32_t tmem_base;
-};
-
-__device__ __forceinline__ uint4 lds16(uint32_t saddr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
-  return r;
-}
-
-template <typename TO, typename TOUT>
-__global__ void __launch_bounds__(V5_THREADS, 1) dcn_tc5_fwd_kernel(const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  TcSmem5& s = *reinterpret_cast<TcSmem5*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int W_MMA = TC_PRODUCER_WARPS, W_COPY = TC_PRODUCER_WARPS + 5;   // warps 25..28: geometry + epilogue
-
-  if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(smem_u32(&s.full[i]), TC_GROUP_WARPS + 1);
-      mbar_init(smem_u32(&s.empty[i]), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&s.acc_full[i]), 1);
-      mbar_init(smem_u32(&s.acc_empty[i]), 4);
-      mbar_init(smem_u32(&s.geo_full[i]), 4);
-      mbar_init(smem_u32(&s.geo_empty[i]), TC_PRODUCER_WARPS);
-      mbar_init(smem_u32(&s.src_full[i]), 1);                   // the copy lane's expect_tx arrival (+ the bytes)
-      mbar_init(smem_u32(&s.src_empty[i]), TC_PRODUCER_WARPS);
-    }
-    fence_barrier_init();
-  }
-  if (warp == W_MMA) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
-  if (tid < TC_N) s.bias[tid] = p.bias[tid];
-  if (tid < 2 * TC_M) {
-    s.geo_pix[tid >> 7][9][tid & 127] = 0u;
-    s.geo_box[tid >> 7][9][tid & 127] = V5_INSIDE | V5_SAFE;
-    s.geo_w[tid >> 7][9][tid & 127] = make_uint2(0u, 0u);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = s.tmem_base;
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
-  const bool dbg = p.debug != nullptr;
-  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;              // cycles spent in this role's waits (debug only)
-  const long long t_begin = clock64();
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // =========================================================================== A-operand producers
-    const int group = warp >> 3, wig = warp & 7;
-    const int rsub = lane >> 3, j = lane & 7;
-    const int r_main = 4 * wig + rsub;
-    const uint32_t a_off_main = (uint32_t)r_main * 128 + ((uint32_t)(j ^ (r_main & 7)) << 4);
-    const uint8_t* gsrc_main = p.x_main + j * 16;
-    const uint32_t main_row = p.main_stride * (uint32_t)p.W, tail_row = p.tail_stride * (uint32_t)p.W;
-    uint8_t* a_stage = &s.a[group][0];
-    const uint32_t full_bar = smem_u32(&s.full[group]), empty_bar = smem_u32(&s.empty[group]);
-    for (int it = 0; it < my_tiles; ++it) {
-      const int gb = it & 1;
-      const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait_t(smem_u32(&s.geo_full[gb]), tphase, dbg, w0);      // this tile's geometry has been written
-      mbar_wait_t(smem_u32(&s.src_full[gb]), tphase, dbg, w1);      // this tile's source box has landed in shared memory
-      const uint32_t box_main = smem_u32(&s.src_main[gb][0]) + j * 16, box_tail = smem_u32(&s.src_tail[gb][0]);
-      const int n0 = it * TC_KBLOCKS;
-      int kb = group - n0 % TC_GROUPS;
-      if (kb < 0) kb += TC_GROUPS;
-      for (; kb < TC_KBLOCKS; kb += TC_GROUPS) {
-        const uint32_t phase = (uint32_t)((n0 + kb) / TC_STAGES) & 1u;
-        // The stage buffer is only needed when the first lerp result is stored: the gathers of the first batch are
-        // issued BEFORE waiting for the tensor core to release the stage, so the MMA + commit latency of this group's
-        // previous block overlaps with shared-memory load latency instead of adding to it.
-        auto acquire_stage = [&]() {
-          mbar_wait_t(empty_bar, phase ^ 1, dbg, w2);
-          if (wig == 0 && lane == 0) {
-            mbar_arrive_expect_tx(full_bar, TC_B_BYTES);
-            bulk_g2s(smem_u32(&s.b[group][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, full_bar);
-          }
-        };
-        if (kb < 9) {
-          // ---- the 64 main channels of tap kb: 8 lanes read one pixel's 128 B from the staged box
-          const uint32_t* gx = &s.geo_box[gb][kb][r_main];
-          const uint32_t* gp = &s.geo_pix[gb][kb][r_main];
-          const uint2* gw = &s.geo_w[gb][kb][r_main];
-#pragma unroll
-          for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4];
-            uint32_t bx[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              bx[q] = gx[(batch * 2 + q) * 32];
-              const uint32_t a00 = box_main + (bx[q] & 0xffffu) * (TC_CMAIN * 2);
-              const uint32_t dx = (bx[q] & 0x10000u) ? TC_CMAIN * 2 : 0u, dy = (bx[q] & 0x20000u) ? V5_BOX_W * TC_CMAIN * 2 : 0u;
-              v[q][0] = lds16(a00); v[q][1] = lds16(a00 + dx); v[q][2] = lds16(a00 + dy); v[q][3] = lds16(a00 + dy + dx);
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q)     // rare: a corner of this row lies outside the box -> global memory (v4 path)
-              if (!(bx[q] & V5_INSIDE)) gather4(gsrc_main, p.main_stride, main_row, gp[(batch * 2 + q) * 32], v[q]);
-            if (batch == 0) acquire_stage();
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              *reinterpret_cast<uint4*>(a_stage + a_off_main + (batch * 2 + q) * 4096) =
-                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], gw[(batch * 2 + q) * 32]);
-          }
-        } else if (kb == 9) {
-          // ---- tails of taps 0..7: warp wig owns tap wig (chunk wig), lane = row
-          const int tap = wig;
-          acquire_stage();
-#pragma unroll
-          for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4];
-            uint32_t bx[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int r = (batch * 2 + q) * 32 + lane;
-              bx[q] = s.geo_box[gb][tap][r];
-              const uint32_t a00 = box_tail + (bx[q] & 0xffffu) * (TC_CTAIL * 2);
-              const uint32_t dx = (bx[q] & 0x10000u) ? TC_CTAIL * 2 : 0u, dy = (bx[q] & 0x20000u) ? V5_BOX_W * TC_CTAIL * 2 : 0u;
-              v[q][0] = lds16(a00); v[q][1] = lds16(a00 + dx); v[q][2] = lds16(a00 + dy); v[q][3] = lds16(a00 + dy + dx);
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              if (!(bx[q] & V5_INSIDE))
-                gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][tap][(batch * 2 + q) * 32 + lane], v[q]);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int r = (batch * 2 + q) * 32 + lane;
-              *reinterpret_cast<uint4*>(a_stage + r * 128 + ((tap ^ (r & 7)) << 4)) =
-                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], s.geo_w[gb][tap][r]);
-            }
-          }
-        } else {
-          acquire_stage();
-          if (wig < 4) {
-          // ---- tail of tap 8 (chunk 0) and the zero chunk 1 of the last UMMA_K step
-          const int r = wig * 32 + lane;
-          uint4 v[4];
-          const uint32_t bx = s.geo_box[gb][8][r];
-          const uint32_t a00 = box_tail + (bx & 0xffffu) * (TC_CTAIL * 2);
-          const uint32_t dx = (bx & 0x10000u) ? TC_CTAIL * 2 : 0u, dy = (bx & 0x20000u) ? V5_BOX_W * TC_CTAIL * 2 : 0u;
-          v[0] = lds16(a00); v[1] = lds16(a00 + dx); v[2] = lds16(a00 + dy); v[3] = lds16(a00 + dy + dx);
-          if (!(bx & V5_INSIDE)) gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][8][r], v);
-          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk(v[0], v[1], v[2], v[3], s.geo_w[gb][8][r]);
-          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar);
-      }
-      __syncwarp();
-      if (lane == 0) {                                   // this warp no longer reads geometry / source buffer gb
-        mbar_arrive(smem_u32(&s.geo_empty[gb]));
-        mbar_arrive(smem_u32(&s.src_empty[gb]));
-      }
-    }
-  } else if (warp == W_MMA) {
-    // =========================================================================== MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase[2] = {0, 0};
-      for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait_t(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1, dbg, w0);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
-        for (int kb = 0; kb < TC_KBLOCKS; ++kb) {
-          mbar_wait_t(smem_u32(&s.full[stage]), phase, dbg, w1);
-          const long long ti0 = dbg ? clock64() : 0;
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[stage][0]));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[stage][0]));
-          const int nk = (kb == TC_KBLOCKS - 1) ? 1 : 4;
-          for (int k = 0; k < nk; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          const long long ti1 = dbg ? clock64() : 0;
-          umma_commit(smem_u32(&s.empty[stage]));
-          if (dbg) { w2 += ti1 - ti0; w3 += clock64() - ti1; }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(smem_u32(&s.acc_full[acc]));
-        acc_phase[acc] ^= 1;
-        acc ^= 1;
-      }
-    }
-    __syncwarp();
-  } else if (warp == W_COPY) {
-    // =========================================================================== source-box copies (one lane)
-    if (lane == 0) {
-      for (int it = 0; it < my_tiles; ++it) {
-        const int sb = it & 1;
-        mbar_wait_t(smem_u32(&s.src_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, dbg, w0);   // producers are done with the old box
-        int b, ty0, tx0;
-        tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-        const int by0 = ty0 - V5_BOX_TOP, bx0 = tx0 - V5_BOX_LEFT;
-        const int ya = max(by0, 0), yb = min(by0 + V5_BOX_H, p.H), xa = max(bx0, 0), xb = min(bx0 + V5_BOX_W, p.W);
-        const uint32_t ncol = (uint32_t)(xb - xa), nrow = (uint32_t)(yb - ya);
-        const uint32_t bar = smem_u32(&s.src_full[sb]);
-        mbar_arrive_expect_tx(bar, nrow * ncol * (TC_CMAIN + TC_CTAIL) * 2);
-        for (int y = ya; y < yb; ++y) {
-          const size_t gpix = (size_t)(b * p.H + y) * p.W + xa;
-          const uint32_t bpix = (uint32_t)((y - by0) * V5_BOX_W + (xa - bx0));
-          bulk_g2s(smem_u32(&s.src_main[sb][0]) + bpix * (TC_CMAIN * 2), p.x_main + gpix * p.main_stride, ncol * TC_CMAIN * 2, bar);
-          bulk_g2s(smem_u32(&s.src_tail[sb][0]) + bpix * (TC_CTAIL * 2), p.x_tail + gpix * p.tail_stride, ncol * TC_CTAIL * 2, bar);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================================================================== geometry + epilogue (4 warps)
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    uint32_t acc = 0, acc_phase[2] = {0, 0};
-
-    auto make_geometry = [&](int it) {
-      const int gb = it & 1;
-      mbar_wait_t(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, dbg, w0);
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
-      const int by0 = ty0 - V5_BOX_TOP, bx0 = tx0 - V5_BOX_LEFT;
-      if (y < p.H && x < p.W) {
-        // all 27 offset / mask values of this pixel are requested before the first one is used: one DRAM round trip per
-        // tile instead of three (the producers were waiting 12 % of their time for this stage)
-        const int f_sc = (int)p.f_sc, m_sc = (int)p.m_sc;
-        const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
-        const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
-        const int base = b * p.H * p.W;
-        TO rdy[9], rdx[9], rmk[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const int j0 = 2 * k, j1 = 2 * k + 1;
-          if (p.fused27) {
-            rdy[k] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
-            rdx[k] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
-            rmk[k] = __ldg(msk + (9 + k) * m_sc);
-          } else {
-            rdy[k] = __ldg(off + j0 * f_sc);
-            rdx[k] = __ldg(off + j1 * f_sc);
-            rmk[k] = __ldg(msk + k * m_sc);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float mk = to_f32<TO>(rmk[k]);
-          if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
-          uint32_t pixf;
-          uint2 wq;
-          tc_geo_entry<uint2>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[k]), to_f32<TO>(rdx[k]), mk, pixf, wq);
-          // position of the (clamped) corner 00 inside the staged box; the step flags are those of pixf
-          const int pix00 = (int)(pixf & 0x3fffffffu) - base;
-          const int cy = pix00 / p.W, cx = pix00 - cy * p.W;
-          const int sx = (int)((pixf >> 30) & 1u), sy = (int)(pixf >> 31);
-          const int ry = cy - by0, rx = cx - bx0;
-          const bool dead = (wq.x | wq.y) == 0u;                       // all four weights are (+)0: value irrelevant
-          const bool in = ry >= 0 && ry + sy < V5_BOX_H && rx >= 0 && rx + sx < V5_BOX_W;
-          uint32_t box = (in && !dead) ? (uint32_t)(ry * V5_BOX_W + rx) | ((uint32_t)sx << 16) | ((uint32_t)sy << 17) : V5_SAFE;
-          if (in || dead) box |= V5_INSIDE;
-          s.geo_pix[gb][k][row] = pixf;
-          s.geo_box[gb][k][row] = box;
-          s.geo_w[gb][k][row] = wq;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          s.geo_pix[gb][k][row] = 0u; s.geo_box[gb][k][row] = V5_INSIDE | V5_SAFE; s.geo_w[gb][k][row] = make_uint2(0u, 0u);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
-    };
-
-    if (my_tiles > 0) make_geometry(0);
-    for (int it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles) make_geometry(it + 1);
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      mbar_wait_t(smem_u32(&s.acc_full[acc]), acc_phase[acc], dbg, w1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
-      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
-      const bool inside = y < p.H && x < p.W;
-      const size_t pixel = (size_t)(b * p.H + y) * p.W + x;
-      __nv_bfloat16* om = reinterpret_cast<__nv_bfloat16*>(p.out) + pixel * TC_CMAIN;
-      __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(p.out_tail) + pixel * TC_CTAIL;
-      TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
-#pragma unroll
-      for (int c16 = 0; c16 < TC_N / 16; ++c16) {
-        uint32_t d[16];
-        tmem_ld16(taddr + c16 * 16, d);
-        tmem_ld_wait();
-        if (c16 == TC_N / 16 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
-        }
-        if (inside) {
-          if (p.out_tail) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = c16 * 16 + h * 8;
-              if (c0 >= TC_CMAX) break;
-              uint32_t w4[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c0 + 2 * i],
-                                                          __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c0 + 2 * i + 1]);
-                w4[i] = *reinterpret_cast<uint32_t*>(&hv);
-              }
-              __nv_bfloat16* dst = c0 < TC_CMAIN ? om + c0 : ot;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c16 * 16 + i;
-              if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]) + s.bias[c]);
-            }
-          }
-        }
-      }
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
-    }
-  }
-
-  if (dbg && lane == 0) {
-    unsigned long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
-    d[0] = (unsigned long long)(clock64() - t_begin); d[1] = w0; d[2] = w1; d[3] = w2; d[4] = w3; d[5] = my_tiles;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
-  }
-}
+#include "dcn_tc6.cuh"   // v6: TMEM-resident A operand, source box staged in shared memory
 
 // ------------------------------------------------------------------------------------------------ UMMA self test
 // D[128, 80] = A[128, K] * Bm[80, K]^T with A, Bm row-major bf16 in global memory, K a multiple of 64.  Uses exactly
@@ -1057,7 +697,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __nv_bfloat
 
 }  // namespace
 
-// VFI_DCN_DEBUG=1: per-warp wait-cycle counters of the last v5 launch, [256 CTAs][32 warps][8] u64 (diagnostics only).
+// VFI_DCN_DEBUG=1: per-warp wait-cycle counters of the last launch, [256 CTAs][32 warps][8] u64 (diagnostics only).
 unsigned long long* dcn_tc_debug_buffer() {
   static unsigned long long* buf = [] {
     unsigned long long* b = nullptr;
@@ -1075,7 +715,7 @@ static bool is_plane(const vfi_tensor* t, long long stride) {
 }
 
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
-                       void* packed, float* bias_out, cudaStream_t st) {
+                       void* packed, float* bias_out, cudaStream_t st, int variant) {
   VFI_REQUIRE(weight && packed, VFI_ERR_INVALID, "vfi_dcn_pack_weight: null pointer");
   VFI_REQUIRE(O > 0 && O <= TC_N && C > 0 && C <= TC_CMAX, VFI_ERR_UNSUPPORTED,
               "vfi_dcn_pack_weight: tensor-core path supports C <= %d, O <= %d (got C=%lld, O=%lld)", TC_CMAX, TC_N, C, O);
@@ -1083,7 +723,7 @@ int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, i
   const int n = TC_KBLOCKS * TC_N * 64;
   VFI_DISPATCH(weight_dtype, TW, {
     pack_weight_kernel<TW><<<ceil_div(n, 256), 256, 0, st>>>(reinterpret_cast<const TW*>(weight), bias, bias_dtype, (int)O,
-                                                           (int)C, reinterpret_cast<uint8_t*>(packed), bias_out);
+                                                           (int)C, reinterpret_cast<uint8_t*>(packed), bias_out, variant);
   });
   VFI_LAUNCH_CHECK("pack_weight_kernel");
   return VFI_OK;
@@ -1163,7 +803,12 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
               "%s(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float* bias_ws = reinterpret_cast<float*>(ws + ws_bias_off());
-  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st);
+  // Kernel variant.  v6 (default): A operand in tensor memory, source box staged in shared memory (dcn_tc6.cuh); it takes
+  // the packed-bf16 blend and at most four tail channels (C <= 68).  v4 (VFI_DCN_KERNEL=v4, the HQ blend, C > 68): gathers
+  // through L1 into a shared-memory A ring.
+  static const bool force_v4 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '4'; }();
+  const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4;
+  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, use_v6 ? 6 : 4);
   if (rc) return rc;
   if (x_tail) {
     p.x_main = reinterpret_cast<const uint8_t*>(x->data);
@@ -1188,23 +833,16 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
-  // Kernel variant.  Default: v4 (gathers through L1).  VFI_DCN_KERNEL=v5 selects the variant that stages each tile's
-  // source box in shared memory; measured 7.56 vs 7.03 ms per layer at cfg2.  Both are limited by the SM's L1/shared-memory
-  // array bandwidth, which the gathers, the A-stage stores, the bulk copies and the tensor core's own operand reads share
-  // (per-role counters, VFI_DCN_DEBUG: issuing one tcgen05.mma takes ~190 cycles because its smem operand reads queue
-  // behind the LSU traffic), not by where the gather hits.
-  static const bool use_v5 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '5'; }();
-  if (!hq && use_v5) {
-    // v5: source box staged in shared memory (fast-path arithmetic only; the HQ geometry does not fit next to the boxes)
-    const size_t smem5 = sizeof(TcSmem5) + 1024;
+  if (use_v6) {
+    const size_t smem6 = sizeof(V6Smem) + 1024;
     VFI_DISPATCH(offset->dtype, TO, {
       VFI_DISPATCH(out_dtype, TOUT, {
-        auto kern = dcn_tc5_fwd_kernel<TO, TOUT>;
-        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-        kern<<<grid, V5_THREADS, smem5, st>>>(p);
+        auto kern = dcn_tc6_fwd_kernel<TO, TOUT>;
+        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+        kern<<<grid, V6_THREADS, smem6, st>>>(p);
       });
     });
-    VFI_LAUNCH_CHECK("dcn_tc5_fwd_kernel");
+    VFI_LAUNCH_CHECK("dcn_tc6_fwd_kernel");
     return VFI_OK;
   }
   const size_t smem = (hq ? sizeof(TcSmem<true>) : sizeof(TcSmem<false>)) + 1024;
@@ -1247,6 +885,16 @@ int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t s
   umma_selftest_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(A),
                                              reinterpret_cast<const __nv_bfloat16*>(Bm), D, K);
   VFI_LAUNCH_CHECK("umma_selftest_kernel");
+  return VFI_OK;
+}
+
+int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st) {
+  VFI_REQUIRE(A && Bm && D && raw, VFI_ERR_INVALID, "vfi_selftest_umma_ts: need A [128,64], B [80,64], D [128,80], raw [128,32]");
+  const size_t smem = TC_B_BYTES + 64 + 1024;
+  VFI_CUDA(cudaFuncSetAttribute(umma_ts_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_ts_selftest_kernel<<<1, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(A),
+                                                reinterpret_cast<const __nv_bfloat16*>(Bm), D, raw);
+  VFI_LAUNCH_CHECK("umma_ts_selftest_kernel");
   return VFI_OK;
 }
 

@@ -138,6 +138,20 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return d
 
 
+def selftest_umma_ts(a: torch.Tensor, b: torch.Tensor):
+    """Diagnostic: (2 * a @ b.T, raw TMEM image of a) for bf16 a [128,64], b [80,64] with the A operand staged in tensor
+    memory by tcgen05.st and consumed by the A-from-TMEM MMA form (the plumbing of the v6 DCN kernel)."""
+    dev = require_cuda(a, b)
+    assert a.dtype == b.dtype == torch.bfloat16 and tuple(a.shape) == (128, 64) and tuple(b.shape) == (80, 64)
+    a, b = a.contiguous(), b.contiguous()
+    d = torch.empty((128, 80), dtype=torch.float32, device=dev)
+    raw = torch.zeros((128, 32), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().vfi_selftest_umma_ts(a.data_ptr(), b.data_ptr(), d.data_ptr(), raw.data_ptr(), stream_handle(dev)),
+              "vfi_selftest_umma_ts")
+    return d, raw
+
+
 def dcn_workspace_bytes(B: int, C: int, O: int, H: int, W: int, math: str = "auto") -> int:
     return int(_lib.load().vfi_dcn_workspace_bytes(B, C, O, H, W, _MATH[math]))
 
