@@ -32,6 +32,7 @@
 //               half of a double buffer and prefetch its footprint into L2 while the producers gather tile i; then
 //               tcgen05.ld tile i's accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -94,22 +95,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uin
   return done != 0;
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity, 20000u)) {
-    __nanosleep(128);                                   // the hinted try_wait still returns early: do not burn issue slots
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
+  // try_wait itself suspends the thread in hardware (~100 cycles per attempt), so this loop is three instructions per
+  // attempt; a protocol bug traps (launch failure) after ~2^26 attempts instead of hanging the GPU.
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity, 100000u))
+    if (++spins > (1u << 26)) __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity, 2000u)) return;
   mbar_wait_slow(bar, parity);
-}
-// mbar_wait that adds the cycles spent waiting to `acc` (only used when the debug buffer is enabled)
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool timed, long long& acc) {
-  if (!timed) { mbar_wait(bar, parity); return; }
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -176,6 +170,12 @@ __host__ __device__ inline void tc_k_to_tap_channel(int kb, int kk, int& tap, in
 
 __host__ __device__ inline void v6_k_to_tap_channel(int kb, int kk, int& tap, int& c);   // dcn_tc6.cuh
 
+__device__ __forceinline__ float load_bias(const void* bias, int bias_dtype, int i) {
+  if (bias_dtype == VFI_F32) return reinterpret_cast<const float*>(bias)[i];
+  if (bias_dtype == VFI_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[i]);
+  return __half2float(reinterpret_cast<const __half*>(bias)[i]);
+}
+
 // variant 4: the K order of the v4 kernel (11 blocks); variant 6: that of v6 (10 blocks, block 10 left zero)
 template <typename TW>
 __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, int bias_dtype, int O, int C,
@@ -188,16 +188,18 @@ __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, i
     else tc_k_to_tap_channel(kb, kk, tap, c);
     float v = 0.0f;
     if (o < O && c >= 0 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + tap]);
+    if (variant == 6 && kb == 9 && (kk == 36 || kk == 37) && o < O && bias) {
+      // v6 adds the bias on the tensor core: A holds 1.0 at K elements 36 and 37 of the tail block, the weight image the
+      // bias split into two bf16 terms (hi + lo carries 16 significant bits)
+      const float bv = load_bias(bias, bias_dtype, o);
+      const float hi = __bfloat162float(__float2bfloat16_rn(bv));
+      v = kk == 36 ? hi : bv - hi;
+    }
     size_t off = (size_t)kb * TC_B_BYTES + (size_t)o * 128 + ((((kk >> 3) ^ (o & 7))) << 4) + (kk & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
   }
   if (bias_out && idx < TC_N) {
-    float bv = 0.0f;
-    if (bias && idx < O) {
-      if (bias_dtype == VFI_F32) bv = reinterpret_cast<const float*>(bias)[idx];
-      else if (bias_dtype == VFI_BF16) bv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(bias)[idx]);
-      else bv = __half2float(reinterpret_cast<const __half*>(bias)[idx]);
-    }
+    const float bv = (bias && idx < O) ? load_bias(bias, bias_dtype, idx) : 0.0f;
     bias_out[idx] = bv;
   }
 }

@@ -27,8 +27,9 @@
 constexpr int V6_BOX_H = 18, V6_BOX_W = 26, V6_BOX_PX = V6_BOX_H * V6_BOX_W;      // 468 pixels
 constexpr int V6_BOX_TOP = 5, V6_BOX_LEFT = 5;                                    // box origin = tile origin - (5, 5)
 constexpr int V6_PRODUCER_WARPS = 16;                                             // 4 groups x 4 TMEM sub-partitions
-constexpr int V6_W_MMA = 16, V6_W_BOX = 17, V6_W_EPI = 18, V6_W_BLOAD = 22;       // warps 18..21: geometry + epilogue
-constexpr int V6_THREADS = 23 * 32;                                               // 736
+constexpr int V6_W_MMA = 16, V6_W_BOX = 17, V6_W_BLOAD = 18, V6_W_BACK = 20;      // warp 19 idles; warps 20..27: back end
+constexpr int V6_BACK_WARPS = 8;                                                  // geometry + epilogue, two per TMEM quarter
+constexpr int V6_THREADS = 28 * 32;                                               // 896
 constexpr int V6_KBLOCKS = 10;                                                    // 9 main + 1 tail
 constexpr int V6_NA = 8, V6_NB = 3;                                               // TMEM A ring / smem B ring depth
 constexpr int V6_A_COL0 = 256;                                                    // TMEM columns [256, 512): A ring
@@ -50,7 +51,6 @@ struct __align__(1024) V6Smem {
   uint8_t box_tail[2][V6_BOX_PX * TC_CTAIL * 2];       // 2 x  7,488 B
   uint4 geo[2][9][TC_M];                               // x: box index + flags, y/z: 4 bf16 weights, w: global pixel (v4 pixf)
   uint8_t ostage[TC_M * 128];                          // epilogue staging tile (chunk j of row r at j ^ (r & 7))
-  float bias[TC_N];
   unsigned long long a_full[V6_NA], a_empty[V6_NA], b_full[V6_NB], b_empty[V6_NB];
   unsigned long long acc_full[2], acc_empty[2], geo_full[2], geo_empty[2], box_full[2], box_empty[2];
   uint32_t tmem_base;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 back-end warps
 
 // Sampling geometry of tap k at output pixel (y, x): Appendix B of SURVEY.md, corners clamped into the image (zero weight
 // where torchvision skips a corner), located inside the staged box when all four corners are there.
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
-      mbar_init(smem_u32(&s.acc_empty[i]), 4);                  // four epilogue warps
-      mbar_init(smem_u32(&s.geo_full[i]), 4);                   // four geometry (= epilogue) warps
+      mbar_init(smem_u32(&s.acc_empty[i]), V6_BACK_WARPS);      // the back-end warps (epilogue halves)
+      mbar_init(smem_u32(&s.geo_full[i]), V6_BACK_WARPS);       // the back-end warps (geometry halves)
       mbar_init(smem_u32(&s.geo_empty[i]), V6_PRODUCER_WARPS);
       mbar_init(smem_u32(&s.box_full[i]), 1);                   // the copy warp's expect_tx arrival (+ the bytes)
       mbar_init(smem_u32(&s.box_empty[i]), V6_PRODUCER_WARPS);
@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     fence_barrier_init();
   }
   if (warp == V6_W_MMA) tmem_alloc(smem_u32(&s.tmem_base), V6_TMEM_COLS);
-  if (tid < TC_N) s.bias[tid] = p.bias[tid];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -265,8 +264,9 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
             const uint2 v = v6_sample_tail(s.geo[gb][k][row], box_tail, p.x_tail, tail_row);
             r[2 * k] = v.x; r[2 * k + 1] = v.y;
           }
+          r[18] = 0x3f803f80u;                               // K elements 36, 37 = 1.0: the weight image holds bias hi / lo there
 #pragma unroll
-          for (int i = 18; i < 24; ++i) r[i] = 0u;
+          for (int i = 19; i < 24; ++i) r[i] = 0u;
           mbar_wait(empty_bar, empty_par);
           tc_fence_after();
           tmem_st_32x32b_x8(a_taddr, r);
@@ -350,15 +350,20 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       }
       __syncwarp();
     }
-  } else {
-    // =========================================================================== geometry + epilogue (4 warps)
+  } else if (warp >= V6_W_BACK) {
+    // =========================================================================== back end: geometry + epilogue (8 warps)
+    // Two warps per TMEM quarter; `half` splits both jobs so that the per-tile dependent chain of one warp is short
+    // enough to hide behind the producers: half 0 computes taps 0..4 and drains accumulator columns 0..31, half 1 taps
+    // 5..8 and columns 32..79.
     const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
+    const int half = (warp - V6_W_BACK) >> 2;
     const int row = quad * 32 + lane;                    // tile row = TMEM lane = geometry row of this thread
-    const int etid = (warp - V6_W_EPI) * 32 + lane;      // 0..127 for the cooperative store
+    const int etid = (warp - V6_W_BACK) * 32 + lane;     // 0..255 for the cooperative store
     uint32_t acc = 0, acc_phase[2] = {0, 0};
     const uint32_t ostage = smem_u32(&s.ostage[0]);
 
-    auto make_geometry = [&](int it) {
+    auto make_geometry = [&](int it, auto half_tag) {
+      constexpr int K0 = decltype(half_tag)::value ? 5 : 0, NK = decltype(half_tag)::value ? 4 : 5;
       const int gb = it & 1;
       mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old contents
       int b, ty0, tx0;
@@ -366,45 +371,50 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
       const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
       if (y < p.H && x < p.W) {
-        // all 27 offset / mask values of this pixel are requested before the first one is used (one DRAM round trip)
+        // all offset / mask values of this thread are requested before the first one is used (one DRAM round trip)
         const int f_sc = (int)p.f_sc, m_sc = (int)p.m_sc;
         const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
         const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
         const int base = b * p.H * p.W;
-        TO rdy[9], rdx[9], rmk[9];
+        TO rdy[NK], rdx[NK], rmk[NK];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const int j0 = 2 * k, j1 = 2 * k + 1;
+        for (int i = 0; i < NK; ++i) {
+          const int k = K0 + i, j0 = 2 * k, j1 = 2 * k + 1;
           if (p.fused27) {
             // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets (tap k uses channels 2k and
             // 2k+1 of their concatenation), the middle third is the pre-sigmoid mask
-            rdy[k] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
-            rdx[k] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
-            rmk[k] = __ldg(msk + (9 + k) * m_sc);
+            rdy[i] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
+            rdx[i] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
+            rmk[i] = __ldg(msk + (9 + k) * m_sc);
           } else {
-            rdy[k] = __ldg(off + j0 * f_sc);
-            rdx[k] = __ldg(off + j1 * f_sc);
-            rmk[k] = __ldg(msk + k * m_sc);
+            rdy[i] = __ldg(off + j0 * f_sc);
+            rdx[i] = __ldg(off + j1 * f_sc);
+            rmk[i] = __ldg(msk + k * m_sc);
           }
         }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float mk = to_f32<TO>(rmk[k]);
+        for (int i = 0; i < NK; ++i) {
+          float mk = to_f32<TO>(rmk[i]);
           // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
           if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
-          s.geo[gb][k][row] = v6_geo_entry(p.H, p.W, base, by0, bx0, y, x, k, to_f32<TO>(rdy[k]), to_f32<TO>(rdx[k]), mk);
+          s.geo[gb][K0 + i][row] =
+              v6_geo_entry(p.H, p.W, base, by0, bx0, y, x, K0 + i, to_f32<TO>(rdy[i]), to_f32<TO>(rdx[i]), mk);
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s.geo[gb][k][row] = make_uint4(V6_INSIDE | V6_SAFE, 0u, 0u, 0u);
+        for (int i = 0; i < NK; ++i) s.geo[gb][K0 + i][row] = make_uint4(V6_INSIDE | V6_SAFE, 0u, 0u, 0u);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
     };
+    auto geometry = [&](int it) {
+      if (half) make_geometry(it, std::integral_constant<int, 1>{});
+      else make_geometry(it, std::integral_constant<int, 0>{});
+    };
 
-    if (my_tiles > 0) make_geometry(0);
+    if (my_tiles > 0) geometry(0);
     for (int it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles) make_geometry(it + 1);      // overlaps the producers' work on tile `it`
+      if (it + 1 < my_tiles) geometry(it + 1);           // overlaps the producers' work on tile `it`
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
@@ -415,16 +425,17 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const size_t pixel = (size_t)(b * p.H + y) * p.W + x;
       __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(p.out_tail) + pixel * TC_CTAIL;
       TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
-#pragma unroll
-      for (int c16 = 0; c16 < TC_N / 16; ++c16) {
+      const int c16_lo = half ? 2 : 0, c16_hi = half ? TC_N / 16 : 2;
+      for (int c16 = c16_lo; c16 < c16_hi; ++c16) {
         uint32_t d[16];
         tmem_ld16(taddr + c16 * 16, d);
         tmem_ld_wait();
-        if (c16 == TC_N / 16 - 1) {                      // last TMEM read of this accumulator: hand it back early
+        if (c16 == c16_hi - 1) {                         // last TMEM read of this accumulator by this warp: hand it back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
         }
+        // the bias is already in the accumulator (K elements 36/37 of the tail block)
         if (p.out_tail) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -434,8 +445,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
             uint32_t* w = reinterpret_cast<uint32_t*>(&w4);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c0 + 2 * i],
-                                                        __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c0 + 2 * i + 1]);
+              __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]), __uint_as_float(d[h * 8 + 2 * i + 1]));
               w[i] = *reinterpret_cast<uint32_t*>(&hv);
             }
             if (c0 < TC_CMAIN) sts16(ostage + (uint32_t)row * 128 + ((uint32_t)((c0 >> 3) ^ (row & 7)) << 4), w4);
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = c16 * 16 + i;
-            if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]) + s.bias[c]);
+            if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]));
           }
         }
       }
@@ -454,8 +464,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         epi_bar_sync();
         uint8_t* om = reinterpret_cast<uint8_t*>(p.out);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = i * 128 + etid, r = idx >> 3, c = idx & 7;
+        for (int i = 0; i < 4; ++i) {
+          const int idx = i * 256 + etid, r = idx >> 3, c = idx & 7;
           const int yy = ty0 + r / TC_TW, xx = tx0 + r % TC_TW;
           const uint4 v = lds16(ostage + (uint32_t)r * 128 + ((uint32_t)(c ^ (r & 7)) << 4));
           if (yy < p.H && xx < p.W)
