@@ -2,7 +2,6 @@
 import os, sys
 os.environ["VFI_DCN_DEBUG"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ['VFI_DCN_KERNEL'] = 'v5'
 import numpy as np, torch, ctypes
 import vfi_b200
 from vfi_b200 import ops, _lib
@@ -23,11 +22,11 @@ def show(name, warps, labels):
     x = d[:, warps, :]
     tot = x[..., 0].mean()
     print(f"{name:10s} total {tot/1e3:8.1f} kcyc  " + "  ".join(f"{l} {x[..., i+1].mean()/tot*100:5.1f}%" for i, l in enumerate(labels)))
-show("producers", list(range(24)), ["geo_full", "src_full", "stage_empty"])
-show("mma", [24], ["acc_empty", "stage_full", "mma_issue", "commit"])
-show("epilogue", [25, 26, 27, 28], ["geo_empty", "acc_full"])
-show("copy", [29], ["src_empty"])
+show("producers", list(range(16)), ["geo_full", "box_full", "a_empty"])
+show("mma", [16], ["acc_empty", "b_full", "a_full", "issue"])
+print("   mma commit %5.1f%%" % (d[:, 16, 6].mean() / d[:, 16, 0].mean() * 100))
+show("box", [17], ["box_empty"])
+show("bload", [18], ["b_empty"])
+show("epilogue", list(range(20, 24)), ["-", "acc_full", "-", "epilogue"])
+show("geometry", list(range(24, 28)), ["geo_empty", "-", "geometry"])
 print("tiles per CTA", d[:, 0, 5].mean(), " cycles per tile", d[:, 0, 0].mean() / d[:, 0, 5].mean())
-for g in range(3):
-    x = d[:, 8*g:8*g+8, :]; tot = x[..., 0].mean()
-    print(f" group {g}: geo_full {x[...,1].mean()/tot*100:5.1f}%  src_full {x[...,2].mean()/tot*100:5.1f}%  stage_empty {x[...,3].mean()/tot*100:5.1f}%")

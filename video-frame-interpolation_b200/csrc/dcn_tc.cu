@@ -94,17 +94,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uin
                : "memory");
   return done != 0;
 }
+// Slow path of a wait.  try_wait returns whenever ANY mbarrier of the CTA sees an arrival (measured: a waiting warp came
+// back every ~170 cycles regardless of the hint), so a bare retry loop burns the issue slots the producers need; the
+// explicit sleep bounds that cost.  NS trades issue slots against wake-up latency per wait site.  A protocol bug traps
+// (launch failure) after a few seconds instead of hanging the GPU.
+template <int NS>
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-  // try_wait itself suspends the thread in hardware (~100 cycles per attempt), so this loop is three instructions per
-  // attempt; a protocol bug traps (launch failure) after ~2^26 attempts instead of hanging the GPU.
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity, 100000u))
+  do {
+    __nanosleep(NS);
     if (++spins > (1u << 26)) __trap();
+  } while (!mbar_try_wait(bar, parity, 100000u));
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+template <int NS>
+__device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity, 2000u)) return;
-  mbar_wait_slow(bar, parity);
+  mbar_wait_slow<NS>(bar, parity);
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_ns<64>(bar, parity); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -244,6 +251,7 @@ struct TcParams {
   long long o_sn, o_sc, o_sh, o_sw;                // generic strided output otherwise
   int B, H, W, O;
   int tiles_x, tiles_y, num_tiles;
+  int experiment;                                  // VFI_DCN_EXPERIMENT (diagnostics only, results are wrong when non-zero)
   unsigned long long* debug;                       // optional [grid][32 warps][8] cycle counters (VFI_DCN_DEBUG), else null
 };
 
@@ -809,7 +817,12 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   // the packed-bf16 blend and at most four tail channels (C <= 68).  v4 (VFI_DCN_KERNEL=v4, the HQ blend, C > 68): gathers
   // through L1 into a shared-memory A ring.
   static const bool force_v4 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '4'; }();
-  const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4;
+  // v6 brings the offsets / masks in with 16-byte bulk copies: 16-bit dtype, unit pixel stride, 16-byte aligned rows
+  auto bulk_ok = [](const vfi_tensor* t) {
+    return (t->dtype == VFI_BF16 || t->dtype == VFI_F16) && t->sw == 1 && t->w % 8 == 0 && t->sh % 8 == 0 && t->sc % 8 == 0 &&
+           t->sn % 8 == 0 && aligned(t->data, 16) && t->sh >= 0 && t->sc >= 0 && t->sn >= 0;
+  };
+  const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4 && bulk_ok(offset) && bulk_ok(mask);
   int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, use_v6 ? 6 : 4);
   if (rc) return rc;
   if (x_tail) {
@@ -830,6 +843,7 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y;
   p.debug = dcn_tc_debug_buffer();
+  p.experiment = 0;
   int dev = 0, sms = 148;
   VFI_CUDA(cudaGetDevice(&dev));
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -837,13 +851,36 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
   if (use_v6) {
     const size_t smem6 = sizeof(V6Smem) + 1024;
-    VFI_DISPATCH(offset->dtype, TO, {
+    const bool dbg = p.debug != nullptr;
+#define VFI_V6_LAUNCH(FUSED, PLANES, DBG)                                                                      \
+  do {                                                                                                         \
+    auto kern = dcn_tc6_fwd_kernel<TO, TOUT, FUSED, PLANES, DBG>;                                              \
+    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));             \
+    kern<<<grid, V6_THREADS, smem6, st>>>(p);                                                                  \
+  } while (0)
+    if (out_tail) {
+      // planes out (always bf16): the hot-path form; the only one with a debug-counter instantiation
+      using TOUT = __nv_bfloat16;
+      if (offset->dtype == VFI_BF16) {
+        using TO = __nv_bfloat16;
+        if (p.fused27) { if (dbg) VFI_V6_LAUNCH(true, true, true); else VFI_V6_LAUNCH(true, true, false); }
+        else VFI_V6_LAUNCH(false, true, false);
+      } else {
+        using TO = __half;
+        if (p.fused27) VFI_V6_LAUNCH(true, true, false); else VFI_V6_LAUNCH(false, true, false);
+      }
+    } else {
       VFI_DISPATCH(out_dtype, TOUT, {
-        auto kern = dcn_tc6_fwd_kernel<TO, TOUT>;
-        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-        kern<<<grid, V6_THREADS, smem6, st>>>(p);
+        if (offset->dtype == VFI_BF16) {
+          using TO = __nv_bfloat16;
+          if (p.fused27) VFI_V6_LAUNCH(true, false, false); else VFI_V6_LAUNCH(false, false, false);
+        } else {
+          using TO = __half;
+          if (p.fused27) VFI_V6_LAUNCH(true, false, false); else VFI_V6_LAUNCH(false, false, false);
+        }
       });
-    });
+    }
+#undef VFI_V6_LAUNCH
     VFI_LAUNCH_CHECK("dcn_tc6_fwd_kernel");
     return VFI_OK;
   }

@@ -10,7 +10,8 @@
 //     into an 8-stage ring of 32-column K blocks, and the MMA is issued in the A-from-TMEM form
 //     (tcgen05.mma [d], [a_tmem], b_desc): no A stores to shared memory, no A reads from it;
 //   * the activation box of a tile (tile + 3x3 reach + 4 px halo = 18 x 26 pixels, 66 KB) is staged in shared memory
-//     by bulk copies one tile ahead (double buffered), so every corner is an LDS.128 with no L1 tag / miss traffic;
+//     by bulk copies one tile ahead (double buffered), ZERO PADDED outside the image, so every corner is an LDS.128 at a
+//     compile-time offset from the sample's first corner (no clamping, no per-corner validity, no L1 tag / miss traffic);
 //     samples that leave the box (|offset| > 4 px at the tile edge) read global memory lane by lane;
 //   * the epilogue transposes through a swizzled staging tile so that global stores are full 128 B lines.
 //
@@ -26,18 +27,22 @@
 
 constexpr int V6_BOX_H = 18, V6_BOX_W = 26, V6_BOX_PX = V6_BOX_H * V6_BOX_W;      // 468 pixels
 constexpr int V6_BOX_TOP = 5, V6_BOX_LEFT = 5;                                    // box origin = tile origin - (5, 5)
-constexpr int V6_PRODUCER_WARPS = 16;                                             // 4 groups x 4 TMEM sub-partitions
-constexpr int V6_W_MMA = 16, V6_W_BOX = 17, V6_W_BLOAD = 18, V6_W_BACK = 20;      // warp 19 idles; warps 20..27: back end
-constexpr int V6_BACK_WARPS = 8;                                                  // geometry + epilogue, two per TMEM quarter
+constexpr int V6_MAIN_PX = TC_CMAIN * 2, V6_TAIL_PX = TC_CTAIL * 2;               // bytes per pixel: 128 / 16
+constexpr int V6_MAIN_ROW = V6_BOX_W * V6_MAIN_PX, V6_TAIL_ROW = V6_BOX_W * V6_TAIL_PX;   // bytes per box row: 3328 / 416
+constexpr int V6_GROUPS = 4;                                                      // producer groups
+constexpr int V6_PRODUCER_WARPS = 4 * V6_GROUPS;                                  // x 4 TMEM sub-partitions
+constexpr int V6_W_MMA = 16, V6_W_BOX = 17, V6_W_BLOAD = 18;                      // warp 19 idles
+constexpr int V6_W_EPI = 20, V6_EPI_WARPS = 4;                                    // warps 20..23: epilogue (one per TMEM quarter)
+constexpr int V6_W_GEO = 24, V6_GEO_WARPS = 4;                                    // warps 24..27: tap geometry
 constexpr int V6_THREADS = 28 * 32;                                               // 896
 constexpr int V6_KBLOCKS = 10;                                                    // 9 main + 1 tail
 constexpr int V6_NA = 8, V6_NB = 3;                                               // TMEM A ring / smem B ring depth
 constexpr int V6_A_COL0 = 256;                                                    // TMEM columns [256, 512): A ring
 constexpr int V6_TMEM_COLS = 512;
-constexpr uint32_t V6_INSIDE = 0x80000000u;
-// Box index of the tile's own first pixel: always inside the image and always copied.  Zero-weight entries (dead samples,
-// rows of a partial tile) point here so that they never multiply 0 by uninitialised shared memory.
-constexpr uint32_t V6_SAFE = V6_BOX_TOP * V6_BOX_W + V6_BOX_LEFT;
+constexpr uint32_t V6_SLOW = 0x80000000u;                                         // entry.x: sample not served by the box
+// Box offset of the tile's own first pixel: always inside the image and always copied.  Zero-weight entries (dead samples,
+// rows of a partial tile) point here.
+constexpr uint32_t V6_SAFE = (V6_BOX_TOP * V6_BOX_W + V6_BOX_LEFT) * V6_MAIN_PX;
 
 __host__ __device__ inline void v6_k_to_tap_channel(int kb, int kk, int& tap, int& c) {
   if (kb < 9) { tap = kb; c = ((kk >> 5) << 5) + 8 * ((kk >> 2) & 3) + 4 * ((kk >> 4) & 1) + (kk & 3); }
@@ -47,11 +52,12 @@ __host__ __device__ inline void v6_k_to_tap_channel(int kb, int kk, int& tap, in
 
 struct __align__(1024) V6Smem {
   uint8_t b[V6_NB][TC_B_BYTES];                        // weight K blocks (bulk copies, SWIZZLE_128B image)
-  uint8_t box_main[2][V6_BOX_PX * TC_CMAIN * 2];       // 2 x 59,904 B
-  uint8_t box_tail[2][V6_BOX_PX * TC_CTAIL * 2];       // 2 x  7,488 B
-  uint4 geo[2][9][TC_M];                               // x: box index + flags, y/z: 4 bf16 weights, w: global pixel (v4 pixf)
+  uint8_t box_main[2][V6_BOX_PX * V6_MAIN_PX];         // 2 x 59,904 B
+  uint8_t box_tail[2][V6_BOX_PX * V6_TAIL_PX];         // 2 x  7,488 B
+  uint4 geo[2][9][TC_M];                               // x: box byte offset | V6_SLOW, y/z: 4 bf16 weights, w: global pixel (slow)
   uint8_t ostage[TC_M * 128];                          // epilogue staging tile (chunk j of row r at j ^ (r & 7))
-  unsigned long long a_full[V6_NA], a_empty[V6_NA], b_full[V6_NB], b_empty[V6_NB];
+  uint16_t raw[27][TC_M];                              // offset / mask values of the next tile (cp.async), [channel][tile row]
+  unsigned long long full[V6_NA], done[V6_NA];         // per K block n (slot n % 8): operands ready / MMAs complete
   unsigned long long acc_full[2], acc_empty[2], geo_full[2], geo_empty[2], box_full[2], box_empty[2];
   uint32_t tmem_base;
 };
@@ -70,10 +76,18 @@ __device__ __forceinline__ void sts16(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // A-from-TMEM form of the MMA: A = 128 lanes x 8 columns (16 bf16 of K per lane) at a_tmem, B from shared memory.
+// Called by the whole converged warp (operands warp-uniform); one elected lane issues.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "{\n\t.reg .pred p, pe;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
 // 16 TMEM lanes x 32 columns: thread (g, u) supplies columns 8i + 2u, 8i + 2u + 1 of lane g (r[4i], r[4i+1]) and of
@@ -103,16 +117,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 back-end warps
+// a tensor element as raw bits in a 32-bit register (no conversion instruction at load time), and back
+template <typename T> __device__ __forceinline__ uint32_t ldg_bits(const T* p);
+template <> __device__ __forceinline__ uint32_t ldg_bits<float>(const float* p) { return __float_as_uint(__ldg(p)); }
+template <> __device__ __forceinline__ uint32_t ldg_bits<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const unsigned short*>(p));
+}
+template <> __device__ __forceinline__ uint32_t ldg_bits<__half>(const __half* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+template <typename T> __device__ __forceinline__ float bits_to_f32(uint32_t v);
+template <> __device__ __forceinline__ float bits_to_f32<float>(uint32_t v) { return __uint_as_float(v); }
+template <> __device__ __forceinline__ float bits_to_f32<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v << 16); }
+template <> __device__ __forceinline__ float bits_to_f32<__half>(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)v)); }
 
-// Sampling geometry of tap k at output pixel (y, x): Appendix B of SURVEY.md, corners clamped into the image (zero weight
-// where torchvision skips a corner), located inside the staged box when all four corners are there.
-__device__ __forceinline__ uint4 v6_geo_entry(int H, int W, int base, int by0, int bx0, int y, int x, int k, float dy, float dx,
-                                              float mk) {
+template <int OFF> __device__ __forceinline__ uint4 lds16o(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr), "n"(OFF));
+  return r;
+}
+template <int OFF> __device__ __forceinline__ uint2 lds8o(uint32_t saddr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(r.x), "=r"(r.y) : "r"(saddr), "n"(OFF));
+  return r;
+}
+__device__ __forceinline__ void geo_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }   // the 4 geometry warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
+// mbar_wait that adds the cycles spent waiting to `acc` when the debug buffer is enabled (VFI_DCN_DEBUG=1)
+template <int NS, bool DBG>
+__device__ __forceinline__ void mbar_wait_d(uint32_t bar, uint32_t parity, long long& acc) {
+  if (!DBG) { mbar_wait_ns<NS>(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait_ns<NS>(bar, parity);
+  acc += clock64() - t0;
+}
+
+// Rare path of the geometry: the sample is not served by the staged box.  Appendix B of SURVEY.md with corners clamped
+// into the image and zero weight where torchvision skips a corner; the producers read these from global memory.
+__device__ __noinline__ uint4 v6_geo_entry_slow(int H, int W, int base, int y, int x, int k, float dy, float dx, float mk) {
   float py = (float)(y - 1 + k / 3) + dy;
   float px = (float)(x - 1 + k % 3) + dx;
   const bool live = (py > -1.0f) && (py < (float)H) && (px > -1.0f) && (px < (float)W);
-  if (!live) { py = -2.0f; px = -2.0f; mk = 0.0f; }
+  if (!live) return make_uint4(V6_SAFE, 0u, 0u, 0u);
   const float fy = floorf(py), fx = floorf(px);
   const int y0 = (int)fy, x0 = (int)fx;
   const float lh = py - fy, lw = px - fx, hh = 1.0f - lh, hw = 1.0f - lw;
@@ -120,36 +165,42 @@ __device__ __forceinline__ uint4 v6_geo_entry(int H, int W, int base, int by0, i
   const bool c0 = (unsigned)x0 < (unsigned)W, c1 = (unsigned)(x0 + 1) < (unsigned)W;
   const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
   const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
-  const int sx = cx1 - cx0, sy = cy1 - cy0;
   uint2 wq;
   store_geo_w(wq, (r0 && c0) ? hh * hw * mk : 0.0f, (r0 && c1) ? hh * lw * mk : 0.0f, (r1 && c0) ? lh * hw * mk : 0.0f,
               (r1 && c1) ? lh * lw * mk : 0.0f);
-  const bool dead = ((wq.x | wq.y) & 0x7fff7fffu) == 0u;           // all four weights are +-0: the value is irrelevant
-  const int ry = cy0 - by0, rx = cx0 - bx0;
-  const bool in = ry >= 0 && ry + sy < V6_BOX_H && rx >= 0 && rx + sx < V6_BOX_W;
-  uint4 e;
-  e.x = dead ? (V6_INSIDE | V6_SAFE)
-             : in ? (V6_INSIDE | (uint32_t)(ry * V6_BOX_W + rx) | ((uint32_t)sx << 16) | ((uint32_t)sy << 17)) : 0u;
-  e.y = dead ? 0u : wq.x;
-  e.z = dead ? 0u : wq.y;
-  e.w = (uint32_t)(base + cy0 * W + cx0) | ((uint32_t)sx << 30) | ((uint32_t)sy << 31);
-  return e;
+  return make_uint4(V6_SLOW, wq.x, wq.y,
+                    (uint32_t)(base + cy0 * W + cx0) | ((uint32_t)(cx1 - cx0) << 30) | ((uint32_t)(cy1 - cy0) << 31));
 }
 
-// Two 16-byte chunks (c_first, c_second: byte offsets inside the 128-byte pixel) of the modulated bilinear sample `e`.
-__device__ __forceinline__ void v6_sample_main(const uint4& e, uint32_t box_main, const uint8_t* x_main, uint32_t main_row,
+// Sampling geometry of one tap: fy0 / fx0 = (float)(y - 1 + i) / (float)(x - 1 + j).  Fast path: no clamping and no corner
+// validity -- the box is zero padded outside the image, so an out-of-image corner contributes w * 0 exactly as torchvision's
+// skipped corner does, and its "dead sample" rule (py <= -1, py >= H, ...) falls out of the same zeros.
+// Returns false (entry invalid) when the box does not serve the sample; the caller then uses v6_geo_entry_slow.
+__device__ __forceinline__ bool v6_geo_entry(int by0, int bx0, float fy0, float fx0, float dy, float dx, float mk, uint4& e) {
+  const float py = fy0 + dy, px = fx0 + dx;
+  const float fy = floorf(py), fx = floorf(px);
+  const float lh = py - fy, lw = px - fx, hh = 1.0f - lh, hw = 1.0f - lw;
+  const int ry = (int)fy - by0, rx = (int)fx - bx0;
+  uint2 wq;
+  store_geo_w(wq, hh * hw * mk, hh * lw * mk, lh * hw * mk, lh * lw * mk);
+  e = make_uint4((uint32_t)(ry * V6_BOX_W + rx) * V6_MAIN_PX, wq.x, wq.y, 0u);
+  return (unsigned)ry <= (unsigned)(V6_BOX_H - 2) && (unsigned)rx <= (unsigned)(V6_BOX_W - 2);
+}
+
+// Two 16-byte chunks of the modulated bilinear sample `e`; bF / bS = box base + the lane's first / second chunk offset.
+// FAST: the caller has checked that the sample is served by the box (straight-line code, all eight loads in flight).
+template <bool FAST>
+__device__ __forceinline__ void v6_sample_main(const uint4& e, uint32_t bF, uint32_t bS, const uint8_t* x_main, uint32_t main_row,
                                                uint32_t c_first, uint32_t c_second, uint4& F, uint4& S) {
   uint4 f[4], g[4];
-  if (e.x & V6_INSIDE) {
-    const uint32_t a00 = box_main + (e.x & 0xffffu) * (TC_CMAIN * 2);
-    const uint32_t a01 = a00 + ((e.x & 0x10000u) ? TC_CMAIN * 2 : 0u);
-    const uint32_t dy = (e.x & 0x20000u) ? V6_BOX_W * TC_CMAIN * 2 : 0u;
-    f[0] = lds16(a00 + c_first); f[1] = lds16(a01 + c_first); f[2] = lds16(a00 + dy + c_first); f[3] = lds16(a01 + dy + c_first);
-    g[0] = lds16(a00 + c_second); g[1] = lds16(a01 + c_second); g[2] = lds16(a00 + dy + c_second); g[3] = lds16(a01 + dy + c_second);
+  if (FAST || (int)e.x >= 0) {
+    const uint32_t aF = bF + e.x, aS = bS + e.x;
+    f[0] = lds16o<0>(aF); f[1] = lds16o<V6_MAIN_PX>(aF); f[2] = lds16o<V6_MAIN_ROW>(aF); f[3] = lds16o<V6_MAIN_ROW + V6_MAIN_PX>(aF);
+    g[0] = lds16o<0>(aS); g[1] = lds16o<V6_MAIN_PX>(aS); g[2] = lds16o<V6_MAIN_ROW>(aS); g[3] = lds16o<V6_MAIN_ROW + V6_MAIN_PX>(aS);
   } else {
-    // rare: a corner of this sample lies outside the staged box -> global memory
-    const uint8_t* a00 = x_main + (unsigned long long)(e.w & 0x3fffffffu) * (TC_CMAIN * 2);
-    const uint8_t* a01 = a00 + ((e.w & 0x40000000u) ? TC_CMAIN * 2 : 0);
+    // rare: the sample is not served by the staged box -> global memory (clamped corners, validity in the weights)
+    const uint8_t* a00 = x_main + (unsigned long long)(e.w & 0x3fffffffu) * V6_MAIN_PX;
+    const uint8_t* a01 = a00 + ((e.w & 0x40000000u) ? V6_MAIN_PX : 0);
     const uint32_t dy = (e.w & 0x80000000u) ? main_row : 0u;
     f[0] = __ldg(reinterpret_cast<const uint4*>(a00 + c_first)); f[1] = __ldg(reinterpret_cast<const uint4*>(a01 + c_first));
     f[2] = __ldg(reinterpret_cast<const uint4*>(a00 + dy + c_first)); f[3] = __ldg(reinterpret_cast<const uint4*>(a01 + dy + c_first));
@@ -164,14 +215,12 @@ __device__ __forceinline__ void v6_sample_main(const uint4& e, uint32_t box_main
 // The first four tail channels (8 bytes) of the modulated bilinear sample `e`.
 __device__ __forceinline__ uint2 v6_sample_tail(const uint4& e, uint32_t box_tail, const uint8_t* x_tail, uint32_t tail_row) {
   uint2 v[4];
-  if (e.x & V6_INSIDE) {
-    const uint32_t a00 = box_tail + (e.x & 0xffffu) * (TC_CTAIL * 2);
-    const uint32_t a01 = a00 + ((e.x & 0x10000u) ? TC_CTAIL * 2 : 0u);
-    const uint32_t dy = (e.x & 0x20000u) ? V6_BOX_W * TC_CTAIL * 2 : 0u;
-    v[0] = lds8(a00); v[1] = lds8(a01); v[2] = lds8(a00 + dy); v[3] = lds8(a01 + dy);
+  if ((int)e.x >= 0) {
+    const uint32_t a = box_tail + (e.x >> 3);                      // 16 B per pixel instead of 128
+    v[0] = lds8o<0>(a); v[1] = lds8o<V6_TAIL_PX>(a); v[2] = lds8o<V6_TAIL_ROW>(a); v[3] = lds8o<V6_TAIL_ROW + V6_TAIL_PX>(a);
   } else {
-    const uint8_t* a00 = x_tail + (unsigned long long)(e.w & 0x3fffffffu) * (TC_CTAIL * 2);
-    const uint8_t* a01 = a00 + ((e.w & 0x40000000u) ? TC_CTAIL * 2 : 0);
+    const uint8_t* a00 = x_tail + (unsigned long long)(e.w & 0x3fffffffu) * V6_TAIL_PX;
+    const uint8_t* a01 = a00 + ((e.w & 0x40000000u) ? V6_TAIL_PX : 0);
     const uint32_t dy = (e.w & 0x80000000u) ? tail_row : 0u;
     v[0] = __ldg(reinterpret_cast<const uint2*>(a00)); v[1] = __ldg(reinterpret_cast<const uint2*>(a01));
     v[2] = __ldg(reinterpret_cast<const uint2*>(a00 + dy)); v[3] = __ldg(reinterpret_cast<const uint2*>(a01 + dy));
@@ -181,29 +230,34 @@ __device__ __forceinline__ uint2 v6_sample_tail(const uint4& e, uint32_t box_tai
   return make_uint2(r.x, r.y);
 }
 
-template <typename TO, typename TOUT>
+// TO: 16-bit dtype of the offset / mask tensors; TOUT: output dtype; FUSED27: offsets and mask come from the 27-channel
+// offset_conv output; PLANES: output as bf16 planes (else any strided tensor); DBG: per-role cycle counters.
+template <typename TO, typename TOUT, bool FUSED27, bool PLANES, bool DBG>
 __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   V6Smem& s = *reinterpret_cast<V6Smem*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    // One pair of barriers per K block n (slot n % 8), so that the MMA warp does ONE wait and ONE commit per block (every
+    // tcgen05 / mbarrier instruction on that warp costs ~100 cycles of issue latency, and its blocks are only 160 tensor
+    // cycles long): full = the A stage (4 producer warps) and the weight block (loader's expect_tx + bytes) are ready;
+    // done = the block's MMAs have completed -> A stage n % 8 and B stage n % 3 are free.  The loader reads done[n - 3]
+    // before block n - 3 + 8 can complete (that block needs a weight block the loader has not issued yet), so the
+    // two consumers of `done` never see the barrier two phases ahead.
     for (int i = 0; i < V6_NA; ++i) {
-      mbar_init(smem_u32(&s.a_full[i]), 4);                     // the four sub-partition warps of the producing group
-      mbar_init(smem_u32(&s.a_empty[i]), 1);                    // one tcgen05.commit
-    }
-    for (int i = 0; i < V6_NB; ++i) {
-      mbar_init(smem_u32(&s.b_full[i]), 1);                     // the loader's expect_tx arrival (+ the bytes)
-      mbar_init(smem_u32(&s.b_empty[i]), 1);                    // one tcgen05.commit
+      mbar_init(smem_u32(&s.full[i]), 5);
+      mbar_init(smem_u32(&s.done[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
-      mbar_init(smem_u32(&s.acc_empty[i]), V6_BACK_WARPS);      // the back-end warps (epilogue halves)
-      mbar_init(smem_u32(&s.geo_full[i]), V6_BACK_WARPS);       // the back-end warps (geometry halves)
+      mbar_init(smem_u32(&s.acc_empty[i]), V6_EPI_WARPS);
+      mbar_init(smem_u32(&s.geo_full[i]), V6_GEO_WARPS);
       mbar_init(smem_u32(&s.geo_empty[i]), V6_PRODUCER_WARPS);
       mbar_init(smem_u32(&s.box_full[i]), 1);                   // the copy warp's expect_tx arrival (+ the bytes)
       mbar_init(smem_u32(&s.box_empty[i]), V6_PRODUCER_WARPS);
     }
+
     fence_barrier_init();
   }
   if (warp == V6_W_MMA) tmem_alloc(smem_u32(&s.tmem_base), V6_TMEM_COLS);
@@ -215,6 +269,9 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
   // fetched from DRAM once and found in L2 by the neighbour).
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
+  constexpr bool dbg = DBG;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;      // cycles spent in this role's waits (debug only)
+  const long long t_begin = clock64();
 
   if (warp < V6_PRODUCER_WARPS) {
     // =========================================================================== A-operand producers
@@ -224,39 +281,45 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     const int g = lane >> 2, u = lane & 3;
     const bool par = (g & 1) != 0;
     const uint32_t c_first = (uint32_t)(u + (par ? 4 : 0)) * 16, c_second = (uint32_t)(u + (par ? 0 : 4)) * 16;
-    const uint32_t main_row = TC_CMAIN * 2 * (uint32_t)p.W, tail_row = TC_CTAIL * 2 * (uint32_t)p.W;
+    const uint32_t main_row = V6_MAIN_PX * (uint32_t)p.W, tail_row = V6_TAIL_PX * (uint32_t)p.W;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(smem_u32(&s.geo_full[gb]), tphase);             // this tile's geometry has been written
-      mbar_wait(smem_u32(&s.box_full[gb]), tphase);             // this tile's source box has landed in shared memory
+      mbar_wait_d<64, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);  // this tile's geometry has been written
+      mbar_wait_d<64, DBG>(smem_u32(&s.box_full[gb]), tphase, w1);  // this tile's source box has landed in shared memory
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]), box_tail = smem_u32(&s.box_tail[gb][0]);
+      const uint32_t bF = box_main + c_first, bS = box_main + c_second;
       const int n0 = it * V6_KBLOCKS;
-      int kb = (group - n0) & 3;
-      for (; kb < V6_KBLOCKS; kb += 4) {
+      int kb = (group - n0) & (V6_GROUPS - 1);
+      for (; kb < V6_KBLOCKS; kb += V6_GROUPS) {
         const int n = n0 + kb, sa = n % V6_NA;
-        const uint32_t empty_bar = smem_u32(&s.a_empty[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
+        const uint32_t empty_bar = smem_u32(&s.done[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
         if (kb < 9) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint4 e0 = s.geo[gb][kb][q * 32 + h * 16 + g], e1 = s.geo[gb][kb][q * 32 + h * 16 + g + 8];
             uint4 F0, S0, F1, S1;
-            v6_sample_main(e0, box_main, p.x_main, main_row, c_first, c_second, F0, S0);
-            v6_sample_main(e1, box_main, p.x_main, main_row, c_first, c_second, F1, S1);
+            if ((int)(e0.x | e1.x) >= 0) {                  // both samples served by the box: one basic block
+              v6_sample_main<true>(e0, bF, bS, p.x_main, main_row, c_first, c_second, F0, S0);
+              v6_sample_main<true>(e1, bF, bS, p.x_main, main_row, c_first, c_second, F1, S1);
+            } else {
+              v6_sample_main<false>(e0, bF, bS, p.x_main, main_row, c_first, c_second, F0, S0);
+              v6_sample_main<false>(e1, bF, bS, p.x_main, main_row, c_first, c_second, F1, S1);
+            }
             // chunk u (X) and chunk u + 4 (Y) of both pixels: odd g loaded them in the opposite order
             const uint4 X0 = par ? S0 : F0, Y0 = par ? F0 : S0, X1 = par ? S1 : F1, Y1 = par ? F1 : S1;
             const uint32_t r[16] = {X0.x, X0.y, X1.x, X1.y, X0.z, X0.w, X1.z, X1.w,
                                     Y0.x, Y0.y, Y1.x, Y1.y, Y0.z, Y0.w, Y1.z, Y1.w};
             if (h == 0) {                                        // the ring stage is needed only now, after the gathers
-              mbar_wait(empty_bar, empty_par);
+              mbar_wait_d<32, DBG>(empty_bar, empty_par, w2);
               tc_fence_after();
             }
             tmem_st_16x256b_x4(a_taddr + ((uint32_t)(h * 16) << 16), r);
           }
         } else {
-          // ---- tail block: lane = tile row, four channels of each of the nine taps (K = 36 of 48, rest zero)
+          // ---- tail block: lane = tile row, four channels of each of the nine taps (K = 36 of 48, then the bias slots)
           const int row = q * 32 + lane;
           uint32_t r[24];
 #pragma unroll
@@ -267,7 +330,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
           r[18] = 0x3f803f80u;                               // K elements 36, 37 = 1.0: the weight image holds bias hi / lo there
 #pragma unroll
           for (int i = 19; i < 24; ++i) r[i] = 0u;
-          mbar_wait(empty_bar, empty_par);
+          mbar_wait_d<32, DBG>(empty_bar, empty_par, w2);
           tc_fence_after();
           tmem_st_32x32b_x8(a_taddr, r);
           tmem_st_32x32b_x8(a_taddr + 8, r + 8);
@@ -276,7 +339,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         tmem_st_wait();                                          // TMEM writes complete ...
         tc_fence_before();                                       // ... and ordered before the arrive the MMA lane waits on
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.a_full[sa]));
+        if (lane == 0) mbar_arrive(smem_u32(&s.full[sa]));
       }
       __syncwarp();
       if (lane == 0) {                                           // this warp no longer reads geometry / box buffer gb
@@ -285,31 +348,35 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       }
     }
   } else if (warp == V6_W_MMA) {
-    // =========================================================================== MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
-      uint32_t acc = 0, acc_phase[2] = {0, 0};
-      int n = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);   // epilogue has drained this accumulator
+    // =========================================================================== MMA issuer
+    // The whole warp runs the loop so that stage indices, TMEM addresses and descriptors are warp-uniform (uniform
+    // datapath, no R2UR chain in front of every UTCHMMA); lane 0 issues.  Measured before: ~130 cycles of dependent
+    // scalar code per tcgen05.mma made this warp the pipeline's bottleneck at ~11k cycles per tile.
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+    const uint32_t b_smem = smem_u32(&s.b[0][0]);
+    int n = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t acc = (uint32_t)it & 1u, acc_phase = ((uint32_t)it >> 1) & 1u;
+      mbar_wait_d<32, DBG>(smem_u32(&s.acc_empty[acc]), acc_phase ^ 1, w0);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
+#pragma unroll 1
+      for (int kb = 0; kb < V6_KBLOCKS; ++kb, ++n) {
+        const int sa = n % V6_NA, sb = n % V6_NB;
+        mbar_wait_d<20, DBG>(smem_u32(&s.full[sa]), (uint32_t)(n / V6_NA) & 1u, w2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
-        for (int kb = 0; kb < V6_KBLOCKS; ++kb, ++n) {
-          const int sa = n % V6_NA, sb = n % V6_NB;
-          mbar_wait(smem_u32(&s.b_full[sb]), (uint32_t)(n / V6_NB) & 1u);
-          mbar_wait(smem_u32(&s.a_full[sa]), (uint32_t)(n / V6_NA) & 1u);
-          tc_fence_after();
-          const uint32_t a_tmem = tmem_base + (uint32_t)(V6_A_COL0 + sa * 32);
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[sb][0]));
-          const int nk = (kb == V6_KBLOCKS - 1) ? 3 : 4;
-          for (int k = 0; k < nk; ++k)                   // 16 bf16 of K = 8 TMEM columns of A = 32 B of the B swizzle atom
-            umma_bf16_ts(d_tmem, a_tmem + 8 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(smem_u32(&s.a_empty[sa]));
-          umma_commit(smem_u32(&s.b_empty[sb]));
-        }
-        umma_commit(smem_u32(&s.acc_full[acc]));
-        acc_phase[acc] ^= 1;
-        acc ^= 1;
+        const uint32_t a_tmem = tmem_base + (uint32_t)(V6_A_COL0 + sa * 32);
+        const uint64_t bdesc = umma_desc_sw128(b_smem + (uint32_t)sb * TC_B_BYTES);
+        const long long ti0 = dbg ? clock64() : 0;
+        // 16 bf16 of K = 8 TMEM columns of A = 32 B of the B swizzle atom (+2 in the encoded start address)
+        umma_bf16_ts(d_tmem, a_tmem, bdesc, idesc, kb != 0);
+        umma_bf16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+        umma_bf16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+        if (kb != V6_KBLOCKS - 1) umma_bf16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+        const long long ti1 = dbg ? clock64() : 0;
+        umma_commit_elect(smem_u32(&s.done[sa]));
+        if (kb == V6_KBLOCKS - 1) umma_commit_elect(smem_u32(&s.acc_full[acc]));
+        if (dbg) { w3 += ti1 - ti0; w4 += clock64() - ti1; }
       }
     }
     __syncwarp();
@@ -320,8 +387,11 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       int kb = 0;
       for (int n = 0; n < total; ++n) {
         const int sb = n % V6_NB;
-        mbar_wait(smem_u32(&s.b_empty[sb]), ((uint32_t)(n / V6_NB) & 1u) ^ 1u);
-        const uint32_t bar = smem_u32(&s.b_full[sb]);
+        if (n >= V6_NB) {                                // block n - 3 (the previous user of stage sb) has completed
+          const int m = n - V6_NB;
+          mbar_wait_d<64, DBG>(smem_u32(&s.done[m % V6_NA]), (uint32_t)(m / V6_NA) & 1u, w0);
+        }
+        const uint32_t bar = smem_u32(&s.full[n % V6_NA]);
         mbar_arrive_expect_tx(bar, TC_B_BYTES);
         bulk_g2s(smem_u32(&s.b[sb][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, bar);
         if (++kb == V6_KBLOCKS) kb = 0;
@@ -332,92 +402,130 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     // =========================================================================== source-box copies (one lane per box row)
     for (int it = 0; it < my_tiles; ++it) {
       const int sb = it & 1;
-      mbar_wait(smem_u32(&s.box_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old box
+      mbar_wait_d<256, DBG>(smem_u32(&s.box_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old box
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
       const int ya = max(by0, 0), yb = min(by0 + V6_BOX_H, p.H), xa = max(bx0, 0), xb = min(bx0 + V6_BOX_W, p.W);
       const uint32_t ncol = (uint32_t)(xb - xa), nrow = (uint32_t)(yb - ya);
       const uint32_t bar = smem_u32(&s.box_full[sb]);
-      if (lane == 0) mbar_arrive_expect_tx(bar, nrow * ncol * (TC_CMAIN + TC_CTAIL) * 2);
+      const uint32_t dst_main = smem_u32(&s.box_main[sb][0]), dst_tail = smem_u32(&s.box_tail[sb][0]);
+      if (nrow * ncol != (uint32_t)V6_BOX_PX) {
+        // border tile: the part of the box outside the image is zero padding (what torchvision's skipped corners amount to)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lane; i < V6_BOX_PX; i += 32) {
+          const int yy = by0 + i / V6_BOX_W, xx = bx0 + i % V6_BOX_W;
+          if (yy < ya || yy >= yb || xx < xa || xx >= xb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sts16(dst_main + (uint32_t)i * V6_MAIN_PX + c * 16, z);
+            sts16(dst_tail + (uint32_t)i * V6_TAIL_PX, z);
+          }
+        }
+      }
+      __syncwarp();                                      // the zero padding is ordered before the arrive below (release)
+      if (lane == 0) mbar_arrive_expect_tx(bar, nrow * ncol * (V6_MAIN_PX + V6_TAIL_PX));
       __syncwarp();
       const int y = by0 + lane;
       if (lane < V6_BOX_H && y >= ya && y < yb) {
         const size_t gpix = (size_t)(b * p.H + y) * p.W + xa;
         const uint32_t bpix = (uint32_t)(lane * V6_BOX_W + (xa - bx0));
-        bulk_g2s(smem_u32(&s.box_main[sb][0]) + bpix * (TC_CMAIN * 2), p.x_main + gpix * (TC_CMAIN * 2), ncol * TC_CMAIN * 2, bar);
-        bulk_g2s(smem_u32(&s.box_tail[sb][0]) + bpix * (TC_CTAIL * 2), p.x_tail + gpix * (TC_CTAIL * 2), ncol * TC_CTAIL * 2, bar);
+        bulk_g2s(dst_main + bpix * V6_MAIN_PX, p.x_main + gpix * V6_MAIN_PX, ncol * V6_MAIN_PX, bar);
+        bulk_g2s(dst_tail + bpix * V6_TAIL_PX, p.x_tail + gpix * V6_TAIL_PX, ncol * V6_TAIL_PX, bar);
       }
       __syncwarp();
     }
-  } else if (warp >= V6_W_BACK) {
-    // =========================================================================== back end: geometry + epilogue (8 warps)
-    // Two warps per TMEM quarter; `half` splits both jobs so that the per-tile dependent chain of one warp is short
-    // enough to hide behind the producers: half 0 computes taps 0..4 and drains accumulator columns 0..31, half 1 taps
-    // 5..8 and columns 32..79.
-    const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
-    const int half = (warp - V6_W_BACK) >> 2;
-    const int row = quad * 32 + lane;                    // tile row = TMEM lane = geometry row of this thread
-    const int etid = (warp - V6_W_BACK) * 32 + lane;     // 0..255 for the cooperative store
-    uint32_t acc = 0, acc_phase[2] = {0, 0};
-    const uint32_t ostage = smem_u32(&s.ostage[0]);
-
-    auto make_geometry = [&](int it, auto half_tag) {
-      constexpr int K0 = decltype(half_tag)::value ? 5 : 0, NK = decltype(half_tag)::value ? 4 : 5;
+  } else if (warp >= V6_W_GEO) {
+    // =========================================================================== tap geometry (4 warps)
+    // Thread = tile row, nine taps.  Runs one tile ahead of the producers (double-buffered entries); the offset / mask
+    // values arrive in shared memory by cp.async a further tile ahead, so no DRAM round trip sits in this warp.
+    const int row = (warp - V6_W_GEO) * 32 + lane;
+    // Offsets and masks of a tile: 27 channels x 8 tile rows x 16 pixels = 432 chunks of 16 bytes of the NCHW tensor,
+    // brought into raw[channel][tile row * 16 + x] by cp.async (four per thread, no registers held) one tile ahead.
+    auto fetch_raw = [&](int it) {
+      int b, ty0, tx0;
+      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+      const int rows = min(TC_TH, p.H - ty0), cols = min(TC_TW, p.W - tx0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = row + 128 * j, c = i >> 4, r = (i >> 1) & 7, x8 = (i & 1) * 8;
+        if (i < 27 * 16 && r < rows && x8 < cols) {
+          const TO* src;
+          if (FUSED27) src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + (c < 18 ? (c < 9 ? c : c + 9) : c - 9) * p.f_sc;
+          else if (c < 18) src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + c * p.f_sc;
+          else src = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + (c - 18) * p.m_sc;
+          src += (long long)(ty0 + r) * (c < 18 || FUSED27 ? p.f_sh : p.m_sh) + tx0 + x8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.raw[c][r * TC_TW + x8])), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t raw[27];                                    // [dy x9 | dx x9 | mask x9] as raw bits
+    if (my_tiles > 0) fetch_raw(0);
+    for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
-      mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old contents
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      geo_bar_sync();                                      // every thread's chunks of this tile have landed
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {                        // tap k: channels 2k, 2k+1 of the offsets, channel k of the mask
+        raw[k] = s.raw[2 * k][row];
+        raw[9 + k] = s.raw[2 * k + 1][row];
+        raw[18 + k] = s.raw[18 + k][row];
+      }
+      geo_bar_sync();                                      // everybody holds its values: the buffer is free
+      if (it + 1 < my_tiles) fetch_raw(it + 1);
+      mbar_wait_d<256, DBG>(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old contents
+      const long long tg0 = dbg ? clock64() : 0;
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
       const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
       if (y < p.H && x < p.W) {
-        // all offset / mask values of this thread are requested before the first one is used (one DRAM round trip)
-        const int f_sc = (int)p.f_sc, m_sc = (int)p.m_sc;
-        const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
-        const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
         const int base = b * p.H * p.W;
-        TO rdy[NK], rdx[NK], rmk[NK];
+        const float fy0 = (float)(y - 1), fx0 = (float)(x - 1);
+        uint32_t slow = 0;                                 // taps the box does not serve (rare): patched below
 #pragma unroll
-        for (int i = 0; i < NK; ++i) {
-          const int k = K0 + i, j0 = 2 * k, j1 = 2 * k + 1;
-          if (p.fused27) {
-            // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets (tap k uses channels 2k and
-            // 2k+1 of their concatenation), the middle third is the pre-sigmoid mask
-            rdy[i] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
-            rdx[i] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
-            rmk[i] = __ldg(msk + (9 + k) * m_sc);
-          } else {
-            rdy[i] = __ldg(off + j0 * f_sc);
-            rdx[i] = __ldg(off + j1 * f_sc);
-            rmk[i] = __ldg(msk + k * m_sc);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NK; ++i) {
-          float mk = to_f32<TO>(rmk[i]);
+        for (int k = 0; k < 9; ++k) {                      // straight-line code: the nine taps interleave
+          float mk = bits_to_f32<TO>(raw[18 + k]);
           // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
-          if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
-          s.geo[gb][K0 + i][row] =
-              v6_geo_entry(p.H, p.W, base, by0, bx0, y, x, K0 + i, to_f32<TO>(rdy[i]), to_f32<TO>(rdx[i]), mk);
+          if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
+          uint4 e;
+          if (!v6_geo_entry(by0, bx0, fy0 + (float)(k / 3), fx0 + (float)(k % 3), bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk, e))
+            slow |= 1u << k;
+          s.geo[gb][k][row] = e;
+        }
+        if (slow) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {                    // static indices keep `raw` in registers
+            if (!(slow & (1u << k))) continue;
+            float mk = bits_to_f32<TO>(raw[18 + k]);
+            if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
+            s.geo[gb][k][row] = v6_geo_entry_slow(p.H, p.W, base, y, x, k, bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk);
+          }
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < NK; ++i) s.geo[gb][K0 + i][row] = make_uint4(V6_INSIDE | V6_SAFE, 0u, 0u, 0u);
+        for (int k = 0; k < 9; ++k) s.geo[gb][k][row] = make_uint4(V6_SAFE, 0u, 0u, 0u);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
-    };
-    auto geometry = [&](int it) {
-      if (half) make_geometry(it, std::integral_constant<int, 1>{});
-      else make_geometry(it, std::integral_constant<int, 0>{});
-    };
-
-    if (my_tiles > 0) geometry(0);
+      if (dbg) w2 += clock64() - tg0;
+    }
+  } else if (warp >= V6_W_EPI) {
+    // =========================================================================== epilogue (4 warps)
+    const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
+    const int row = quad * 32 + lane;                    // tile row = TMEM lane of this thread
+    const int etid = (warp - V6_W_EPI) * 32 + lane;      // 0..127 for the cooperative store
+    const uint32_t ostage = smem_u32(&s.ostage[0]);
+    // cooperative store: thread = (tile column etid / 8, 16-byte chunk etid % 8); pass i = tile row i
+    const int cs_x = etid >> 3, cs_c = etid & 7;
+    const uint32_t cs_src = ostage + (uint32_t)cs_x * 128 + ((uint32_t)(cs_c ^ (cs_x & 7)) << 4);   // + 2048 per tile row (16 % 8 == 0)
+    const size_t cs_row = (size_t)p.W * V6_MAIN_PX;
     for (int it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles) geometry(it + 1);           // overlaps the producers' work on tile `it`
+      const uint32_t acc = (uint32_t)it & 1u, acc_phase = ((uint32_t)it >> 1) & 1u;
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
+      mbar_wait_d<256, DBG>(smem_u32(&s.acc_full[acc]), acc_phase, w1);
+      const long long te0 = dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
@@ -425,18 +533,18 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const size_t pixel = (size_t)(b * p.H + y) * p.W + x;
       __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(p.out_tail) + pixel * TC_CTAIL;
       TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
-      const int c16_lo = half ? 2 : 0, c16_hi = half ? TC_N / 16 : 2;
-      for (int c16 = c16_lo; c16 < c16_hi; ++c16) {
+#pragma unroll
+      for (int c16 = 0; c16 < TC_N / 16; ++c16) {
         uint32_t d[16];
         tmem_ld16(taddr + c16 * 16, d);
         tmem_ld_wait();
-        if (c16 == c16_hi - 1) {                         // last TMEM read of this accumulator by this warp: hand it back early
+        if (c16 == TC_N / 16 - 1) {                      // last TMEM read of this accumulator: hand it back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
         }
         // the bias is already in the accumulator (K elements 36/37 of the tail block)
-        if (p.out_tail) {
+        if (PLANES) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c0 = c16 * 16 + h * 8;
@@ -459,25 +567,26 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
           }
         }
       }
-      if (p.out_tail) {
-        // main plane: the staged tile leaves as full 128-byte lines (8 lanes per pixel)
+      if (PLANES) {
+        // main plane: the staged tile leaves as full 128-byte lines (8 lanes per pixel, 4 pixels per warp store)
         epi_bar_sync();
-        uint8_t* om = reinterpret_cast<uint8_t*>(p.out);
+        const int xx = tx0 + cs_x;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(b * p.H + ty0) * p.W + xx) * V6_MAIN_PX + cs_c * 16;
+        if (xx < p.W) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = i * 256 + etid, r = idx >> 3, c = idx & 7;
-          const int yy = ty0 + r / TC_TW, xx = tx0 + r % TC_TW;
-          const uint4 v = lds16(ostage + (uint32_t)r * 128 + ((uint32_t)(c ^ (r & 7)) << 4));
-          if (yy < p.H && xx < p.W)
-            *reinterpret_cast<uint4*>(om + ((size_t)(b * p.H + yy) * p.W + xx) * (TC_CMAIN * 2) + c * 16) = v;
+          for (int i = 0; i < TC_TH; ++i)
+            if (ty0 + i < p.H) *reinterpret_cast<uint4*>(dst + i * cs_row) = lds16(cs_src + i * (TC_TW * 128));
         }
         epi_bar_sync();                                   // the staging tile may be overwritten by the next tile
       }
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
+      if (dbg) w3 += clock64() - te0;
     }
   }
 
+  if (dbg && lane == 0) {
+    unsigned long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
+    d[0] = (unsigned long long)(clock64() - t_begin); d[1] = w0; d[2] = w1; d[3] = w2; d[4] = w3; d[5] = my_tiles; d[6] = w4;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == V6_W_MMA) {
@@ -537,13 +646,13 @@ __global__ void __launch_bounds__(128, 1) umma_ts_selftest_kernel(const __nv_bfl
   tmem_st_wait();
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {                           // whole warp: the MMA / commit wrappers elect their own lane
     tc_fence_after();
     constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
     const uint64_t bdesc = umma_desc_sw128(smem_u32(sb));
     for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base, tmem_base + a_col + 8 * k, bdesc + 2 * k, idesc, k != 0);
     for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base, tmem_base + a_col + 32 + 8 * k, bdesc + 2 * k, idesc, 1);
-    umma_commit(smem_u32(bar));
+    umma_commit_elect(smem_u32(bar));
   }
   mbar_wait(smem_u32(bar), 0);
   tc_fence_after();
