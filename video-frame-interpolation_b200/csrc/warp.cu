@@ -138,6 +138,105 @@ __global__ void __launch_bounds__(WARP_BLOCK) warp_fwd_kernel(const WarpParams p
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, fast path
+// The form the hot path calls: C = 3 planar source with unit pixel stride (NCHW frames), flow with unit pixel stride, out
+// planar or tail-plane records.  The generic kernel above spends ~250 instructions per pixel on 64-bit strided
+// addressing, run-time division modes and predicated corner loads; this one is specialised down to ~110:
+//   * the division mode is a template parameter; all plane offsets are 32-bit and the three planes share them;
+//   * no predicated loads and two addresses per plane: the 2 x 2 patch is clamped into the frame as a whole, the 1-D weights
+//     are re-slotted / zeroed for patches hanging over an edge (zeros padding), so all twelve gathers of a pixel are
+//     unconditional, in flight together, and ten of them use immediate offsets.
+// Arithmetic per corner and the coordinate replay are those of the generic kernel (warp_math.h), bit for bit.
+constexpr int WARPF_BLOCK = 128;
+
+template <bool RECIP> __device__ __forceinline__ float warp_coord_t(int pix, float disp, const WarpAxis& ax) {
+  float g = VFI_MUL(2.0f, VFI_ADD((float)pix, disp));
+  float q = VFI_MUL(g, ax.inv_denom);
+  if (!RECIP) q = VFI_FMA(VFI_FMA(-q, ax.denom, g), ax.inv_denom, q);      // Markstein: q = RN(g / denom)
+  const float i = VFI_MUL(VFI_MUL(VFI_ADD(VFI_SUB(q, 1.0f), 1.0f), 0.5f), ax.size_m1);
+  return fminf(fmaxf(i, -4.0f), ax.hi);
+}
+
+template <typename T> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<__nv_bfloat16> { using type = __nv_bfloat162; };
+template <> struct Pair<__half> { using type = __half2; };
+__device__ __forceinline__ float2 pair_to_f32(float2 v) { return v; }
+__device__ __forceinline__ float2 pair_to_f32(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ float2 pair_to_f32(__half2 v) { return __half22float2(v); }
+template <typename T> __device__ __forceinline__ typename Pair<T>::type pair_from_f32(float a, float b);
+template <> __device__ __forceinline__ float2 pair_from_f32<float>(float a, float b) { return make_float2(a, b); }
+template <> __device__ __forceinline__ __nv_bfloat162 pair_from_f32<__nv_bfloat16>(float a, float b) { return __floats2bfloat162_rn(a, b); }
+template <> __device__ __forceinline__ __half2 pair_from_f32<__half>(float a, float b) { return __floats2half2_rn(a, b); }
+
+constexpr int WARPF_PPT = 2;                      // pixels per thread, one block apart (x, x + 128)
+
+// Lanes are CONSECUTIVE pixels: the 2-byte gathers of a warp then span ~64 bytes + the flow's variation, i.e. one or two
+// 128-byte lines per request.  (A thread owning two ADJACENT pixels halves the flow / store requests but doubles that span;
+// measured: 3.7 L1 wavefronts per request and the LSU data pipe at 73 % -- the kernel's bound -- against ~1.3 here.)
+template <typename TS, typename TF, bool REC, bool RECIP>
+__global__ void __launch_bounds__(WARPF_BLOCK) warp_fwd_fast_kernel(const WarpParams p) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int xb = blockIdx.x * (WARPF_BLOCK * WARPF_PPT) + threadIdx.x;
+  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + (long long)y * p.f_sh;
+  const TF* fly = fl + p.f_sc;
+  const TS* s0 = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
+  const TS* s1 = s0 + p.s_sc;
+  const TS* s2 = s1 + p.s_sc;
+  const int pitch = (int)p.s_sh, H = p.H, W = p.W;
+  float fx[WARPF_PPT], fy[WARPF_PPT];
+#pragma unroll
+  for (int i = 0; i < WARPF_PPT; ++i) {
+    const int x = min(xb + i * WARPF_BLOCK, W - 1);             // out-of-range threads recompute the last pixel (not stored)
+    fx[i] = to_f32<TF>(__ldcs(fl + x));
+    fy[i] = to_f32<TF>(__ldcs(fly + x));
+  }
+  float r[WARPF_PPT][3];
+#pragma unroll
+  for (int i = 0; i < WARPF_PPT; ++i) {
+    const int x = min(xb + i * WARPF_BLOCK, W - 1);
+    const float ix = warp_coord_t<RECIP>(x, fx[i], p.ax);
+    const float iy = warp_coord_t<RECIP>(y, fy[i], p.ay);
+    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);
+    const float x0f = (float)x0, y0f = (float)y0;
+    // The 2 x 2 patch is addressed from its clamped north-west pixel (xc, yc) in [0, W-2] x [0, H-2]: the other three
+    // corners are at compile-time byte offsets / one row pitch.  d = x0 - xc is 0 inside the frame; -1 / +1 when the
+    // true patch hangs over the left / right edge by one pixel (its inner column then sits in the other slot); anything
+    // else means no valid corner.  Zero weights stand for aten's skipped corners, and the order of the non-zero
+    // products (nw, ne, sw, se) is unchanged.
+    const int xc = min(max(x0, 0), W - 2), yc = min(max(y0, 0), H - 2);
+    const int dx = x0 - xc, dy = y0 - yc;
+    const float ax1 = ix - x0f, ax0 = (x0f + 1.0f) - ix, ay1 = iy - y0f, ay0 = (y0f + 1.0f) - iy;
+    const float wxa = dx == 0 ? ax0 : (dx == -1 ? ax1 : 0.0f), wxb = dx == 0 ? ax1 : (dx == 1 ? ax0 : 0.0f);
+    const float wya = dy == 0 ? ay0 : (dy == -1 ? ay1 : 0.0f), wyb = dy == 0 ? ay1 : (dy == 1 ? ay0 : 0.0f);
+    const float w00 = wxa * wya, w01 = wxb * wya, w10 = wxa * wyb, w11 = wxb * wyb;
+    const unsigned o = (unsigned)(yc * pitch + xc);
+    auto lerp = [&](const TS* pl) {
+      const TS* q0 = pl + o;
+      const TS* q1 = q0 + pitch;
+      const float a = ldg_f32(q0), bb = ldg_f32(q0 + 1), d = ldg_f32(q1), e = ldg_f32(q1 + 1);
+      return fmaf(e, w11, fmaf(d, w10, fmaf(bb, w01, a * w00)));
+    };
+    r[i][0] = lerp(s0); r[i][1] = lerp(s1); r[i][2] = lerp(s2);
+  }
+#pragma unroll
+  for (int i = 0; i < WARPF_PPT; ++i) {
+    const int x = xb + i * WARPF_BLOCK;
+    if (x >= W) continue;
+    if constexpr (REC) {
+      // tail-plane record: 16 bytes per pixel, channels 3..7 zero
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + (long long)x * 8;
+      const __nv_bfloat162 c01 = __floats2bfloat162_rn(r[i][0], r[i][1]), c2z = __floats2bfloat162_rn(r[i][2], 0.0f);
+      __stcs(reinterpret_cast<uint4*>(out),
+             make_uint4(*reinterpret_cast<const uint32_t*>(&c01), *reinterpret_cast<const uint32_t*>(&c2z), 0u, 0u));
+    } else {
+      TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) __stcs(out + c * p.o_sc, from_f32<TS>(r[i][c]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ blend (W3)
 struct BlendParams {
   WarpParams a;          // src_a / flow_a / out
@@ -260,7 +359,23 @@ WarpParams make_params(const vfi_tensor* src, const vfi_tensor* flow, const vfi_
 }
 
 template <typename TS, typename TF>
-int launch_fwd(const WarpParams& p, bool rec, cudaStream_t st) {
+int launch_fwd(const WarpParams& p, bool rec, bool fast, cudaStream_t st) {
+  if (fast) {
+    dim3 grid(ceil_div(p.W, WARPF_BLOCK * WARPF_PPT), p.H, p.B);
+    const bool recip = p.ax.recip != 0;
+    if constexpr (std::is_same<TS, __nv_bfloat16>::value) {
+      if (rec) {
+        if (recip) warp_fwd_fast_kernel<TS, TF, true, true><<<grid, WARPF_BLOCK, 0, st>>>(p);
+        else warp_fwd_fast_kernel<TS, TF, true, false><<<grid, WARPF_BLOCK, 0, st>>>(p);
+        VFI_LAUNCH_CHECK("warp_fwd_fast_kernel<rec>");
+        return VFI_OK;
+      }
+    }
+    if (recip) warp_fwd_fast_kernel<TS, TF, false, true><<<grid, WARPF_BLOCK, 0, st>>>(p);
+    else warp_fwd_fast_kernel<TS, TF, false, false><<<grid, WARPF_BLOCK, 0, st>>>(p);
+    VFI_LAUNCH_CHECK("warp_fwd_fast_kernel");
+    return VFI_OK;
+  }
   dim3 grid(ceil_div(p.W, WARP_BLOCK * WARP_PPT), p.H, p.B);
   if constexpr (std::is_same<TS, __nv_bfloat16>::value) {
     if (rec) {
@@ -292,9 +407,12 @@ extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const
   // tail-plane record output: [B,H,W,8] bf16 records holding C = 3 channels + zeros
   const bool rec = src->dtype == VFI_BF16 && src->c == 3 && out->sc == 1 && out->sw == 8 && out->sh % 8 == 0 &&
                    out->sn % 8 == 0 && aligned(out->data, 16);
+  // fast path: three planar channels with unit pixel strides
+  const bool fast = src->c == 3 && src->sw == 1 && flow->sw == 1 && src->w >= 2 && src->h >= 2 && src->sh >= 0 && src->sc >= 0 &&
+                    src->sn >= 0 && (rec || out->sw == 1);
   VFI_DISPATCH(src->dtype, TS, {
-    if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, rec, st); }
-    else { rc = launch_fwd<TS, TS>(p, rec, st); }
+    if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, rec, fast, st); }
+    else { rc = launch_fwd<TS, TS>(p, rec, fast, st); }
   });
   return rc;
 }
