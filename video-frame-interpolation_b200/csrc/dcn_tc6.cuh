@@ -58,7 +58,7 @@ struct __align__(1024) V6Smem {
   uint8_t ostage[TC_M * 128];                          // epilogue staging tile (chunk j of row r at j ^ (r & 7))
   uint16_t raw[27][TC_M];                              // offset / mask values of the next tile (cp.async), [channel][tile row]
   unsigned long long full[V6_NA], done[V6_NA];         // per K block n (slot n % 8): operands ready / MMAs complete
-  unsigned long long acc_full[2], acc_empty[2], geo_full[2], geo_empty[2], box_full[2], box_empty[2];
+  unsigned long long acc_full[2], acc_empty[2], geo_first[2], geo_full[2], geo_empty[2], box_full[2], box_empty[2];
   uint32_t tmem_base;
 };
 
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
       mbar_init(smem_u32(&s.acc_empty[i]), V6_EPI_WARPS);
-      mbar_init(smem_u32(&s.geo_full[i]), V6_GEO_WARPS);
+      mbar_init(smem_u32(&s.geo_first[i]), V6_GEO_WARPS);       // taps 0..3 written (what the first K blocks of a tile need)
+      mbar_init(smem_u32(&s.geo_full[i]), V6_GEO_WARPS);        // all nine taps written
       mbar_init(smem_u32(&s.geo_empty[i]), V6_PRODUCER_WARPS);
       mbar_init(smem_u32(&s.box_full[i]), 1);                   // the copy warp's expect_tx arrival (+ the bytes)
       mbar_init(smem_u32(&s.box_empty[i]), V6_PRODUCER_WARPS);
@@ -286,8 +287,9 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait_d<64, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);  // this tile's geometry has been written
+      mbar_wait_d<64, DBG>(smem_u32(&s.geo_first[gb]), tphase, w0); // this tile's geometry, taps 0..3, has been written
       mbar_wait_d<64, DBG>(smem_u32(&s.box_full[gb]), tphase, w1);  // this tile's source box has landed in shared memory
+      bool all_taps = false;
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]), box_tail = smem_u32(&s.box_tail[gb][0]);
       const uint32_t bF = box_main + c_first, bS = box_main + c_second;
       const int n0 = it * V6_KBLOCKS;
@@ -296,6 +298,10 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         const int n = n0 + kb, sa = n % V6_NA;
         const uint32_t empty_bar = smem_u32(&s.done[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
+        if (kb >= 4 && !all_taps) {                              // taps 4..8 (and the tail block, which reads all nine)
+          mbar_wait_d<64, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);
+          all_taps = true;
+        }
         if (kb < 9) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -482,29 +488,40 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       if (y < p.H && x < p.W) {
         const int base = b * p.H * p.W;
         const float fy0 = (float)(y - 1), fx0 = (float)(x - 1);
-        uint32_t slow = 0;                                 // taps the box does not serve (rare): patched below
+        // taps 0..3 first: they are all the first K blocks of the tile need, so the producers start on them while
+        // taps 4..8 are still being computed (the geometry of a tile cannot start before the previous tile but one is done)
+        auto taps = [&](auto k0_tag, auto k1_tag) {
+          constexpr int K0 = decltype(k0_tag)::value, K1 = decltype(k1_tag)::value;
+          uint32_t slow = 0;                               // taps the box does not serve (rare): patched below
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {                      // straight-line code: the nine taps interleave
-          float mk = bits_to_f32<TO>(raw[18 + k]);
-          // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
-          if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
-          uint4 e;
-          if (!v6_geo_entry(by0, bx0, fy0 + (float)(k / 3), fx0 + (float)(k % 3), bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk, e))
-            slow |= 1u << k;
-          s.geo[gb][k][row] = e;
-        }
-        if (slow) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) {                    // static indices keep `raw` in registers
-            if (!(slow & (1u << k))) continue;
+          for (int k = K0; k < K1; ++k) {                  // straight-line code: the taps interleave
             float mk = bits_to_f32<TO>(raw[18 + k]);
+            // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
             if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
-            s.geo[gb][k][row] = v6_geo_entry_slow(p.H, p.W, base, y, x, k, bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk);
+            uint4 e;
+            if (!v6_geo_entry(by0, bx0, fy0 + (float)(k / 3), fx0 + (float)(k % 3), bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk, e))
+              slow |= 1u << k;
+            s.geo[gb][k][row] = e;
           }
-        }
+          if (slow) {
+#pragma unroll
+            for (int k = K0; k < K1; ++k) {                // static indices keep `raw` in registers
+              if (!(slow & (1u << k))) continue;
+              float mk = bits_to_f32<TO>(raw[18 + k]);
+              if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
+              s.geo[gb][k][row] = v6_geo_entry_slow(p.H, p.W, base, y, x, k, bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk);
+            }
+          }
+        };
+        taps(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
+        taps(std::integral_constant<int, 4>{}, std::integral_constant<int, 9>{});
       } else {
 #pragma unroll
         for (int k = 0; k < 9; ++k) s.geo[gb][k][row] = make_uint4(V6_SAFE, 0u, 0u, 0u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
