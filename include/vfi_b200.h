@@ -101,7 +101,9 @@ size_t vfi_dcn_workspace_bytes(int64_t B, int64_t C, int64_t O, int64_t H, int64
 
 /* Tensor-core path operand formats.
  *  - Activation "planes": channels-last bf16 in two dense buffers, main [B,H,W,64] (128 B per pixel: one aligned cache
- *    line per bilinear corner) and tail [B,H,W,8] (16 B per pixel: channels 64..71, zero beyond C).
+ *    line per bilinear corner) and tail [B,H,W,8] (16 B per pixel: channels 64..71, zero beyond C; when there are at most four tail channels -- the
+ *    reference's C = 67 -- bytes 8..15 of every record must MIRROR bytes 0..7, which every kernel of this library that
+ *    writes planes does: the gather may then read either half and spreads its 8-byte reads over all shared-memory banks).
  *  - Weight image: 11 K blocks x [80 rows (o, zero padded)] x 128 B; K block t < 9 holds the 64 main channels of tap t,
  *    block 9 the 8-channel tails of taps 0..7, block 10 the tail of tap 8 + zeros; each row's eight 16-byte chunks are
  *    already permuted for the SWIZZLE_128B canonical layout (chunk j of row r stored at j ^ (r & 7)).
@@ -122,7 +124,7 @@ int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor*
  *  - the offset/mask split of ema_vfi.py:57-59: conv27 is the raw [B,27,H,W] offset_conv output; offsets are its
  *    thirds 0 and 2, the mask is sigmoid(third 1), computed in the kernel's geometry stage;
  *  - the torch.cat of ema_vfi.py:134: the input is given as planes, x_main [B,64,H,W] + x_tail [B,<=8,H,W] (dense
- *    channels-last bf16, pixel strides 64 and 8 elements, pad channels of the tail zero) -- feat and the warped frame
+ *    channels-last bf16, pixel strides 64 and 8 elements, pad channels of the tail zero, upper record half mirrored for <= 4 tail channels) -- feat and the warped frame
  *    as they exist before the cat.  x_tail may be NULL, in which case x_main is handled as vfi_dcn_fwd handles x.
  * Output: planes when out_tail != NULL (out [B,64,H,W], out_tail [B,O-64,H,W]; what the next layer reads directly),
  * otherwise any strided [B,O,H,W] tensor. */

@@ -119,7 +119,7 @@ def test_warp_into_tail_plane_records():
     out = vfi_b200.warp(src.to(DEV), flow.to(DEV), out=pl.tail_nchw(3))
     assert out.data_ptr() == pl.tail.data_ptr()
     assert relerr(pl.tail_nchw(3), ref) <= 1e-2
-    assert float(pl.tail[..., 3:].abs().max()) == 0.0
+    assert float(pl.tail[..., 3].abs().max()) == 0.0 and torch.equal(pl.tail[..., 4:], pl.tail[..., :4])   # mirrored halves
     assert maxabs(pl.tail_nchw(3), vfi_b200.warp(src.to(DEV), flow.to(DEV))) == 0.0   # same values as the planar kernel
 
 
@@ -336,12 +336,13 @@ def test_dcn_fused_split_input_and_conv27(math, bar):
     b = ((torch.rand(67, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
     src = ops.Planes(B, H, W, DEV, zero_tail=True)
     src.main.copy_(feat.permute(0, 2, 3, 1))
-    src.tail[..., :3] = tail3.permute(0, 2, 3, 1).to(DEV)
+    src.set_tail(tail3)
     out = ops.deform_conv2d_fused(src.main_nchw, src.tail_nchw(3), c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
     off, m = oracle.pack_split(c27.float().numpy())
     ref = oracle.dcn_fwd(torch.cat([feat, tail3], 1).float().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
     assert relerr(out.to_nchw(), ref) <= bar
-    assert float(out.tail[..., 3:].abs().max()) == 0.0            # pad channels of the tail plane are written as zeros
+    # channel 3 of the tail plane is zero padding, the upper half of every record mirrors the lower one
+    assert float(out.tail[..., 3].abs().max()) == 0.0 and torch.equal(out.tail[..., 4:], out.tail[..., :4])
     # planes in -> planes out (what layers 2 and 3 of the path do), and a plain NCHW tensor in
     out2 = ops.deform_conv2d_fused(out.main_nchw, out.tail_nchw(), c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
     ref2 = oracle.dcn_fwd(out.to_nchw().float().cpu().numpy(), off, bf16_round(m), w.float().numpy(), b.float().numpy())
@@ -383,7 +384,7 @@ g = torch.Generator().manual_seed(77)
 B, H, W = 2, 44, 88
 feat = torch.randn(B, 64, H, W, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
 src = ops.Planes(B, H, W, 'cuda', zero_tail=True)
-src.tail[..., :3] = torch.randn(B, H, W, 3, generator=g).to(torch.bfloat16).cuda()
+src.set_tail(torch.randn(B, 3, H, W, generator=g))
 c27 = torch.randn(B, 27, H, W, generator=g)
 c27[:, :9] *= 6.0
 c27[:, 18:] *= 6.0

@@ -8,7 +8,9 @@
 //
 // Activation layout ("planes"): channels-last bf16 in two dense buffers,
 //     main [B, H, W, 64]  (128 B per pixel = exactly one aligned L1 line per bilinear corner) and
-//     tail [B, H, W,  8]  ( 16 B per pixel: channels 64..66 + zeros; eight pixels share a line).
+//     tail [B, H, W,  8]  ( 16 B per pixel: channels 64.. and zeros; when there are at most four tail channels the
+//                           upper 8 bytes MIRROR the lower 8, so that a gather may read either half -- v6 picks it by lane
+//                           parity and so spreads its 8-byte reads over all 32 banks).
 // This is how feat (64 ch) and the warped frame (3 ch) exist before the reference's torch.cat (ema_vfi.py:134), and it is
 // what the kernel writes for the next layer.  Any other input layout is converted by pack_input_kernel (workspace).
 //
@@ -231,6 +233,7 @@ __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long l
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int c = chunk * 8 + i;
+    if (chunk == 8 && i >= 4 && C <= TC_CMAIN + 4) c -= 4;      // tail of <= 4 channels: upper half mirrors the lower
     v[i] = __float2bfloat16_rn(c < C ? to_f32<TX>(__ldg(src + c * sc)) : 0.0f);
   }
   __nv_bfloat16* dst = chunk < 8 ? main_plane + pix * TC_CMAIN + chunk * 8 : tail_plane + pix * TC_CTAIL;
@@ -620,6 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
                 w4[i] = *reinterpret_cast<uint32_t*>(&hv);
               }
               __nv_bfloat16* dst = c0 < TC_CMAIN ? om + c0 : ot;
+              if (c0 == TC_CMAIN && p.O <= TC_CMAIN + 4) { w4[2] = w4[0]; w4[3] = w4[1]; }   // tail of <= 4 channels: mirrored
               *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
           } else {

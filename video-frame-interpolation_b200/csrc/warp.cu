@@ -81,7 +81,7 @@ __device__ __forceinline__ float sample(const TS* plane, const Corners& c) {
 // Instruction-level parallelism comes from PPT pixels per thread spaced one block apart (x, x + 256): all 2 x 4 x C
 // gathers of a thread are independent and in flight together.  grid = (ceil(W / 512), H, B).
 // REC = true: out is a channels-last bf16 "tail plane" (unit channel stride, 8 elements = 16 B per pixel) -- the tail
-// input of the tensor-core DCN kernel; channels >= C are written as zeros (no pre-clearing, no torch.cat).
+// input of the tensor-core DCN kernel: [c0 c1 c2 0 | c0 c1 c2 0], every byte written (no pre-clearing, no torch.cat).
 constexpr int WARP_BLOCK = 256;
 constexpr int WARP_PPT = 2;
 
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(WARP_BLOCK) warp_fwd_kernel(const WarpParams p
       if (!ok[i]) continue;
       __align__(16) __nv_bfloat16 rec[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) rec[c] = __float2bfloat16_rn(c < CT ? r[i][c < CT ? c : 0] : 0.0f);
+      for (int c = 0; c < 8; ++c) rec[c] = __float2bfloat16_rn((c & 3) < CT ? r[i][(c & 3) < CT ? (c & 3) : 0] : 0.0f);   // mirrored halves
       __stcs(reinterpret_cast<uint4*>(out + (x0 + i * WARP_BLOCK) * o_sw), *reinterpret_cast<uint4*>(rec));
     }
   } else {
@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(WARPF_BLOCK) warp_fwd_fast_kernel(const WarpPa
     const int x = xb + i * WARPF_BLOCK;
     if (x >= W) continue;
     if constexpr (REC) {
-      // tail-plane record: 16 bytes per pixel, channels 3..7 zero
+      // tail-plane record: 16 bytes per pixel = [c0 c1 c2 0 | c0 c1 c2 0] (mirrored halves, see dcn_tc.cu)
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + (long long)x * 8;
       const __nv_bfloat162 c01 = __floats2bfloat162_rn(r[i][0], r[i][1]), c2z = __floats2bfloat162_rn(r[i][2], 0.0f);
-      __stcs(reinterpret_cast<uint4*>(out),
-             make_uint4(*reinterpret_cast<const uint32_t*>(&c01), *reinterpret_cast<const uint32_t*>(&c2z), 0u, 0u));
+      const uint32_t lo = *reinterpret_cast<const uint32_t*>(&c01), hi = *reinterpret_cast<const uint32_t*>(&c2z);
+      __stcs(reinterpret_cast<uint4*>(out), make_uint4(lo, hi, lo, hi));
     } else {
       TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + x;
 #pragma unroll

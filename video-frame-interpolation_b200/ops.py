@@ -106,13 +106,24 @@ MAIN_C, TAIL_C = 64, 8   # channels per pixel in the two activation planes of th
 class Planes:
     """An activation of up to 72 channels in the layout the tcgen05 DCN kernel gathers from and writes: two dense
     channels-last bf16 buffers, ``main`` [B,H,W,64] (128 B per pixel) and ``tail`` [B,H,W,8] (16 B per pixel, channels
-    64.. and zero padding).  ``main_nchw`` / ``tail_nchw(c)`` are the logical [B,C,H,W] views handed to the C ABI."""
+    64.. and zero padding; with at most four tail channels the upper half of the record mirrors the lower half, which
+    the kernels that write planes do themselves -- use :meth:`set_tail` when filling one by hand).  ``main_nchw`` /
+    ``tail_nchw(c)`` are the logical [B,C,H,W] views handed to the C ABI."""
 
     def __init__(self, B: int, H: int, W: int, device, channels: int = 67, zero_tail: bool = False):
         self.channels = channels
         self.main = torch.empty((B, H, W, MAIN_C), dtype=torch.bfloat16, device=device)
         alloc = torch.zeros if zero_tail else torch.empty
         self.tail = alloc((B, H, W, TAIL_C), dtype=torch.bfloat16, device=device)
+
+    def set_tail(self, t: torch.Tensor) -> None:
+        """Fill the tail plane from a [B,c,H,W] tensor (c <= 8): channels, zero padding and, for c <= 4, the mirrored half."""
+        c = t.shape[1]
+        v = t.permute(0, 2, 3, 1).to(device=self.tail.device, dtype=torch.bfloat16)
+        self.tail.zero_()
+        self.tail[..., :c] = v
+        if c <= 4:
+            self.tail[..., 4:4 + c] = v
 
     @property
     def main_nchw(self) -> torch.Tensor:
