@@ -323,7 +323,13 @@ def main():
                      "achieved": dcn_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                      "frac": dcn_tflops / pk["tensor_sustained"], "traffic": tr.get("dcn_tc_fwd_kernel"), "peak_source": pk["source"] + " sustained bf16",
                      "frac_of_burst_peak": dcn_tflops / pk["tensor_burst"], "ms_per_launch": dcn_ms,
-                     "algorithmic_flop_per_launch": P * FLOP_PER_PX},
+                     "algorithmic_flop_per_launch": P * FLOP_PER_PX,
+                     # what actually bounds the operator on this SM: building one A row reads
+                     # 9 taps x 4 corners x 128 B of activations through the 128 B/clk/SM load/store data path
+                     "lsu_bound": (lambda f_hz: {"bytes_per_px": 36 * 128, "floor_ms": 1e3 * P * 36 / 148 / f_hz,
+                                                 "frac": (1e3 * P * 36 / 148 / f_hz) / dcn_ms,
+                                                 "note": "36 x 128 B gather per output pixel / (128 B/clk/SM x 148 SMs) at the sampled SM clock"})(
+                         1e6 * float((clocks or {}).get("sm_mhz") or 1965.0))},
         "roofline_warp": {"bound": "hbm", "kernel": "warp_fwd (planar NCHW bf16 in/out, timed alone, 20 launches)",
                           "achieved": P * WARP_BYTES_PER_PX_BF16 / (planar_ms["bf16"] * 1e-3) / 1e9, "peak": pk["hbm"],
                           "unit": "GB/s", "frac": P * WARP_BYTES_PER_PX_BF16 / (planar_ms["bf16"] * 1e-3) / 1e9 / pk["hbm"],
