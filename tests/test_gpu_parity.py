@@ -318,6 +318,19 @@ def test_dcn_tensor_core_path(B, H, W, sigma):
     assert relerr(out3, ref3) <= 1e-2
 
 
+def test_dcn_tensor_core_path_fp16_offsets_under_autocast_dtypes():
+    """What the unmodified model hands over under fp16 autocast: fp32 input, fp16 offset / mask.  With
+    math="bf16_tc" this takes the v6 kernel (fp16 geometry inputs, input packed to planes inside the call)."""
+    z = rand_dcn(2, 67, 67, 24, 48, 1.5, seed=77)
+    off16 = torch.from_numpy(z["offset"]).to(torch.float16)
+    m16 = torch.from_numpy(z["mask"]).to(torch.float16)
+    out = vfi_b200.deform_conv2d(cu(z["x"]), off16.to(DEV), cu(z["weight"]), cu(z["bias"]), stride=1, padding=1, dilation=1,
+                                 mask=m16.to(DEV), math="bf16_tc")
+    assert out.dtype == torch.float32 and out.shape == (2, 67, 24, 48)
+    ref = oracle.dcn_fwd(bf16_round(z["x"]), off16.float().numpy(), m16.float().numpy(), bf16_round(z["weight"]), z["bias"])
+    assert relerr(out, ref) <= 1e-2
+
+
 @pytest.mark.parametrize("math,bar", [("bf16_tc", 1e-2), ("bf16_tc_hq", 6e-3)])
 def test_dcn_fused_split_input_and_conv27(math, bar):
     """vfi_dcn_fwd_fused: (feat 64ch channels-last, 3-channel tail) + raw 27-channel offset_conv output, against the

@@ -847,7 +847,8 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y;
   p.debug = dcn_tc_debug_buffer();
-  p.experiment = 0;
+  static const int experiment = [] { const char* e = getenv("VFI_DCN_EXPERIMENT"); return e ? atoi(e) : 0; }();
+  p.experiment = experiment;                          // only read by the debug-counter instantiation (VFI_DCN_DEBUG=1)
   int dev = 0, sms = 148;
   VFI_CUDA(cudaGetDevice(&dev));
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -378,10 +378,12 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         const uint64_t bdesc = umma_desc_sw128(b_smem + (uint32_t)sb * TC_B_BYTES);
         const long long ti0 = dbg ? clock64() : 0;
         // 16 bf16 of K = 8 TMEM columns of A = 32 B of the B swizzle atom (+2 in the encoded start address)
-        umma_bf16_ts(d_tmem, a_tmem, bdesc, idesc, kb != 0);
-        umma_bf16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
-        umma_bf16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
-        if (kb != V6_KBLOCKS - 1) umma_bf16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+        if (!(DBG && (p.experiment & 2))) {                  // diagnostics: bit 1 = issue no MMA
+          umma_bf16_ts(d_tmem, a_tmem, bdesc, idesc, kb != 0);
+          umma_bf16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1);
+          umma_bf16_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1);
+          if (kb != V6_KBLOCKS - 1) umma_bf16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
+        }
         const long long ti1 = dbg ? clock64() : 0;
         umma_commit_elect(smem_u32(&s.done[sa]));
         if (kb == V6_KBLOCKS - 1) umma_commit_elect(smem_u32(&s.acc_full[acc]));
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
           mbar_wait_d<64, DBG>(smem_u32(&s.done[m % V6_NA]), (uint32_t)(m / V6_NA) & 1u, w0);
         }
         const uint32_t bar = smem_u32(&s.full[n % V6_NA]);
+        if (DBG && (p.experiment & 1) && n >= V6_NB) { mbar_arrive(bar); if (++kb == V6_KBLOCKS) kb = 0; continue; }   // diagnostics: no refill
         mbar_arrive_expect_tx(bar, TC_B_BYTES);
         bulk_g2s(smem_u32(&s.b[sb][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, bar);
         if (++kb == V6_KBLOCKS) kb = 0;
