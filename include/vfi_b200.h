@@ -112,6 +112,12 @@ size_t vfi_dcn_packed_weight_bytes(void);
 int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
                         vfi_stream_t stream);
 
+/* Host-only query (no GPU needed): K element kk of block kb of the weight image multiplies weight[:, channel, tap] (channel
+ * -1: zero padding or, for variant 6, the two bias slots 36/37 of block 9).  variant 4 = the v4 kernel's image (the one
+ * vfi_dcn_pack_weight writes), 6 = the image the v6 kernel builds in its workspace, whose main blocks follow the thread <->
+ * column mapping of tcgen05.st.16x256b. */
+int vfi_dcn_k_order(int32_t variant, int32_t kb, int32_t kk, int32_t* tap, int32_t* channel);
+
 /* Converts an activation tensor of any supported layout/dtype (C <= 72) into planes: main_plane B*H*W*64 bf16,
  * tail_plane B*H*W*8 bf16. */
 int vfi_dcn_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, vfi_stream_t stream);

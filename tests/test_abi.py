@@ -143,3 +143,37 @@ def test_launcher_shims():
     run.apply_compat_shims()
     opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1)
     torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.5, patience=5, verbose=True)  # train.py:84
+
+
+def test_weight_image_k_order_is_a_bijection():
+    """Host logic of the tensor-core path (no GPU): every (tap, channel) of the 3x3x67 contraction appears exactly once in
+    the K order of each kernel variant's weight image, and v6's main blocks follow the tcgen05.st.16x256b thread mapping
+    (thread u of a pixel holds the 16-byte chunks u and u + 4)."""
+    import ctypes
+
+    from vfi_b200 import _lib
+
+    lib = _lib.load()
+    for variant, blocks in ((4, 11), (6, 10)):
+        seen = {}
+        for kb in range(blocks):
+            for kk in range(64):
+                tap, c = ctypes.c_int32(), ctypes.c_int32()
+                assert lib.vfi_dcn_k_order(variant, kb, kk, ctypes.byref(tap), ctypes.byref(c)) == 0
+                if c.value >= 0:
+                    assert (tap.value, c.value) not in seen, (variant, kb, kk)
+                    seen[(tap.value, c.value)] = (kb, kk)
+        channels = 72 if variant == 4 else 68
+        assert set(seen) == {(t, c) for t in range(9) for c in range(channels)}
+    # v6 main block: K elements 16 i + 4 u + j  <->  channel 32 (i // 2) + 8 u + 4 (i % 2) + j
+    for kk in range(64):
+        tap, c = ctypes.c_int32(), ctypes.c_int32()
+        lib.vfi_dcn_k_order(6, 3, kk, ctypes.byref(tap), ctypes.byref(c))
+        i, u, j = kk // 16, (kk // 4) % 4, kk % 4
+        assert tap.value == 3 and c.value == 32 * (i // 2) + 8 * u + 4 * (i % 2) + j
+    # bias slots of the v6 tail block are not weight elements
+    for kk in (36, 37, 40, 63):
+        tap, c = ctypes.c_int32(), ctypes.c_int32()
+        lib.vfi_dcn_k_order(6, 9, kk, ctypes.byref(tap), ctypes.byref(c))
+        assert c.value == -1
+    assert lib.vfi_dcn_k_order(5, 0, 0, ctypes.byref(tap), ctypes.byref(c)) != 0

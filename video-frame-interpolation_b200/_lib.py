@@ -43,6 +43,7 @@ SIGNATURES = {
     "vfi_dcn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int32]),
     "vfi_dcn_packed_weight_bytes": (c_size_t, []),
     "vfi_dcn_pack_weight": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
+    "vfi_dcn_k_order": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32)]),
     "vfi_dcn_pack_input": (c_int, [_T, c_void_p, c_void_p, c_void_p]),
     "vfi_dcn_fwd": (c_int, [_T, _T, _T, c_void_p, c_int32, c_void_p, c_int32, _T, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "vfi_dcn_fwd_fused": (c_int, [_T, _T, _T, c_void_p, c_int32, c_void_p, c_int32, _T, _T, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),

@@ -28,6 +28,7 @@ size_t dcn_tc_packed_weight_bytes();
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
                        void* packed, float* bias_out, cudaStream_t st, int variant);
 int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st);
+int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 unsigned long long* dcn_tc_debug_buffer();
 int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
@@ -107,6 +108,10 @@ extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const 
 
 extern "C" int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream) {
   return umma_selftest(a_bf16, b_bf16, d, K, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_k_order(int32_t variant, int32_t kb, int32_t kk, int32_t* tap, int32_t* channel) {
+  return dcn_tc_k_order(variant, kb, kk, tap, channel);
 }
 
 extern "C" int vfi_selftest_umma_ts(const void* a_bf16, const void* b_bf16, float* d, uint32_t* raw, vfi_stream_t stream) {

@@ -932,6 +932,15 @@ int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t s
   return VFI_OK;
 }
 
+// Host-only: which (tap, channel) the weight image multiplies at K element kk of block kb (channel -1 = zero / bias slot).
+int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel) {
+  VFI_REQUIRE(tap && channel && kb >= 0 && kb < TC_KBLOCKS && kk >= 0 && kk < 64 && (variant == 4 || variant == 6), VFI_ERR_INVALID,
+              "vfi_dcn_k_order: variant 4|6, kb in [0,11), kk in [0,64)");
+  if (variant == 6) v6_k_to_tap_channel(kb, kk, *tap, *channel);
+  else tc_k_to_tap_channel(kb, kk, *tap, *channel);
+  return VFI_OK;
+}
+
 int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st) {
   VFI_REQUIRE(A && Bm && D && raw, VFI_ERR_INVALID, "vfi_selftest_umma_ts: need A [128,64], B [80,64], D [128,80], raw [128,32]");
   const size_t smem = TC_B_BYTES + 64 + 1024;
