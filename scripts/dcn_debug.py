@@ -22,11 +22,11 @@ def show(name, warps, labels):
     x = d[:, warps, :]
     tot = x[..., 0].mean()
     print(f"{name:10s} total {tot/1e3:8.1f} kcyc  " + "  ".join(f"{l} {x[..., i+1].mean()/tot*100:5.1f}%" for i, l in enumerate(labels)))
-show("producers", list(range(16)), ["geo_full", "box_full", "a_empty"])
-show("mma", [16], ["acc_empty", "b_full", "a_full", "issue"])
-print("   mma commit %5.1f%%" % (d[:, 16, 6].mean() / d[:, 16, 0].mean() * 100))
-show("box", [17], ["box_empty"])
-show("bload", [18], ["b_empty"])
-show("epilogue", list(range(20, 24)), ["-", "acc_full", "-", "epilogue"])
-show("geometry", list(range(24, 28)), ["geo_empty", "-", "geometry"])
+show("producers", list(range(20)), ["geo_full", "box_full", "a_empty"])
+show("mma", [20], ["acc_empty", "b_full", "a_full", "issue"])
+print("   mma commit %5.1f%%" % (d[:, 20, 6].mean() / d[:, 20, 0].mean() * 100))
+show("box", [21], ["box_empty"])
+show("bload", [22], ["b_empty"])
+show("epilogue", list(range(24, 28)), ["-", "acc_full", "-", "epilogue"])
+show("geometry", list(range(28, 32)), ["geo_empty", "-", "geometry"])
 print("tiles per CTA", d[:, 0, 5].mean(), " cycles per tile", d[:, 0, 0].mean() / d[:, 0, 5].mean())

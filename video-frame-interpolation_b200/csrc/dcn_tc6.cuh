@@ -29,12 +29,15 @@ constexpr int V6_BOX_H = 18, V6_BOX_W = 26, V6_BOX_PX = V6_BOX_H * V6_BOX_W;    
 constexpr int V6_BOX_TOP = 5, V6_BOX_LEFT = 5;                                    // box origin = tile origin - (5, 5)
 constexpr int V6_MAIN_PX = TC_CMAIN * 2, V6_TAIL_PX = TC_CTAIL * 2;               // bytes per pixel: 128 / 16
 constexpr int V6_MAIN_ROW = V6_BOX_W * V6_MAIN_PX, V6_TAIL_ROW = V6_BOX_W * V6_TAIL_PX;   // bytes per box row: 3328 / 416
-constexpr int V6_GROUPS = 4;                                                      // producer groups
-constexpr int V6_PRODUCER_WARPS = 4 * V6_GROUPS;                                  // x 4 TMEM sub-partitions
-constexpr int V6_W_MMA = 16, V6_W_BOX = 17, V6_W_BLOAD = 18;                      // warp 19 idles
-constexpr int V6_W_EPI = 20, V6_EPI_WARPS = 4;                                    // warps 20..23: epilogue (one per TMEM quarter)
-constexpr int V6_W_GEO = 24, V6_GEO_WARPS = 4;                                    // warps 24..27: tap geometry
-constexpr int V6_THREADS = 28 * 32;                                               // 896
+// Warp roles.  1024 threads x 64 registers is the whole register file; the fifth producer group is worth more than the
+// eight registers per thread it costs (the producers are latency bound).  setmaxnreg (72 for producers / 40 for helpers)
+// was tried: ptxas fails register allocation in the producer region under a setmaxnreg budget of 72 or even 80.
+constexpr int V6_GROUPS = 5;                                                      // producer groups: K blocks g and g + 5 of every tile
+constexpr int V6_PRODUCER_WARPS = 4 * V6_GROUPS;                                  // x 4 TMEM sub-partitions = warps 0..19
+constexpr int V6_W_MMA = 20, V6_W_BOX = 21, V6_W_BLOAD = 22;                      // warp 23 idles
+constexpr int V6_W_EPI = 24, V6_EPI_WARPS = 4;                                    // warps 24..27: epilogue (one per TMEM quarter)
+constexpr int V6_W_GEO = 28, V6_GEO_WARPS = 4;                                    // warps 28..31: tap geometry
+constexpr int V6_THREADS = 32 * 32;                                               // 1024
 constexpr int V6_KBLOCKS = 10;                                                    // 9 main + 1 tail
 constexpr int V6_NA = 8, V6_NB = 3;                                               // TMEM A ring / smem B ring depth
 constexpr int V6_A_COL0 = 256;                                                    // TMEM columns [256, 512): A ring
@@ -279,8 +282,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
 
   if (warp < V6_PRODUCER_WARPS) {
     // =========================================================================== A-operand producers
-    // Group gi (4 warps, one per TMEM sub-partition) produces the K blocks n = tile_iter * 10 + kb with n % 4 == gi into
-    // A-ring stage n % 8; warp q of a group owns tile rows (= TMEM lanes) [32q, 32q + 32).
+    // Group gi (4 warps, one per TMEM sub-partition) produces K blocks gi and gi + 5 of every tile into A-ring stage n % 8
+    // (n = tile_iter * 10 + kb); warp q of a group owns tile rows (= TMEM lanes) [32q, 32q + 32).
     const int group = warp >> 2, q = warp & 3;
     const int g = lane >> 2, u = lane & 3;
     const bool par = (g & 1) != 0;
@@ -296,8 +299,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]), box_tail = smem_u32(&s.box_tail[gb][0]);
       const uint32_t bF = box_main + c_first, bS = box_main + c_second;
       const int n0 = it * V6_KBLOCKS;
-      int kb = (group - n0) & (V6_GROUPS - 1);
-      for (; kb < V6_KBLOCKS; kb += V6_GROUPS) {
+      for (int kb = group; kb < V6_KBLOCKS; kb += V6_GROUPS) {   // 10 K blocks, 5 groups: n0 % 5 == 0, every group takes two
         const int n = n0 + kb, sa = n % V6_NA;
         const uint32_t empty_bar = smem_u32(&s.done[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
@@ -471,20 +473,11 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    uint32_t raw[27];                                    // [dy x9 | dx x9 | mask x9] as raw bits
     if (my_tiles > 0) fetch_raw(0);
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       geo_bar_sync();                                      // every thread's chunks of this tile have landed
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {                        // tap k: channels 2k, 2k+1 of the offsets, channel k of the mask
-        raw[k] = s.raw[2 * k][row];
-        raw[9 + k] = s.raw[2 * k + 1][row];
-        raw[18 + k] = s.raw[18 + k][row];
-      }
-      geo_bar_sync();                                      // everybody holds its values: the buffer is free
-      if (it + 1 < my_tiles) fetch_raw(it + 1);
       mbar_wait_d<256, DBG>(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old contents
       const long long tg0 = dbg ? clock64() : 0;
       int b, ty0, tx0;
@@ -499,6 +492,13 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         auto taps = [&](auto k0_tag, auto k1_tag) {
           constexpr int K0 = decltype(k0_tag)::value, K1 = decltype(k1_tag)::value;
           uint32_t slow = 0;                               // taps the box does not serve (rare): patched below
+          uint32_t raw[27];                                // [dy x9 | dx x9 | mask x9] as raw bits; only [K0, K1) is live
+#pragma unroll
+          for (int k = K0; k < K1; ++k) {                  // tap k: channels 2k, 2k+1 of the offsets, channel k of the mask
+            raw[k] = s.raw[2 * k][row];
+            raw[9 + k] = s.raw[2 * k + 1][row];
+            raw[18 + k] = s.raw[18 + k][row];
+          }
 #pragma unroll
           for (int k = K0; k < K1; ++k) {                  // straight-line code: the taps interleave
             float mk = bits_to_f32<TO>(raw[18 + k]);
@@ -531,6 +531,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
+      geo_bar_sync();                                      // everybody has read its values: the raw buffer is free
+      if (it + 1 < my_tiles) fetch_raw(it + 1);            // lands while the producers work through this tile
       if (dbg) w2 += clock64() - tg0;
     }
   } else if (warp >= V6_W_EPI) {
