@@ -157,18 +157,6 @@ template <bool RECIP> __device__ __forceinline__ float warp_coord_t(int pix, flo
   return fminf(fmaxf(i, -4.0f), ax.hi);
 }
 
-template <typename T> struct Pair;
-template <> struct Pair<float> { using type = float2; };
-template <> struct Pair<__nv_bfloat16> { using type = __nv_bfloat162; };
-template <> struct Pair<__half> { using type = __half2; };
-__device__ __forceinline__ float2 pair_to_f32(float2 v) { return v; }
-__device__ __forceinline__ float2 pair_to_f32(__nv_bfloat162 v) { return __bfloat1622float2(v); }
-__device__ __forceinline__ float2 pair_to_f32(__half2 v) { return __half22float2(v); }
-template <typename T> __device__ __forceinline__ typename Pair<T>::type pair_from_f32(float a, float b);
-template <> __device__ __forceinline__ float2 pair_from_f32<float>(float a, float b) { return make_float2(a, b); }
-template <> __device__ __forceinline__ __nv_bfloat162 pair_from_f32<__nv_bfloat16>(float a, float b) { return __floats2bfloat162_rn(a, b); }
-template <> __device__ __forceinline__ __half2 pair_from_f32<__half>(float a, float b) { return __floats2half2_rn(a, b); }
-
 constexpr int WARPF_PPT = 2;                      // pixels per thread, one block apart (x, x + 128)
 
 // Lanes are CONSECUTIVE pixels: the 2-byte gathers of a warp then span ~64 bytes + the flow's variation, i.e. one or two
