@@ -12,7 +12,10 @@ from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / "libvfi_b200.so"
+import os
+
+# VFI_B200_LIB selects another build of the same library (kernel tuning experiments); the default is the in-tree one
+LIB_PATH = Path(os.environ.get("VFI_B200_LIB") or Path(__file__).resolve().parent / "libvfi_b200.so")
 
 VFI_OK = 0
 ERR_NAMES = {1: "VFI_ERR_INVALID", 2: "VFI_ERR_UNSUPPORTED", 3: "VFI_ERR_CUDA", 4: "VFI_ERR_WORKSPACE", 5: "VFI_ERR_DEVICE"}

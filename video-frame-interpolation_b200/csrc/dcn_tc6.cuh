@@ -25,6 +25,27 @@
 //   K element e of main block t  ->  channel ((e / 32) * 32) + 8 * ((e % 16) / 4) + 4 * ((e / 16) % 2) + e % 4   (v6_k_to_tap_channel)
 //   tail block (kb = 9)          ->  e < 36: tap e / 4, channel 64 + e % 4 (lane = pixel, tcgen05.st.32x32b); rest zero; K = 48
 
+#ifndef V6_ROTATE
+#define V6_ROTATE 0          // 1: the K blocks a producer group takes rotate from tile to tile (the tail block moves around)
+#endif
+#ifndef V6_FIRST_TAPS
+#define V6_FIRST_TAPS 4      // taps published by the first geometry barrier
+#endif
+#ifndef V6_NS_PROD
+#define V6_NS_PROD 128       // sleep of the producers' per-tile waits (ns); A/B on one box: 32 -> 4.43, 64 -> 4.37, 128 -> 4.25-4.33, 256 -> 4.30 ms
+#endif
+#ifndef V6_NS_STAGE
+#define V6_NS_STAGE 64       // sleep of the producers' A-stage wait (ns)
+#endif
+#ifndef V6_NS_MMA
+#define V6_NS_MMA 20         // sleep of the MMA warp's operand wait (ns)
+#endif
+#ifndef V6_NS_HELP
+#define V6_NS_HELP 256       // sleep of the box / geometry / epilogue warps' waits (ns)
+#endif
+#ifndef V6_NS_LOAD
+#define V6_NS_LOAD 64        // sleep of the weight loader's wait (ns)
+#endif
 constexpr int V6_BOX_H = 18, V6_BOX_W = 26, V6_BOX_PX = V6_BOX_H * V6_BOX_W;      // 468 pixels
 constexpr int V6_BOX_TOP = 5, V6_BOX_LEFT = 5;                                    // box origin = tile origin - (5, 5)
 constexpr int V6_MAIN_PX = TC_CMAIN * 2, V6_TAIL_PX = TC_CTAIL * 2;               // bytes per pixel: 128 / 16
@@ -293,18 +314,18 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait_d<64, DBG>(smem_u32(&s.geo_first[gb]), tphase, w0); // this tile's geometry, taps 0..3, has been written
-      mbar_wait_d<64, DBG>(smem_u32(&s.box_full[gb]), tphase, w1);  // this tile's source box has landed in shared memory
+      mbar_wait_d<V6_NS_PROD, DBG>(smem_u32(&s.geo_first[gb]), tphase, w0); // this tile's geometry, first taps, has been written
+      mbar_wait_d<V6_NS_PROD, DBG>(smem_u32(&s.box_full[gb]), tphase, w1);  // this tile's source box has landed in shared memory
       bool all_taps = false;
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]), box_tail = smem_u32(&s.box_tail[gb][0]);
       const uint32_t bF = box_main + c_first, bS = box_main + c_second;
       const int n0 = it * V6_KBLOCKS;
-      for (int kb = group; kb < V6_KBLOCKS; kb += V6_GROUPS) {   // 10 K blocks, 5 groups: n0 % 5 == 0, every group takes two
+      for (int kb = V6_ROTATE ? (group + it) % V6_GROUPS : group; kb < V6_KBLOCKS; kb += V6_GROUPS) {   // 10 K blocks, 5 groups: two each
         const int n = n0 + kb, sa = n % V6_NA;
         const uint32_t empty_bar = smem_u32(&s.done[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
-        if (kb >= 4 && !all_taps) {                              // taps 4..8 (and the tail block, which reads all nine)
-          mbar_wait_d<64, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);
+        if (kb >= V6_FIRST_TAPS && !all_taps) {                  // the later taps (and the tail block, which reads all nine)
+          mbar_wait_d<V6_NS_PROD, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);
           all_taps = true;
         }
         if (kb < 9) {
@@ -324,7 +345,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
             const uint32_t r[16] = {X0.x, X0.y, X1.x, X1.y, X0.z, X0.w, X1.z, X1.w,
                                     Y0.x, Y0.y, Y1.x, Y1.y, Y0.z, Y0.w, Y1.z, Y1.w};
             if (h == 0) {                                        // the ring stage is needed only now, after the gathers
-              mbar_wait_d<32, DBG>(empty_bar, empty_par, w2);
+              mbar_wait_d<V6_NS_STAGE, DBG>(empty_bar, empty_par, w2);
               tc_fence_after();
             }
             tmem_st_16x256b_x4(a_taddr + ((uint32_t)(h * 16) << 16), r);
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
           r[18] = 0x3f803f80u;                               // K elements 36, 37 = 1.0: the weight image holds bias hi / lo there
 #pragma unroll
           for (int i = 19; i < 24; ++i) r[i] = 0u;
-          mbar_wait_d<32, DBG>(empty_bar, empty_par, w2);
+          mbar_wait_d<V6_NS_STAGE, DBG>(empty_bar, empty_par, w2);
           tc_fence_after();
           tmem_st_32x32b_x8(a_taddr, r);
           tmem_st_32x32b_x8(a_taddr + 8, r + 8);
@@ -374,7 +395,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
 #pragma unroll 1
       for (int kb = 0; kb < V6_KBLOCKS; ++kb, ++n) {
         const int sa = n % V6_NA, sb = n % V6_NB;
-        mbar_wait_d<20, DBG>(smem_u32(&s.full[sa]), (uint32_t)(n / V6_NA) & 1u, w2);
+        mbar_wait_d<V6_NS_MMA, DBG>(smem_u32(&s.full[sa]), (uint32_t)(n / V6_NA) & 1u, w2);
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + (uint32_t)(V6_A_COL0 + sa * 32);
         const uint64_t bdesc = umma_desc_sw128(b_smem + (uint32_t)sb * TC_B_BYTES);
@@ -402,7 +423,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         const int sb = n % V6_NB;
         if (n >= V6_NB) {                                // block n - 3 (the previous user of stage sb) has completed
           const int m = n - V6_NB;
-          mbar_wait_d<64, DBG>(smem_u32(&s.done[m % V6_NA]), (uint32_t)(m / V6_NA) & 1u, w0);
+          mbar_wait_d<V6_NS_LOAD, DBG>(smem_u32(&s.done[m % V6_NA]), (uint32_t)(m / V6_NA) & 1u, w0);
         }
         const uint32_t bar = smem_u32(&s.full[n % V6_NA]);
         if (DBG && (p.experiment & 1) && n >= V6_NB) { mbar_arrive(bar); if (++kb == V6_KBLOCKS) kb = 0; continue; }   // diagnostics: no refill
@@ -416,7 +437,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     // =========================================================================== source-box copies (one lane per box row)
     for (int it = 0; it < my_tiles; ++it) {
       const int sb = it & 1;
-      mbar_wait_d<256, DBG>(smem_u32(&s.box_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old box
+      mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.box_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old box
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
@@ -478,7 +499,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const int gb = it & 1;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       geo_bar_sync();                                      // every thread's chunks of this tile have landed
-      mbar_wait_d<256, DBG>(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old contents
+      mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old contents
       const long long tg0 = dbg ? clock64() : 0;
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
@@ -519,10 +540,10 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
             }
           }
         };
-        taps(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
+        taps(std::integral_constant<int, 0>{}, std::integral_constant<int, V6_FIRST_TAPS>{});
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
-        taps(std::integral_constant<int, 4>{}, std::integral_constant<int, 9>{});
+        taps(std::integral_constant<int, V6_FIRST_TAPS>{}, std::integral_constant<int, 9>{});
       } else {
 #pragma unroll
         for (int k = 0; k < 9; ++k) s.geo[gb][k][row] = make_uint4(V6_SAFE, 0u, 0u, 0u);
@@ -549,7 +570,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const uint32_t acc = (uint32_t)it & 1u, acc_phase = ((uint32_t)it >> 1) & 1u;
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      mbar_wait_d<256, DBG>(smem_u32(&s.acc_full[acc]), acc_phase, w1);
+      mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.acc_full[acc]), acc_phase, w1);
       const long long te0 = dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
