@@ -37,6 +37,12 @@
 #ifndef V6_NS_STAGE
 #define V6_NS_STAGE 64       // sleep of the producers' A-stage wait (ns)
 #endif
+#ifndef V6_PAIRING
+#define V6_PAIRING 0         // 0: group g takes K blocks (g, g + 5); 1: (g, 9 - g), i.e. the tail block goes to group 0
+#endif
+#ifndef V6_HALO
+#define V6_HALO 4            // halo of the staged box beyond the 3x3 reach, in pixels
+#endif
 #ifndef V6_NS_MMA
 #define V6_NS_MMA 20         // sleep of the MMA warp's operand wait (ns)
 #endif
@@ -46,8 +52,8 @@
 #ifndef V6_NS_LOAD
 #define V6_NS_LOAD 64        // sleep of the weight loader's wait (ns)
 #endif
-constexpr int V6_BOX_H = 18, V6_BOX_W = 26, V6_BOX_PX = V6_BOX_H * V6_BOX_W;      // 468 pixels
-constexpr int V6_BOX_TOP = 5, V6_BOX_LEFT = 5;                                    // box origin = tile origin - (5, 5)
+constexpr int V6_BOX_H = TC_TH + 2 + 2 * V6_HALO, V6_BOX_W = TC_TW + 2 + 2 * V6_HALO, V6_BOX_PX = V6_BOX_H * V6_BOX_W;   // 18 x 26 = 468 pixels
+constexpr int V6_BOX_TOP = 1 + V6_HALO, V6_BOX_LEFT = 1 + V6_HALO;                // box origin = tile origin - (5, 5)
 constexpr int V6_MAIN_PX = TC_CMAIN * 2, V6_TAIL_PX = TC_CTAIL * 2;               // bytes per pixel: 128 / 16
 constexpr int V6_MAIN_ROW = V6_BOX_W * V6_MAIN_PX, V6_TAIL_ROW = V6_BOX_W * V6_TAIL_PX;   // bytes per box row: 3328 / 416
 // Warp roles.  1024 threads x 64 registers is the whole register file; the fifth producer group is worth more than the
@@ -320,7 +326,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]), box_tail = smem_u32(&s.box_tail[gb][0]);
       const uint32_t bF = box_main + c_first, bS = box_main + c_second;
       const int n0 = it * V6_KBLOCKS;
-      for (int kb = V6_ROTATE ? (group + it) % V6_GROUPS : group; kb < V6_KBLOCKS; kb += V6_GROUPS) {   // 10 K blocks, 5 groups: two each
+      const int kb_first = V6_ROTATE ? (group + it) % V6_GROUPS : group;
+      for (int kb = kb_first; kb < V6_KBLOCKS; kb = V6_PAIRING ? (kb < V6_GROUPS ? V6_KBLOCKS - 1 - kb : V6_KBLOCKS) : kb + V6_GROUPS) {   // 10 K blocks, 5 groups: two each
         const int n = n0 + kb, sa = n % V6_NA;
         const uint32_t empty_bar = smem_u32(&s.done[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
