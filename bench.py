@@ -276,6 +276,26 @@ def main():
         planar_ms[name] = e0.elapsed_time(e1) / 20
         del f2, fl
 
+    # the fused warp + blend extension (no reference counterpart): two frames, two flows, one mask, bf16
+    blend_ms = None
+    try:
+        fb2 = frame2.flip(0).contiguous()
+        flb = (-flow).contiguous()
+        mm = torch.rand(B, 1, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(5)).to(dtype)
+        for _ in range(3):
+            vfi_b200.warp_blend(frame2, flow, fb2, flb, mm)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(20):
+            vfi_b200.warp_blend(frame2, flow, fb2, flb, mm)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        blend_ms = e0.elapsed_time(e1) / 20
+        del fb2, flb, mm
+    except Exception as exc:   # never let the extension break the headline line
+        print(f"bench: warp_blend timing skipped: {exc}", file=sys.stderr)
+
     # ---------------------------------------------------------------- e2e: pinned host buffers through run_host
     e2e = None
     if not args.no_e2e:
@@ -342,6 +362,12 @@ def main():
                                       "ms_per_launch": warp_ms, "achieved": warp_gbs, "frac": warp_gbs / pk["hbm"]}},
         "clocks": clocks,
     }
+    if blend_ms:
+        bl_bytes = P * (2 * 3 + 2 * 2 + 1 + 3) * 2
+        line["roofline_blend"] = {"bound": "hbm", "kernel": "warp_blend (two planar bf16 frames + two flows + mask -> blended frame, 20 launches)",
+                                  "achieved": bl_bytes / (blend_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                  "frac": bl_bytes / (blend_ms * 1e-3) / 1e9 / pk["hbm"], "ms_per_launch": blend_ms,
+                                  "algorithmic_bytes_per_launch": bl_bytes, "traffic": None, "peak_source": pk["source"]}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

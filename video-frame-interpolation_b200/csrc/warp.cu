@@ -157,6 +157,35 @@ template <bool RECIP> __device__ __forceinline__ float warp_coord_t(int pix, flo
   return fminf(fmaxf(i, -4.0f), ax.hi);
 }
 
+// Three planar channels of one output pixel (x, y) displaced by (fx, fy): the sampler of the fast kernels.
+template <typename TS, bool RECIP>
+__device__ __forceinline__ void sample3(const TS* s0, const TS* s1, const TS* s2, int pitch, int H, int W, int x, int y, float fx,
+                                        float fy, const WarpAxis& ax, const WarpAxis& ay, float (&r)[3]) {
+  const float ix = warp_coord_t<RECIP>(x, fx, ax);
+  const float iy = warp_coord_t<RECIP>(y, fy, ay);
+  const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);
+  const float x0f = (float)x0, y0f = (float)y0;
+  // The 2 x 2 patch is addressed from its clamped north-west pixel (xc, yc) in [0, W-2] x [0, H-2]: the other three
+  // corners are at compile-time byte offsets / one row pitch.  d = x0 - xc is 0 inside the frame; -1 / +1 when the
+  // true patch hangs over the left / right edge by one pixel (its inner column then sits in the other slot); anything
+  // else means no valid corner.  Zero weights stand for aten's skipped corners, and the order of the non-zero
+  // products (nw, ne, sw, se) is unchanged.
+  const int xc = min(max(x0, 0), W - 2), yc = min(max(y0, 0), H - 2);
+  const int dx = x0 - xc, dy = y0 - yc;
+  const float ax1 = ix - x0f, ax0 = (x0f + 1.0f) - ix, ay1 = iy - y0f, ay0 = (y0f + 1.0f) - iy;
+  const float wxa = dx == 0 ? ax0 : (dx == -1 ? ax1 : 0.0f), wxb = dx == 0 ? ax1 : (dx == 1 ? ax0 : 0.0f);
+  const float wya = dy == 0 ? ay0 : (dy == -1 ? ay1 : 0.0f), wyb = dy == 0 ? ay1 : (dy == 1 ? ay0 : 0.0f);
+  const float w00 = wxa * wya, w01 = wxb * wya, w10 = wxa * wyb, w11 = wxb * wyb;
+  const unsigned o = (unsigned)(yc * pitch + xc);
+  auto lerp = [&](const TS* pl) {
+    const TS* q0 = pl + o;
+    const TS* q1 = q0 + pitch;
+    const float a = ldg_f32(q0), bb = ldg_f32(q0 + 1), d = ldg_f32(q1), e = ldg_f32(q1 + 1);
+    return fmaf(e, w11, fmaf(d, w10, fmaf(bb, w01, a * w00)));
+  };
+  r[0] = lerp(s0); r[1] = lerp(s1); r[2] = lerp(s2);
+}
+
 constexpr int WARPF_PPT = 2;                      // pixels per thread, one block apart (x, x + 128)
 
 // Lanes are CONSECUTIVE pixels: the 2-byte gathers of a warp then span ~64 bytes + the flow's variation, i.e. one or two
@@ -181,32 +210,8 @@ __global__ void __launch_bounds__(WARPF_BLOCK) warp_fwd_fast_kernel(const WarpPa
   }
   float r[WARPF_PPT][3];
 #pragma unroll
-  for (int i = 0; i < WARPF_PPT; ++i) {
-    const int x = min(xb + i * WARPF_BLOCK, W - 1);
-    const float ix = warp_coord_t<RECIP>(x, fx[i], p.ax);
-    const float iy = warp_coord_t<RECIP>(y, fy[i], p.ay);
-    const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);
-    const float x0f = (float)x0, y0f = (float)y0;
-    // The 2 x 2 patch is addressed from its clamped north-west pixel (xc, yc) in [0, W-2] x [0, H-2]: the other three
-    // corners are at compile-time byte offsets / one row pitch.  d = x0 - xc is 0 inside the frame; -1 / +1 when the
-    // true patch hangs over the left / right edge by one pixel (its inner column then sits in the other slot); anything
-    // else means no valid corner.  Zero weights stand for aten's skipped corners, and the order of the non-zero
-    // products (nw, ne, sw, se) is unchanged.
-    const int xc = min(max(x0, 0), W - 2), yc = min(max(y0, 0), H - 2);
-    const int dx = x0 - xc, dy = y0 - yc;
-    const float ax1 = ix - x0f, ax0 = (x0f + 1.0f) - ix, ay1 = iy - y0f, ay0 = (y0f + 1.0f) - iy;
-    const float wxa = dx == 0 ? ax0 : (dx == -1 ? ax1 : 0.0f), wxb = dx == 0 ? ax1 : (dx == 1 ? ax0 : 0.0f);
-    const float wya = dy == 0 ? ay0 : (dy == -1 ? ay1 : 0.0f), wyb = dy == 0 ? ay1 : (dy == 1 ? ay0 : 0.0f);
-    const float w00 = wxa * wya, w01 = wxb * wya, w10 = wxa * wyb, w11 = wxb * wyb;
-    const unsigned o = (unsigned)(yc * pitch + xc);
-    auto lerp = [&](const TS* pl) {
-      const TS* q0 = pl + o;
-      const TS* q1 = q0 + pitch;
-      const float a = ldg_f32(q0), bb = ldg_f32(q0 + 1), d = ldg_f32(q1), e = ldg_f32(q1 + 1);
-      return fmaf(e, w11, fmaf(d, w10, fmaf(bb, w01, a * w00)));
-    };
-    r[i][0] = lerp(s0); r[i][1] = lerp(s1); r[i][2] = lerp(s2);
-  }
+  for (int i = 0; i < WARPF_PPT; ++i)
+    sample3<TS, RECIP>(s0, s1, s2, pitch, H, W, min(xb + i * WARPF_BLOCK, W - 1), y, fx[i], fy[i], p.ax, p.ay, r[i]);
 #pragma unroll
   for (int i = 0; i < WARPF_PPT; ++i) {
     const int x = xb + i * WARPF_BLOCK;
@@ -260,6 +265,30 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const BlendParams q) {
     float wb = sample<TS>(sb + c * q.b_sc, cb);
     out[c * p.o_sc] = from_f32<TS>(__fadd_rn(__fmul_rn(m, wa), __fmul_rn(m1, wb)));
   }
+}
+
+// Fast path of the blend (three planar channels, unit pixel strides): the two warps share the fast kernel's sampler, one
+// thread per pixel, lanes consecutive.  out = m * warp(a, fa) + (1 - m) * warp(b, fb), rounded as the composition is.
+template <typename TS, typename TF, bool RECIP>
+__global__ void __launch_bounds__(WARPF_BLOCK) warp_blend_fast_kernel(const BlendParams q) {
+  const WarpParams& p = q.a;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = blockIdx.x * WARPF_BLOCK + threadIdx.x;
+  if (x >= p.W) return;
+  const TF* fa = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + (long long)y * p.f_sh + x;
+  const TF* fb = reinterpret_cast<const TF*>(q.flow_b) + b * q.g_sn + (long long)y * q.g_sh + x;
+  const float fax = to_f32<TF>(__ldcs(fa)), fay = to_f32<TF>(__ldcs(fa + p.f_sc));
+  const float fbx = to_f32<TF>(__ldcs(fb)), fby = to_f32<TF>(__ldcs(fb + q.g_sc));
+  const float m = to_f32<TS>(__ldcs(reinterpret_cast<const TS*>(q.m) + b * q.m_sn + (long long)y * q.m_sh + x));
+  const TS* a0 = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
+  const TS* b0 = reinterpret_cast<const TS*>(q.src_b) + b * q.b_sn;
+  float ra[3], rb[3];
+  sample3<TS, RECIP>(a0, a0 + p.s_sc, a0 + 2 * p.s_sc, (int)p.s_sh, p.H, p.W, x, y, fax, fay, p.ax, p.ay, ra);
+  sample3<TS, RECIP>(b0, b0 + q.b_sc, b0 + 2 * q.b_sc, (int)q.b_sh, p.H, p.W, x, y, fbx, fby, p.ax, p.ay, rb);
+  const float m1 = 1.0f - m;
+  TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) __stcs(out + c * p.o_sc, from_f32<TS>(__fadd_rn(__fmul_rn(m, ra[c]), __fmul_rn(m1, rb[c]))));
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -426,6 +455,24 @@ extern "C" int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flo
   long long total = (long long)out->n * out->h * out->w;
   int blocks = ceil_div(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  auto planar3 = [](const vfi_tensor* t) { return t->c == 3 && t->sw == 1 && t->sh >= 0 && t->sc >= 0 && t->sn >= 0; };
+  const bool fast = planar3(src_a) && planar3(src_b) && planar3(out) && flow_a->sw == 1 && flow_b->sw == 1 && m->sw == 1 &&
+                    out->w >= 2 && out->h >= 2 && out->h <= 65535 && out->n <= 65535;
+  if (fast) {
+    dim3 grid(ceil_div(out->w, WARPF_BLOCK), (unsigned)out->h, (unsigned)out->n);
+    const bool recip = (flags & VFI_WARP_DIV_RECIPROCAL) != 0;
+    VFI_DISPATCH(out->dtype, TS, {
+      if (flow_a->dtype == VFI_F32) {
+        if (recip) warp_blend_fast_kernel<TS, float, true><<<grid, WARPF_BLOCK, 0, st>>>(q);
+        else warp_blend_fast_kernel<TS, float, false><<<grid, WARPF_BLOCK, 0, st>>>(q);
+      } else {
+        if (recip) warp_blend_fast_kernel<TS, TS, true><<<grid, WARPF_BLOCK, 0, st>>>(q);
+        else warp_blend_fast_kernel<TS, TS, false><<<grid, WARPF_BLOCK, 0, st>>>(q);
+      }
+    });
+    VFI_LAUNCH_CHECK("warp_blend_fast_kernel");
+    return VFI_OK;
+  }
   VFI_DISPATCH(out->dtype, TS, {
     if (flow_a->dtype == VFI_F32) warp_blend_kernel<TS, float><<<blocks, 256, 0, st>>>(q);
     else warp_blend_kernel<TS, TS><<<blocks, 256, 0, st>>>(q);
