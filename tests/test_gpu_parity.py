@@ -422,6 +422,34 @@ torch.save(y.cpu(), sys.argv[1])
     assert float((outs[0] != outs[1]).float().mean()) <= 0.05
 
 
+@pytest.mark.parametrize("B,H,W,sigma,gdt", [(1, 8, 16, 1.5, torch.bfloat16), (2, 24, 40, 1.5, torch.bfloat16),
+                                            (1, 40, 64, 6.0, torch.float32), (3, 64, 96, 0.0, torch.bfloat16)])
+def test_dcn_weight_grad_tensor_core(B, H, W, sigma, gdt):
+    """grad_weight / grad_bias as a pixel-reduction GEMM on tcgen05 (A = grad_out^T in tensor memory, B = the producers'
+    sample tile read MN-major, accumulators persistent in TMEM over the CTA's tiles): against the fp32 oracle on the
+    bf16-rounded operands.  24 x 40 has partial tiles; sigma = 6 exercises the out-of-box global path; B = 3 at 64 x 96
+    gives every CTA several tiles to accumulate over."""
+    from vfi_b200 import ops
+
+    z = rand_dcn(B, 67, 67, H, W, sigma, seed=91 + H)
+    xr, offr, mr = bf16_round(z["x"]), bf16_round(z["offset"]), bf16_round(z["mask"])
+    g_in = torch.from_numpy(z["grad_out"]).to(gdt)
+    ref = oracle.dcn_bwd(bf16_round(z["grad_out"]), xr, offr, mr, z["weight"])
+    gw, gb = ops.dcn_weight_grad_tc(g_in.to(DEV), cu(z["x"], torch.bfloat16), cu(z["offset"], torch.bfloat16),
+                                    cu(z["mask"], torch.bfloat16), 67)
+    assert relerr(gw, ref[3]) <= 1e-2
+    assert relerr(gb, ref[4]) <= 1e-2
+    # autograd: a tensor-core forward uses the tensor-core weight gradient
+    x = cu(z["x"], torch.bfloat16).requires_grad_(True)
+    w = cu(z["weight"], torch.bfloat16).requires_grad_(True)
+    b = cu(z["bias"], torch.bfloat16).requires_grad_(True)
+    out = vfi_b200.deform_conv2d(x, cu(z["offset"], torch.bfloat16), w, b, stride=1, padding=1, dilation=1,
+                                 mask=cu(z["mask"], torch.bfloat16), math="bf16_tc")
+    out.backward(cu(z["grad_out"], torch.bfloat16))
+    ref2 = oracle.dcn_bwd(bf16_round(z["grad_out"]), xr, offr, mr, bf16_round(z["weight"]))
+    assert relerr(w.grad, ref2[3]) <= 2e-2 and relerr(b.grad, ref2[4]) <= 2e-2 and relerr(x.grad, ref2[0]) <= 2e-2
+
+
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
     """Full 1080p frame: tcgen05 result against this library's fp32 parity kernel on the same bf16-rounded inputs."""
     g = torch.Generator(device=DEV).manual_seed(41)

@@ -29,6 +29,8 @@ int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, i
                        void* packed, float* bias_out, cudaStream_t st, int variant);
 int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st);
 int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel);
+int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
+                      long long O, float* gw, float* gb, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 unsigned long long* dcn_tc_debug_buffer();
 int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
@@ -108,6 +110,12 @@ extern "C" int vfi_dcn_fwd(const vfi_tensor* x, const vfi_tensor* offset, const 
 
 extern "C" int vfi_selftest_umma(const void* a_bf16, const void* b_bf16, float* d, int32_t K, vfi_stream_t stream) {
   return umma_selftest(a_bf16, b_bf16, d, K, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset,
+                                     const vfi_tensor* mask, int64_t O, float* grad_weight, float* grad_bias, void* workspace,
+                                     size_t workspace_bytes, vfi_stream_t stream) {
+  return dcn_tc_bwd_weight(grad_out, x, offset, mask, O, grad_weight, grad_bias, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int vfi_dcn_k_order(int32_t variant, int32_t kb, int32_t kk, int32_t* tap, int32_t* channel) {

@@ -649,6 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
 }
 
 #include "dcn_tc6.cuh"   // v6: TMEM-resident A operand, source box staged in shared memory
+#include "dcn_tc6_wgrad.cuh"   // weight / bias gradient on tcgen05 (pixel-reduction GEMM, accumulators persistent in TMEM)
 
 // ------------------------------------------------------------------------------------------------ UMMA self test
 // D[128, 80] = A[128, K] * Bm[80, K]^T with A, Bm row-major bf16 in global memory, K a multiple of 64.  Uses exactly
@@ -938,6 +939,77 @@ int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel) {
               "vfi_dcn_k_order: variant 4|6, kb in [0,11), kk in [0,64)");
   if (variant == 6) v6_k_to_tap_channel(kb, kk, *tap, *channel);
   else tc_k_to_tap_channel(kb, kk, *tap, *channel);
+  return VFI_OK;
+}
+
+// grad_weight / grad_bias on the tensor cores.  x: any [B,C,H,W] tensor (packed to planes in the workspace) -- the same
+// operands the forward saw; grad_out [B,O,H,W] bf16 or f32 with unit pixel stride.  Accumulates into gw / gb (fp32).
+int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
+                      long long O, float* gw, float* gb, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const char* who = "vfi_dcn_bwd_weight_tc";
+  VFI_REQUIRE(grad_out && x && offset && mask, VFI_ERR_INVALID, "%s: null tensor descriptor", who);
+  const long long C = x->c;
+  VFI_REQUIRE(C > 0 && C <= TC_CMAIN + 4 && O > 0 && O <= TC_M, VFI_ERR_UNSUPPORTED, "%s: supports C <= %d, O <= %d", who,
+              TC_CMAIN + 4, TC_M);
+  VFI_REQUIRE(offset->n == x->n && offset->c == 18 && offset->h == x->h && offset->w == x->w && mask->n == x->n && mask->c == 9 &&
+                  mask->h == x->h && mask->w == x->w && grad_out->n == x->n && grad_out->c == O && grad_out->h == x->h &&
+                  grad_out->w == x->w, VFI_ERR_INVALID, "%s: shape mismatch", who);
+  const long long P = (long long)x->n * x->h * x->w;
+  if (P == 0 || (!gw && !gb)) return VFI_OK;
+  auto bulk_ok = [](const vfi_tensor* t, int es) {
+    const int a = 16 / es;
+    return t->sw == 1 && t->w % a == 0 && t->sh % a == 0 && t->sc % a == 0 && t->sn % a == 0 && aligned(t->data, 16) && t->sh >= 0 &&
+           t->sc >= 0 && t->sn >= 0;
+  };
+  VFI_REQUIRE((offset->dtype == VFI_BF16 || offset->dtype == VFI_F16) && offset->dtype == mask->dtype && bulk_ok(offset, 2) &&
+                  bulk_ok(mask, 2), VFI_ERR_UNSUPPORTED,
+              "%s: offset / mask must be 16-bit tensors with unit pixel stride and 16-byte aligned rows (W %% 8 == 0)", who);
+  VFI_REQUIRE((grad_out->dtype == VFI_BF16 && bulk_ok(grad_out, 2)) || (grad_out->dtype == VFI_F32 && grad_out->sw == 1),
+              VFI_ERR_UNSUPPORTED, "%s: grad_out must be bf16 (16-byte aligned rows) or f32, unit pixel stride", who);
+  VFI_REQUIRE(x->w % 8 == 0, VFI_ERR_UNSUPPORTED, "%s: W must be a multiple of 8", who);
+  VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "%s: more than 2^30 pixels per call", who);
+  const size_t need = dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
+              "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = dcn_tc_pack_input(x, ws + ws_main_off(), ws + ws_tail_off(P), st);
+  if (rc) return rc;
+  WgParams q;
+  TcParams& p = q.t;
+  p.x_main = ws + ws_main_off(); p.x_tail = ws + ws_tail_off(P);
+  p.main_stride = TC_CMAIN * 2; p.tail_stride = TC_CTAIL * 2;
+  p.offset = offset->data; p.mask = mask->data; p.fused27 = 0;
+  p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
+  p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
+  p.wpacked = nullptr; p.bias = nullptr; p.out = nullptr; p.out_tail = nullptr;
+  p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0;
+  p.B = (int)x->n; p.H = (int)x->h; p.W = (int)x->w; p.O = (int)O;
+  p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
+  p.num_tiles = p.B * p.tiles_x * p.tiles_y;
+  p.experiment = 0; p.debug = nullptr;
+  q.gout = grad_out->data; q.g_sn = grad_out->sn; q.g_sc = grad_out->sc; q.g_sh = grad_out->sh;
+  q.gw = gw; q.gb = gb; q.C = (int)C;
+  int dev = 0, sms = 148;
+  VFI_CUDA(cudaGetDevice(&dev));
+  VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const size_t smem = sizeof(WgSmem) + 1024;
+  for (int pass = 0; pass < 2; ++pass) {
+    q.pass = pass;
+#define VFI_WG_LAUNCH(TO, TG)                                                                         \
+  do {                                                                                                \
+    auto kern = dcn_tc6_wgrad_kernel<TO, TG, false>;                                                  \
+    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, V6_THREADS, smem, st>>>(q);                                                          \
+  } while (0)
+    if (offset->dtype == VFI_BF16) {
+      if (grad_out->dtype == VFI_BF16) VFI_WG_LAUNCH(__nv_bfloat16, __nv_bfloat16); else VFI_WG_LAUNCH(__nv_bfloat16, float);
+    } else {
+      if (grad_out->dtype == VFI_BF16) VFI_WG_LAUNCH(__half, __nv_bfloat16); else VFI_WG_LAUNCH(__half, float);
+    }
+#undef VFI_WG_LAUNCH
+    VFI_LAUNCH_CHECK("dcn_tc6_wgrad_kernel");
+  }
   return VFI_OK;
 }
 

@@ -263,6 +263,139 @@ __device__ __forceinline__ uint2 v6_sample_tail(const uint4& e, uint32_t box_tai
   return make_uint2(r.x, r.y);
 }
 
+// Role: source-box copies (one warp, one lane per box row).  Shared by the forward and the weight-gradient kernel; `S` has
+// box_main / box_tail / box_full / box_empty.
+template <bool DBG, class S>
+__device__ __forceinline__ void v6_role_box(S& s, const TcParams& p, int lane, int my_tiles, int tile0, int tile_step, long long& w0) {
+  for (int it = 0; it < my_tiles; ++it) {
+    const int sb = it & 1;
+    mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.box_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old box
+    int b, ty0, tx0;
+    tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+    const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
+    const int ya = max(by0, 0), yb = min(by0 + V6_BOX_H, p.H), xa = max(bx0, 0), xb = min(bx0 + V6_BOX_W, p.W);
+    const uint32_t ncol = (uint32_t)(xb - xa), nrow = (uint32_t)(yb - ya);
+    const uint32_t bar = smem_u32(&s.box_full[sb]);
+    const uint32_t dst_main = smem_u32(&s.box_main[sb][0]), dst_tail = smem_u32(&s.box_tail[sb][0]);
+    if (nrow * ncol != (uint32_t)V6_BOX_PX) {
+      // border tile: the part of the box outside the image is zero padding (what torchvision's skipped corners amount to)
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = lane; i < V6_BOX_PX; i += 32) {
+        const int yy = by0 + i / V6_BOX_W, xx = bx0 + i % V6_BOX_W;
+        if (yy < ya || yy >= yb || xx < xa || xx >= xb) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sts16(dst_main + (uint32_t)i * V6_MAIN_PX + c * 16, z);
+          sts16(dst_tail + (uint32_t)i * V6_TAIL_PX, z);
+        }
+      }
+    }
+    __syncwarp();                                      // the zero padding is ordered before the arrive below (release)
+    if (lane == 0) mbar_arrive_expect_tx(bar, nrow * ncol * (V6_MAIN_PX + V6_TAIL_PX));
+    __syncwarp();
+    const int y = by0 + lane;
+    if (lane < V6_BOX_H && y >= ya && y < yb) {
+      const size_t gpix = (size_t)(b * p.H + y) * p.W + xa;
+      const uint32_t bpix = (uint32_t)(lane * V6_BOX_W + (xa - bx0));
+      bulk_g2s(dst_main + bpix * V6_MAIN_PX, p.x_main + gpix * V6_MAIN_PX, ncol * V6_MAIN_PX, bar);
+      bulk_g2s(dst_tail + bpix * V6_TAIL_PX, p.x_tail + gpix * V6_TAIL_PX, ncol * V6_TAIL_PX, bar);
+    }
+    __syncwarp();
+  }
+}
+
+// Role: tap geometry (four warps; `row` = tile row of this thread).  Shared by the forward and the weight-gradient kernel;
+// `S` has raw / geo / geo_first / geo_full / geo_empty.
+template <typename TO, bool FUSED27, bool DBG, class S>
+__device__ __forceinline__ void v6_role_geometry(S& s, const TcParams& p, int row, int lane, int my_tiles, int tile0, int tile_step,
+                                                 long long& w0, long long& w2) {
+  constexpr bool dbg = DBG;
+  // =========================================================================== tap geometry (4 warps)
+  // Thread = tile row, nine taps.  Runs one tile ahead of the producers (double-buffered entries); the offset / mask
+  // values arrive in shared memory by cp.async a further tile ahead, so no DRAM round trip sits in this warp.
+  // Offsets and masks of a tile: 27 channels x 8 tile rows x 16 pixels = 432 chunks of 16 bytes of the NCHW tensor,
+  // brought into raw[channel][tile row * 16 + x] by cp.async (four per thread, no registers held) one tile ahead.
+  auto fetch_raw = [&](int it) {
+    int b, ty0, tx0;
+    tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+    const int rows = min(TC_TH, p.H - ty0), cols = min(TC_TW, p.W - tx0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = row + 128 * j, c = i >> 4, r = (i >> 1) & 7, x8 = (i & 1) * 8;
+      if (i < 27 * 16 && r < rows && x8 < cols) {
+        const TO* src;
+        if (FUSED27) src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + (c < 18 ? (c < 9 ? c : c + 9) : c - 9) * p.f_sc;
+        else if (c < 18) src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + c * p.f_sc;
+        else src = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + (c - 18) * p.m_sc;
+        src += (long long)(ty0 + r) * (c < 18 || FUSED27 ? p.f_sh : p.m_sh) + tx0 + x8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.raw[c][r * TC_TW + x8])), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (my_tiles > 0) fetch_raw(0);
+  for (int it = 0; it < my_tiles; ++it) {
+    const int gb = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    geo_bar_sync();                                      // every thread's chunks of this tile have landed
+    mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old contents
+    const long long tg0 = dbg ? clock64() : 0;
+    int b, ty0, tx0;
+    tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
+    const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
+    const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
+    if (y < p.H && x < p.W) {
+      const int base = b * p.H * p.W;
+      const float fy0 = (float)(y - 1), fx0 = (float)(x - 1);
+      // taps 0..3 first: they are all the first K blocks of the tile need, so the producers start on them while
+      // taps 4..8 are still being computed (the geometry of a tile cannot start before the previous tile but one is done)
+      auto taps = [&](auto k0_tag, auto k1_tag) {
+        constexpr int K0 = decltype(k0_tag)::value, K1 = decltype(k1_tag)::value;
+        uint32_t slow = 0;                               // taps the box does not serve (rare): patched below
+        uint32_t raw[27];                                // [dy x9 | dx x9 | mask x9] as raw bits; only [K0, K1) is live
+#pragma unroll
+        for (int k = K0; k < K1; ++k) {                  // tap k: channels 2k, 2k+1 of the offsets, channel k of the mask
+          raw[k] = s.raw[2 * k][row];
+          raw[9 + k] = s.raw[2 * k + 1][row];
+          raw[18 + k] = s.raw[18 + k][row];
+        }
+#pragma unroll
+        for (int k = K0; k < K1; ++k) {                  // straight-line code: the taps interleave
+          float mk = bits_to_f32<TO>(raw[18 + k]);
+          // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
+          if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
+          uint4 e;
+          if (!v6_geo_entry(by0, bx0, fy0 + (float)(k / 3), fx0 + (float)(k % 3), bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk, e))
+            slow |= 1u << k;
+          s.geo[gb][k][row] = e;
+        }
+        if (slow) {
+#pragma unroll
+          for (int k = K0; k < K1; ++k) {                // static indices keep `raw` in registers
+            if (!(slow & (1u << k))) continue;
+            float mk = bits_to_f32<TO>(raw[18 + k]);
+            if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
+            s.geo[gb][k][row] = v6_geo_entry_slow(p.H, p.W, base, y, x, k, bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk);
+          }
+        }
+      };
+      taps(std::integral_constant<int, 0>{}, std::integral_constant<int, V6_FIRST_TAPS>{});
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
+      taps(std::integral_constant<int, V6_FIRST_TAPS>{}, std::integral_constant<int, 9>{});
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s.geo[gb][k][row] = make_uint4(V6_SAFE, 0u, 0u, 0u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
+    geo_bar_sync();                                      // everybody has read its values: the raw buffer is free
+    if (it + 1 < my_tiles) fetch_raw(it + 1);            // lands while the producers work through this tile
+    if (dbg) w2 += clock64() - tg0;
+  }
+}
+
 // TO: 16-bit dtype of the offset / mask tensors; TOUT: output dtype; FUSED27: offsets and mask come from the 27-channel
 // offset_conv output; PLANES: output as bf16 planes (else any strided tensor); DBG: per-role cycle counters.
 template <typename TO, typename TOUT, bool FUSED27, bool PLANES, bool DBG>
@@ -442,127 +575,10 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     __syncwarp();
   } else if (warp == V6_W_BOX) {
     // =========================================================================== source-box copies (one lane per box row)
-    for (int it = 0; it < my_tiles; ++it) {
-      const int sb = it & 1;
-      mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.box_empty[sb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old box
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
-      const int ya = max(by0, 0), yb = min(by0 + V6_BOX_H, p.H), xa = max(bx0, 0), xb = min(bx0 + V6_BOX_W, p.W);
-      const uint32_t ncol = (uint32_t)(xb - xa), nrow = (uint32_t)(yb - ya);
-      const uint32_t bar = smem_u32(&s.box_full[sb]);
-      const uint32_t dst_main = smem_u32(&s.box_main[sb][0]), dst_tail = smem_u32(&s.box_tail[sb][0]);
-      if (nrow * ncol != (uint32_t)V6_BOX_PX) {
-        // border tile: the part of the box outside the image is zero padding (what torchvision's skipped corners amount to)
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = lane; i < V6_BOX_PX; i += 32) {
-          const int yy = by0 + i / V6_BOX_W, xx = bx0 + i % V6_BOX_W;
-          if (yy < ya || yy >= yb || xx < xa || xx >= xb) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) sts16(dst_main + (uint32_t)i * V6_MAIN_PX + c * 16, z);
-            sts16(dst_tail + (uint32_t)i * V6_TAIL_PX, z);
-          }
-        }
-      }
-      __syncwarp();                                      // the zero padding is ordered before the arrive below (release)
-      if (lane == 0) mbar_arrive_expect_tx(bar, nrow * ncol * (V6_MAIN_PX + V6_TAIL_PX));
-      __syncwarp();
-      const int y = by0 + lane;
-      if (lane < V6_BOX_H && y >= ya && y < yb) {
-        const size_t gpix = (size_t)(b * p.H + y) * p.W + xa;
-        const uint32_t bpix = (uint32_t)(lane * V6_BOX_W + (xa - bx0));
-        bulk_g2s(dst_main + bpix * V6_MAIN_PX, p.x_main + gpix * V6_MAIN_PX, ncol * V6_MAIN_PX, bar);
-        bulk_g2s(dst_tail + bpix * V6_TAIL_PX, p.x_tail + gpix * V6_TAIL_PX, ncol * V6_TAIL_PX, bar);
-      }
-      __syncwarp();
-    }
+    v6_role_box<DBG>(s, p, lane, my_tiles, tile0, tile_step, w0);
   } else if (warp >= V6_W_GEO) {
     // =========================================================================== tap geometry (4 warps)
-    // Thread = tile row, nine taps.  Runs one tile ahead of the producers (double-buffered entries); the offset / mask
-    // values arrive in shared memory by cp.async a further tile ahead, so no DRAM round trip sits in this warp.
-    const int row = (warp - V6_W_GEO) * 32 + lane;
-    // Offsets and masks of a tile: 27 channels x 8 tile rows x 16 pixels = 432 chunks of 16 bytes of the NCHW tensor,
-    // brought into raw[channel][tile row * 16 + x] by cp.async (four per thread, no registers held) one tile ahead.
-    auto fetch_raw = [&](int it) {
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      const int rows = min(TC_TH, p.H - ty0), cols = min(TC_TW, p.W - tx0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = row + 128 * j, c = i >> 4, r = (i >> 1) & 7, x8 = (i & 1) * 8;
-        if (i < 27 * 16 && r < rows && x8 < cols) {
-          const TO* src;
-          if (FUSED27) src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + (c < 18 ? (c < 9 ? c : c + 9) : c - 9) * p.f_sc;
-          else if (c < 18) src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + c * p.f_sc;
-          else src = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + (c - 18) * p.m_sc;
-          src += (long long)(ty0 + r) * (c < 18 || FUSED27 ? p.f_sh : p.m_sh) + tx0 + x8;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.raw[c][r * TC_TW + x8])), "l"(src) : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (my_tiles > 0) fetch_raw(0);
-    for (int it = 0; it < my_tiles; ++it) {
-      const int gb = it & 1;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      geo_bar_sync();                                      // every thread's chunks of this tile have landed
-      mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u, w0);   // producers are done with the old contents
-      const long long tg0 = dbg ? clock64() : 0;
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
-      const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
-      if (y < p.H && x < p.W) {
-        const int base = b * p.H * p.W;
-        const float fy0 = (float)(y - 1), fx0 = (float)(x - 1);
-        // taps 0..3 first: they are all the first K blocks of the tile need, so the producers start on them while
-        // taps 4..8 are still being computed (the geometry of a tile cannot start before the previous tile but one is done)
-        auto taps = [&](auto k0_tag, auto k1_tag) {
-          constexpr int K0 = decltype(k0_tag)::value, K1 = decltype(k1_tag)::value;
-          uint32_t slow = 0;                               // taps the box does not serve (rare): patched below
-          uint32_t raw[27];                                // [dy x9 | dx x9 | mask x9] as raw bits; only [K0, K1) is live
-#pragma unroll
-          for (int k = K0; k < K1; ++k) {                  // tap k: channels 2k, 2k+1 of the offsets, channel k of the mask
-            raw[k] = s.raw[2 * k][row];
-            raw[9 + k] = s.raw[2 * k + 1][row];
-            raw[18 + k] = s.raw[18 + k][row];
-          }
-#pragma unroll
-          for (int k = K0; k < K1; ++k) {                  // straight-line code: the taps interleave
-            float mk = bits_to_f32<TO>(raw[18 + k]);
-            // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
-            if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
-            uint4 e;
-            if (!v6_geo_entry(by0, bx0, fy0 + (float)(k / 3), fx0 + (float)(k % 3), bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk, e))
-              slow |= 1u << k;
-            s.geo[gb][k][row] = e;
-          }
-          if (slow) {
-#pragma unroll
-            for (int k = K0; k < K1; ++k) {                // static indices keep `raw` in registers
-              if (!(slow & (1u << k))) continue;
-              float mk = bits_to_f32<TO>(raw[18 + k]);
-              if (FUSED27) mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-mk))));
-              s.geo[gb][k][row] = v6_geo_entry_slow(p.H, p.W, base, y, x, k, bits_to_f32<TO>(raw[k]), bits_to_f32<TO>(raw[9 + k]), mk);
-            }
-          }
-        };
-        taps(std::integral_constant<int, 0>{}, std::integral_constant<int, V6_FIRST_TAPS>{});
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
-        taps(std::integral_constant<int, V6_FIRST_TAPS>{}, std::integral_constant<int, 9>{});
-      } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) s.geo[gb][k][row] = make_uint4(V6_SAFE, 0u, 0u, 0u);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
-      geo_bar_sync();                                      // everybody has read its values: the raw buffer is free
-      if (it + 1 < my_tiles) fetch_raw(it + 1);            // lands while the producers work through this tile
-      if (dbg) w2 += clock64() - tg0;
-    }
+    v6_role_geometry<TO, FUSED27, DBG>(s, p, (warp - V6_W_GEO) * 32 + lane, lane, my_tiles, tile0, tile_step, w0, w2);
   } else if (warp >= V6_W_EPI) {
     // =========================================================================== epilogue (4 warps)
     const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp

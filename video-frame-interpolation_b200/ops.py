@@ -163,6 +163,21 @@ def selftest_umma_ts(a: torch.Tensor, b: torch.Tensor):
     return d, raw
 
 
+def dcn_weight_grad_tc(grad_out: torch.Tensor, x: torch.Tensor, offset: torch.Tensor, mask: torch.Tensor, O: int):
+    """grad_weight [O,C,3,3] and grad_bias [O] (fp32) of the DCNv2 layer on the tensor cores (vfi_dcn_bwd_weight_tc):
+    bf16 operands, fp32 accumulation in tensor memory.  Raises NotImplementedError for shapes / dtypes it does not take."""
+    dev = require_cuda(grad_out, x, offset, mask)
+    B, C, H, W = x.shape
+    lib = _lib.load()
+    gw = torch.zeros((O, C, 3, 3), dtype=torch.float32, device=dev)
+    gb = torch.zeros((O,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, _lib.MATH_BF16_TC)))
+    with torch.cuda.device(dev):
+        check(lib.vfi_dcn_bwd_weight_tc(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O, gw.data_ptr(),
+                                        gb.data_ptr(), ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_bwd_weight_tc")
+    return gw, gb
+
+
 def dcn_workspace_bytes(B: int, C: int, O: int, H: int, W: int, math: str = "auto") -> int:
     return int(_lib.load().vfi_dcn_workspace_bytes(B, C, O, H, W, _MATH[math]))
 
@@ -195,6 +210,7 @@ class _DcnFn(torch.autograd.Function):
                                   dtype_code(bias_c.dtype) if bias_c is not None else 0, ref(desc(out)), O, math,
                                   ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_fwd")
         ctx.save_for_backward(x, offset, mask, weight_c)
+        ctx.tc = tc
         ctx.has_bias = bias is not None
         ctx.bias_dtype = None if bias is None else bias.dtype
         return out
@@ -224,7 +240,19 @@ class _DcnFn(torch.autograd.Function):
                                            stream_handle(dev)), "vfi_dcn_bwd_data")
             gw = torch.zeros(weight.shape, **f32) if need_w else None
             gb = torch.zeros((O,), **f32) if need_b else None
-            if need_w or need_b:
+            done = False
+            if (need_w or need_b) and ctx.tc:
+                # tensor-core forward -> tensor-core weight gradient (bf16 operands, fp32 accumulation); shapes it does not
+                # take (VFI_ERR_UNSUPPORTED) use the fp32 CUDA-core kernel below
+                ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, _lib.MATH_BF16_TC)))
+                rc = lib.vfi_dcn_bwd_weight_tc(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O,
+                                               gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
+                                               ws.data_ptr(), ws.numel(), stream_handle(dev))
+                if rc == 0:
+                    done = True
+                elif rc != 2:
+                    check(rc, "vfi_dcn_bwd_weight_tc")
+            if (need_w or need_b) and not done:
                 check(lib.vfi_dcn_bwd_weight(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O,
                                              gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
                                              stream_handle(dev)), "vfi_dcn_bwd_weight")
