@@ -31,8 +31,12 @@ class Block(torch.nn.Module):
         self.dcn = dcn
 
     def forward(self, x):
-        o1, m, o2 = self.offset_conv(x).chunk(3, dim=1)
-        return self.dcn(x, torch.cat((o1, o2), 1), self.weight, self.bias, stride=1, padding=1, dilation=1, mask=torch.sigmoid(m))
+        # fp32 master parameters; in the bf16 mode they are cast per step and autograd returns fp32 gradients to them
+        dt = x.dtype
+        c27 = torch.nn.functional.conv2d(x, self.offset_conv.weight.to(dt), self.offset_conv.bias.to(dt), padding=1)
+        o1, m, o2 = c27.chunk(3, dim=1)
+        return self.dcn(x, torch.cat((o1, o2), 1), self.weight.to(dt), self.bias.to(dt), stride=1, padding=1, dilation=1,
+                        mask=torch.sigmoid(m))
 
 
 def main():
@@ -40,6 +44,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--stock", action="store_true")
+    ap.add_argument("--math", default="fp32", choices=["fp32", "bf16_tc"],
+                    help="fp32: parity kernels; bf16_tc: bf16 tensors, tcgen05 forward + weight gradient (bf16 tolerances)")
     args = ap.parse_args()
     topo = shard.init_distributed()
     dev = torch.device("cuda", topo.local_rank)
@@ -57,13 +63,16 @@ def main():
             g = torch.stack((2 * g[:, 0] / (W - 1) - 1, 2 * g[:, 1] / (H - 1) - 1), -1)
             return torch.nn.functional.grid_sample(f, g, mode="bilinear", padding_mode="zeros", align_corners=True)
     else:
-        dcn, warp = vfi_b200.deform_conv2d, vfi_b200.warp
+        import functools
+
+        dcn, warp = functools.partial(vfi_b200.deform_conv2d, math=args.math), vfi_b200.warp
+    dt = torch.bfloat16 if (args.math == "bf16_tc" and not args.stock) else torch.float32
     blocks = torch.nn.ModuleList([Block(dcn) for _ in range(3)]).to(dev)
     bucket = shard.GradBucket(blocks.parameters())
     g = torch.Generator(device=dev).manual_seed(100 + topo.rank)
-    frame2 = torch.randn(B, 3, H, W, device=dev, generator=g)
-    feat = torch.randn(B, 64, H, W, device=dev, generator=g)
-    flow = (2.0 * torch.randn(B, 2, H, W, device=dev, generator=g)).requires_grad_(True)
+    frame2 = torch.randn(B, 3, H, W, device=dev, generator=g).to(dt)
+    feat = torch.randn(B, 64, H, W, device=dev, generator=g).to(dt)
+    flow = (2.0 * torch.randn(B, 2, H, W, device=dev, generator=g)).to(dt).requires_grad_(True)
 
     def step():
         bucket.zero()
@@ -71,7 +80,7 @@ def main():
         x = torch.cat((feat, warp(frame2, flow)), 1)
         for blk in blocks:
             x = blk(x)
-        x.square().mean().backward()
+        x.float().square().mean().backward()
         bucket.attach()
         bucket.allreduce_mean()
 
@@ -94,7 +103,7 @@ def main():
     if topo.is_root:
         print(json.dumps({"workload": "cfg3: training step, crop 256x256, global batch 16, fp32: warp + 3 x (offset_conv, DCNv2) "
                           "forward + backward, flat-bucket gradient all-reduce", "impl": "stock torch/torchvision CUDA" if args.stock
-                          else "vfi_b200 (fp32 parity kernels)", "n_gpus": topo.world, "ms_per_step": ms,
+                          else f"vfi_b200 ({args.math})", "n_gpus": topo.world, "ms_per_step": ms,
                           "samples_per_s": 16 / (ms * 1e-3), "grad_flow_finite": bool(torch.isfinite(flow.grad).all())}))
     if topo.world > 1:
         dist.destroy_process_group()

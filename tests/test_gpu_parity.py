@@ -423,12 +423,13 @@ torch.save(y.cpu(), sys.argv[1])
 
 
 @pytest.mark.parametrize("B,H,W,sigma,gdt", [(1, 8, 16, 1.5, torch.bfloat16), (2, 24, 40, 1.5, torch.bfloat16),
-                                            (1, 40, 64, 6.0, torch.float32), (3, 64, 96, 0.0, torch.bfloat16)])
+                                            (1, 40, 64, 6.0, torch.float32), (3, 64, 96, 0.0, torch.bfloat16),
+                                            (2, 256, 256, 1.5, torch.bfloat16)])
 def test_dcn_weight_grad_tensor_core(B, H, W, sigma, gdt):
     """grad_weight / grad_bias as a pixel-reduction GEMM on tcgen05 (A = grad_out^T in tensor memory, B = the producers'
     sample tile read MN-major, accumulators persistent in TMEM over the CTA's tiles): against the fp32 oracle on the
-    bf16-rounded operands.  24 x 40 has partial tiles; sigma = 6 exercises the out-of-box global path; B = 3 at 64 x 96
-    gives every CTA several tiles to accumulate over."""
+    bf16-rounded operands.  24 x 40 has partial tiles; sigma = 6 exercises the out-of-box global path; 2 x 256 x 256 is
+    1024 tiles, i.e. seven per CTA to accumulate over in tensor memory."""
     from vfi_b200 import ops
 
     z = rand_dcn(B, 67, 67, H, W, sigma, seed=91 + H)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "vfi_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "vfi_selftest_umma_ts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vfi_debug_read": (c_int, [c_void_p, c_size_t]),
+    "vfi_debug_abort_info": (c_int, [c_void_p]),
 }
 
 _lib = None

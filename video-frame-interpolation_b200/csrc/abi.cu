@@ -29,6 +29,7 @@ int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, i
                        void* packed, float* bias_out, cudaStream_t st, int variant);
 int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st);
 int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel);
+int dcn_tc_abort_info(unsigned long long* info);
 int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
                       long long O, float* gw, float* gb, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
@@ -117,6 +118,8 @@ extern "C" int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tenso
                                      size_t workspace_bytes, vfi_stream_t stream) {
   return dcn_tc_bwd_weight(grad_out, x, offset, mask, O, grad_weight, grad_bias, workspace, workspace_bytes, (cudaStream_t)stream);
 }
+
+extern "C" int vfi_debug_abort_info(uint64_t* info36) { return dcn_tc_abort_info(reinterpret_cast<unsigned long long*>(info36)); }
 
 extern "C" int vfi_dcn_k_order(int32_t variant, int32_t kb, int32_t kk, int32_t* tap, int32_t* channel) {
   return dcn_tc_k_order(variant, kb, kk, tap, channel);

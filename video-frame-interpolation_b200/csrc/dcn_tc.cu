@@ -98,15 +98,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uin
 }
 // Slow path of a wait.  try_wait returns whenever ANY mbarrier of the CTA sees an arrival (measured: a waiting warp came
 // back every ~170 cycles regardless of the hint), so a bare retry loop burns the issue slots the producers need; the
-// explicit sleep bounds that cost.  NS trades issue slots against wake-up latency per wait site.  A protocol bug traps
-// (launch failure) after a few seconds instead of hanging the GPU.
+// explicit sleep bounds that cost.  NS trades issue slots against wake-up latency per wait site.  A protocol bug ends the
+// kernel through the watchdog below instead of hanging the GPU.
+// Diagnostics of a stuck pipeline: the first waiter that times out records who it is and raises the flag; every other
+// waiter sees the flag and leaves too, so the kernel ends (with garbage results) and vfi_debug_abort_info can be read.
+__device__ unsigned int g_abort_flag = 0;
+__device__ unsigned long long g_abort_info[4 + 32] = {0};        // [block << 32 | warp, barrier smem address, parity, count,
+                                                                 //  then per warp of that block: barrier address | parity << 32]
+
+// Called every 1024 spins of a slow wait.  Returns true when the waiter must give up: either it has spun 2^21 times
+// (0.2 .. 2.7 s: each spin is one nanosleep plus one try_wait of at most 1 us; legitimate waits are milliseconds at most),
+// or another waiter already raised the flag.
+__device__ __noinline__ bool mbar_watchdog(uint32_t bar, uint32_t parity, uint32_t spins) {
+  const bool first = spins >= (1u << 21) && atomicExch(&g_abort_flag, 1u) == 0u;
+  if (first) {
+    g_abort_info[0] = ((unsigned long long)blockIdx.x << 32) | (threadIdx.x >> 5);
+    g_abort_info[1] = bar;
+    g_abort_info[2] = parity;
+    __threadfence();
+  }
+  if (!first && spins < (1u << 21) && !*(volatile unsigned int*)&g_abort_flag) return false;
+  if ((g_abort_info[0] >> 32) == blockIdx.x) g_abort_info[4 + (threadIdx.x >> 5)] = bar | ((unsigned long long)parity << 32);
+  atomicAdd(&g_abort_info[3], 1ull);
+  return true;
+}
+
+// Nothing but the sleep, the counter and the retry sit on this path: every waiting warp runs it, and a larger body (the
+// watchdog inline, a %globaltimer read at entry) cost the forward kernel 6-9 % in register saves around the call.
 template <int NS>
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   do {
     __nanosleep(NS);
-    if (++spins > (1u << 26)) __trap();
-  } while (!mbar_try_wait(bar, parity, 100000u));
+    if ((++spins & 1023u) == 0u && mbar_watchdog(bar, parity, spins)) return;
+  } while (!mbar_try_wait(bar, parity, 1000u));
 }
 template <int NS>
 __device__ __forceinline__ void mbar_wait_ns(uint32_t bar, uint32_t parity) {
@@ -1011,6 +1036,19 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
     VFI_LAUNCH_CHECK("dcn_tc6_wgrad_kernel");
   }
   return VFI_OK;
+}
+
+// Returns 1 when a kernel of this library gave up on a pipeline wait since the last call (results of that launch are
+// invalid), with info = [block << 32 | warp, barrier shared-memory address, parity, number of waiters that gave up].
+int dcn_tc_abort_info(unsigned long long* info) {
+  unsigned int flag = 0, zero = 0;
+  unsigned long long z[36] = {0};
+  VFI_CUDA(cudaDeviceSynchronize());
+  VFI_CUDA(cudaMemcpyFromSymbol(&flag, g_abort_flag, sizeof(flag)));
+  if (info) VFI_CUDA(cudaMemcpyFromSymbol(info, g_abort_info, sizeof(z)));
+  VFI_CUDA(cudaMemcpyToSymbol(g_abort_flag, &zero, sizeof(zero)));
+  VFI_CUDA(cudaMemcpyToSymbol(g_abort_info, z, sizeof(z)));
+  return flag ? 1 : 0;
 }
 
 int umma_ts_selftest(const void* A, const void* Bm, float* D, uint32_t* raw, cudaStream_t st) {

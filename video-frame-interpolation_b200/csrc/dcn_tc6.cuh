@@ -67,6 +67,16 @@ constexpr int V6_W_GEO = 28, V6_GEO_WARPS = 4;                                  
 constexpr int V6_THREADS = 32 * 32;                                               // 1024
 constexpr int V6_KBLOCKS = 10;                                                    // 9 main + 1 tail
 constexpr int V6_NA = 8, V6_NB = 3;                                               // TMEM A ring / smem B ring depth
+// "Block n consumed" barriers, one per A stage.  A parity wait cannot tell "completed k times" from "k - 2 times", so a
+// waiter must never be two phases (16 blocks) ahead of its barrier.  It cannot be: consecutive blocks of a producer group are
+// 5 apart, the group's previous wait established that block n - 13 was consumed, and the MMA warp consumes in order, so
+// block n - 16 is consumed whenever block n is attempted.  (The ring may be made longer than the stage ring -- V6_NDONE_N --
+// but measured slower: 8 -> 4.62, 16 -> 5.88, 24 -> 6.19 ms on one box.  The weight-gradient kernel, whose stage ring (3) is
+// SHORTER than the group stride, needs the longer ring and deadlocked without it.)
+#ifndef V6_NDONE_N
+#define V6_NDONE_N 8
+#endif
+constexpr int V6_NDONE = V6_NDONE_N;
 constexpr int V6_A_COL0 = 256;                                                    // TMEM columns [256, 512): A ring
 constexpr int V6_TMEM_COLS = 512;
 constexpr uint32_t V6_SLOW = 0x80000000u;                                         // entry.x: sample not served by the box
@@ -87,7 +97,7 @@ struct __align__(1024) V6Smem {
   uint4 geo[2][9][TC_M];                               // x: box byte offset | V6_SLOW, y/z: 4 bf16 weights, w: global pixel (slow)
   uint8_t ostage[TC_M * 128];                          // epilogue staging tile (chunk j of row r at j ^ (r & 7))
   uint16_t raw[27][TC_M];                              // offset / mask values of the next tile (cp.async), [channel][tile row]
-  unsigned long long full[V6_NA], done[V6_NA];         // per K block n (slot n % 8): operands ready / MMAs complete
+  unsigned long long full[V6_NA], done[V6_NDONE];      // per K block n: operands ready (slot n % 8) / MMAs complete (slot n % 16)
   unsigned long long acc_full[2], acc_empty[2], geo_first[2], geo_full[2], geo_empty[2], box_full[2], box_empty[2];
   uint32_t tmem_base;
 };
@@ -411,10 +421,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
     // done = the block's MMAs have completed -> A stage n % 8 and B stage n % 3 are free.  The loader reads done[n - 3]
     // before block n - 3 + 8 can complete (that block needs a weight block the loader has not issued yet), so the
     // two consumers of `done` never see the barrier two phases ahead.
-    for (int i = 0; i < V6_NA; ++i) {
-      mbar_init(smem_u32(&s.full[i]), 5);
-      mbar_init(smem_u32(&s.done[i]), 1);
-    }
+    for (int i = 0; i < V6_NA; ++i) mbar_init(smem_u32(&s.full[i]), 5);
+    for (int i = 0; i < V6_NDONE; ++i) mbar_init(smem_u32(&s.done[i]), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
       mbar_init(smem_u32(&s.acc_empty[i]), V6_EPI_WARPS);
@@ -462,7 +470,10 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
       const int kb_first = V6_ROTATE ? (group + it) % V6_GROUPS : group;
       for (int kb = kb_first; kb < V6_KBLOCKS; kb = V6_PAIRING ? (kb < V6_GROUPS ? V6_KBLOCKS - 1 - kb : V6_KBLOCKS) : kb + V6_GROUPS) {   // 10 K blocks, 5 groups: two each
         const int n = n0 + kb, sa = n % V6_NA;
-        const uint32_t empty_bar = smem_u32(&s.done[sa]), empty_par = (((uint32_t)(n / V6_NA)) & 1u) ^ 1u;
+        // stage sa was last used by block n - 8: wait until that block has been consumed (nothing to wait for when n < 8)
+        const int m8 = n - V6_NA;
+        const uint32_t empty_bar = smem_u32(&s.done[(m8 + V6_NDONE) % V6_NDONE]);
+        const uint32_t empty_par = m8 < 0 ? 1u : (uint32_t)(m8 / V6_NDONE) & 1u;
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
         if (kb >= V6_FIRST_TAPS && !all_taps) {                  // the later taps (and the tail block, which reads all nine)
           mbar_wait_d<V6_NS_PROD, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
           if (kb != V6_KBLOCKS - 1) umma_bf16_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1);
         }
         const long long ti1 = dbg ? clock64() : 0;
-        umma_commit_elect(smem_u32(&s.done[sa]));
+        umma_commit_elect(smem_u32(&s.done[n % V6_NDONE]));
         if (kb == V6_KBLOCKS - 1) umma_commit_elect(smem_u32(&s.acc_full[acc]));
         if (dbg) { w3 += ti1 - ti0; w4 += clock64() - ti1; }
       }
@@ -563,7 +574,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
         const int sb = n % V6_NB;
         if (n >= V6_NB) {                                // block n - 3 (the previous user of stage sb) has completed
           const int m = n - V6_NB;
-          mbar_wait_d<V6_NS_LOAD, DBG>(smem_u32(&s.done[m % V6_NA]), (uint32_t)(m / V6_NA) & 1u, w0);
+          mbar_wait_d<V6_NS_LOAD, DBG>(smem_u32(&s.done[m % V6_NDONE]), (uint32_t)(m / V6_NDONE) & 1u, w0);
         }
         const uint32_t bar = smem_u32(&s.full[n % V6_NA]);
         if (DBG && (p.experiment & 1) && n >= V6_NB) { mbar_arrive(bar); if (++kb == V6_KBLOCKS) kb = 0; continue; }   // diagnostics: no refill

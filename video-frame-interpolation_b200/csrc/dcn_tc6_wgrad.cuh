@@ -23,6 +23,7 @@
 //     Five producer groups, one block each per tile.
 
 constexpr int WG_STAGES = 3;                                   // col stages in shared memory (16 KB each)
+constexpr int WG_NDONE = 12;                                   // completion barriers: 24 blocks (~5 tiles) of aliasing distance
 constexpr int WG_BLOCKS = 5;                                   // blocks (taps, or the tail block) per tile and pass
 constexpr int WG_GOUT_COL0 = WG_BLOCKS * 64;                   // TMEM columns [0, 320): accumulators; [320, 448): gout^T x 2
 constexpr int WG_W_MMA = 20, WG_W_BOX = 21;                    // warps 22, 23 idle
@@ -35,7 +36,7 @@ struct __align__(1024) WgSmem {
   uint8_t box_tail[2][V6_BOX_PX * V6_TAIL_PX];
   uint4 geo[2][9][TC_M];
   uint16_t raw[27][TC_M];
-  unsigned long long stage_full[WG_STAGES], stage_empty[WG_STAGES];
+  unsigned long long stage_full[WG_STAGES], stage_empty[WG_NDONE];   // "block n consumed": ring of its own, see V6_NDONE
   unsigned long long box_full[2], box_empty[2], geo_first[2], geo_full[2], geo_empty[2], gout_full[2], gout_empty[2], acc_done;
   uint32_t tmem_base;
 };
@@ -67,10 +68,8 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_wgrad_kernel(const WgPa
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) {
-      mbar_init(smem_u32(&s.stage_full[i]), 4);                 // the four warps of the producing group
-      mbar_init(smem_u32(&s.stage_empty[i]), 1);                // one tcgen05.commit
-    }
+    for (int i = 0; i < WG_STAGES; ++i) mbar_init(smem_u32(&s.stage_full[i]), 4);    // the four warps of the producing group
+    for (int i = 0; i < WG_NDONE; ++i) mbar_init(smem_u32(&s.stage_empty[i]), 1);    // one tcgen05.commit
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.box_full[i]), 1);
       mbar_init(smem_u32(&s.box_empty[i]), V6_PRODUCER_WARPS);
@@ -109,7 +108,10 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_wgrad_kernel(const WgPa
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]) + (uint32_t)j * 16, box_tail = smem_u32(&s.box_tail[gb][0]);
       const int n = it * WG_BLOCKS + group, st = n % WG_STAGES;
       const uint32_t stage = smem_u32(&s.stage[st][0]);
-      mbar_wait_ns<V6_NS_STAGE>(smem_u32(&s.stage_empty[st]), (((uint32_t)(n / WG_STAGES)) & 1u) ^ 1u);
+      if (n >= WG_STAGES) {                                     // the stage was last used by block n - 3: wait until it is consumed
+        const int m = n - WG_STAGES;
+        mbar_wait_ns<V6_NS_STAGE>(smem_u32(&s.stage_empty[m % WG_NDONE]), (uint32_t)(m / WG_NDONE) & 1u);
+      }
       if (tap < 9) {
 #pragma unroll 2
         for (int i = 0; i < 8; ++i) {
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_wgrad_kernel(const WgPa
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)                          // 16 pixels = 8 TMEM columns of A = two 8-row groups of B
           umma_bf16_ts(d_tmem, a_tmem + 8 * kk, bdesc + (uint64_t)(kk * (2048 >> 4)), idesc, (it | kk) != 0);
-        umma_commit_elect(smem_u32(&s.stage_empty[st]));
+        umma_commit_elect(smem_u32(&s.stage_empty[n % WG_NDONE]));
       }
       umma_commit_elect(smem_u32(&s.gout_empty[gbuf]));
     }
