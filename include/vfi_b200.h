@@ -175,7 +175,8 @@ int vfi_selftest_umma_ts(const void* a_bf16, const void* b_bf16, float* d, uint3
  * each of its pipeline waits; this copies `count` u64 counters ([cta][32 warps][8]) of the last launch to host memory
  * (synchronises the device). */
 int vfi_debug_read(uint64_t* host_dst, size_t count);
-/* Pipeline watchdog of the tcgen05 kernels: a warp that waits on an mbarrier for more than 2 s records itself, raises a
+/* Pipeline watchdog of the tcgen05 kernels (builds with -DVFI_WATCHDOG only; the default build traps after ~5 s instead and
+ * this call then always returns 0): a warp that waits on an mbarrier for more than ~2 s records itself, raises a
  * flag that makes every other waiter leave as well, and the kernel ends instead of hanging the GPU (its results are
  * invalid).  Returns 1 if that happened since the last call (synchronises the device, clears the flag); info36 (may be NULL)
  * receives [block << 32 | warp, shared-memory address of the barrier, parity waited for, number of waiters that gave up] and,

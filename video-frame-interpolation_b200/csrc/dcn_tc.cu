@@ -106,31 +106,38 @@ __device__ unsigned int g_abort_flag = 0;
 __device__ unsigned long long g_abort_info[4 + 32] = {0};        // [block << 32 | warp, barrier smem address, parity, count,
                                                                  //  then per warp of that block: barrier address | parity << 32]
 
-// Called every 1024 spins of a slow wait.  Returns true when the waiter must give up: either it has spun 2^21 times
-// (0.2 .. 2.7 s: each spin is one nanosleep plus one try_wait of at most 1 us; legitimate waits are milliseconds at most),
-// or another waiter already raised the flag.
-__device__ __noinline__ bool mbar_watchdog(uint32_t bar, uint32_t parity, uint32_t spins) {
-  const bool first = spins >= (1u << 21) && atomicExch(&g_abort_flag, 1u) == 0u;
-  if (first) {
-    g_abort_info[0] = ((unsigned long long)blockIdx.x << 32) | (threadIdx.x >> 5);
-    g_abort_info[1] = bar;
-    g_abort_info[2] = parity;
-    __threadfence();
-  }
-  if (!first && spins < (1u << 21) && !*(volatile unsigned int*)&g_abort_flag) return false;
-  if ((g_abort_info[0] >> 32) == blockIdx.x) g_abort_info[4 + (threadIdx.x >> 5)] = bar | ((unsigned long long)parity << 32);
-  atomicAdd(&g_abort_info[3], 1ull);
-  return true;
-}
-
-// Nothing but the sleep, the counter and the retry sit on this path: every waiting warp runs it, and a larger body (the
-// watchdog inline, a %globaltimer read at entry) cost the forward kernel 6-9 % in register saves around the call.
+// Slow path of a wait.  Nothing but the sleep, the counter and the retry sit on the hot path: every waiting warp runs it.
+// (A %globaltimer read at entry, or an out-of-line watchdog function -- any CALL in this body makes the compiler save
+// registers around it -- cost the forward kernel 6-9 %.)  Every 1024 spins the waiter looks at the abort flag; after 2^21
+// spins (0.2 .. 2.7 s: a spin is one nanosleep plus one try_wait of at most 1 us; legitimate waits are milliseconds) it
+// raises the flag itself.  Either way it records what it was waiting on and leaves, so the kernel ends instead of hanging.
 template <int NS>
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   do {
     __nanosleep(NS);
-    if ((++spins & 1023u) == 0u && mbar_watchdog(bar, parity, spins)) return;
+#ifndef VFI_WATCHDOG
+    // default build: a protocol bug traps (launch failure) after 2^22 spins (<= 5.5 s) -- costs nothing measurable.  The
+    // recording watchdog below is 2.6 % slower on the forward kernel; build it with scripts/build_variant.sh wd -DVFI_WATCHDOG
+    // and load it through VFI_B200_LIB when a pipeline needs debugging (that is how the parity aliasing of the weight-
+    // gradient kernel was found).
+    if (++spins > (1u << 22)) __trap();
+#else
+    if ((++spins & 1023u) == 0u) {
+      const bool expired = spins >= (1u << 21);
+      if (expired || *(volatile unsigned int*)&g_abort_flag) {
+        if (expired && atomicExch(&g_abort_flag, 1u) == 0u) {
+          g_abort_info[0] = ((unsigned long long)blockIdx.x << 32) | (threadIdx.x >> 5);
+          g_abort_info[1] = bar;
+          g_abort_info[2] = parity;
+          __threadfence();
+        }
+        if ((g_abort_info[0] >> 32) == blockIdx.x) g_abort_info[4 + (threadIdx.x >> 5)] = bar | ((unsigned long long)parity << 32);
+        atomicAdd(&g_abort_info[3], 1ull);
+        return;
+      }
+    }
+#endif
   } while (!mbar_try_wait(bar, parity, 1000u));
 }
 template <int NS>
