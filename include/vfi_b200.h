@@ -154,7 +154,7 @@ int vfi_dcn_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vf
  * vfi_dcn_bwd_weight with the activations, the modulated samples and grad_out rounded to bf16 -- the training companion of
  * VFI_DCN_MATH_BF16_TC (tolerance: max|delta| / max|ref| <= 1e-2).  x is any [B,C,H,W] tensor with C <= 68 (packed to planes
  * in the workspace, vfi_dcn_workspace_bytes(..., VFI_DCN_MATH_BF16_TC)); offset / mask 16-bit with unit pixel stride and
- * W % 8 == 0; grad_out bf16 or f32.  Accumulates into grad_weight [O,C,3,3] / grad_bias [O] (either may be NULL) with fp32
+ * W % 8 == 0; grad_out bf16 or f32, any strides (NCHW or channels_last).  Accumulates into grad_weight [O,C,3,3] / grad_bias [O] (either may be NULL) with fp32
  * atomics, so the caller zero-fills them or points them into a flat gradient bucket.  Anything outside these limits
  * returns VFI_ERR_UNSUPPORTED and the caller uses vfi_dcn_bwd_weight. */
 int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,

@@ -440,6 +440,11 @@ def test_dcn_weight_grad_tensor_core(B, H, W, sigma, gdt):
                                     cu(z["mask"], torch.bfloat16), 67)
     assert relerr(gw, ref[3]) <= 1e-2
     assert relerr(gb, ref[4]) <= 1e-2
+    # channels_last grad_out (what a cuDNN backward hands over after a channels_last forward) takes the same kernel
+    gw_cl, gb_cl = ops.dcn_weight_grad_tc(g_in.to(DEV).contiguous(memory_format=torch.channels_last),
+                                          cu(z["x"], torch.bfloat16), cu(z["offset"], torch.bfloat16),
+                                          cu(z["mask"], torch.bfloat16), 67)
+    assert relerr(gw_cl, ref[3]) <= 1e-2 and relerr(gb_cl, ref[4]) <= 1e-2
     # autograd: a tensor-core forward uses the tensor-core weight gradient
     x = cu(z["x"], torch.bfloat16).requires_grad_(True)
     w = cu(z["weight"], torch.bfloat16).requires_grad_(True)

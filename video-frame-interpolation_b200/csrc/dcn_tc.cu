@@ -996,8 +996,8 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
   VFI_REQUIRE((offset->dtype == VFI_BF16 || offset->dtype == VFI_F16) && offset->dtype == mask->dtype && bulk_ok(offset, 2) &&
                   bulk_ok(mask, 2), VFI_ERR_UNSUPPORTED,
               "%s: offset / mask must be 16-bit tensors with unit pixel stride and 16-byte aligned rows (W %% 8 == 0)", who);
-  VFI_REQUIRE((grad_out->dtype == VFI_BF16 && bulk_ok(grad_out, 2)) || (grad_out->dtype == VFI_F32 && grad_out->sw == 1),
-              VFI_ERR_UNSUPPORTED, "%s: grad_out must be bf16 (16-byte aligned rows) or f32, unit pixel stride", who);
+  VFI_REQUIRE(grad_out->dtype == VFI_BF16 || grad_out->dtype == VFI_F32, VFI_ERR_UNSUPPORTED, "%s: grad_out must be bf16 or f32",
+              who);
   VFI_REQUIRE(x->w % 8 == 0, VFI_ERR_UNSUPPORTED, "%s: W must be a multiple of 8", who);
   VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "%s: more than 2^30 pixels per call", who);
   const size_t need = dcn_tc_workspace_bytes(x->n, x->h, x->w);
@@ -1019,7 +1019,8 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
   p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y;
   p.experiment = 0; p.debug = nullptr;
-  q.gout = grad_out->data; q.g_sn = grad_out->sn; q.g_sc = grad_out->sc; q.g_sh = grad_out->sh;
+  q.gout = grad_out->data; q.g_sn = grad_out->sn; q.g_sc = grad_out->sc; q.g_sh = grad_out->sh; q.g_sw = grad_out->sw;
+  q.g_vec = (grad_out->dtype == VFI_BF16 && bulk_ok(grad_out, 2)) ? 1 : 0;
   q.gw = gw; q.gb = gb; q.C = (int)C;
   int dev = 0, sms = 148;
   VFI_CUDA(cudaGetDevice(&dev));

@@ -54,7 +54,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
 
 struct WgParams {
   TcParams t;                                    // planes, offsets / mask, geometry of the tiling (out / weights unused)
-  const void* gout; long long g_sn, g_sc, g_sh;  // grad_out [B,O,H,W], unit pixel stride
+  const void* gout; long long g_sn, g_sc, g_sh, g_sw;  // grad_out [B,O,H,W], any strides (NCHW or channels_last)
+  int g_vec;                                         // 1: 16-bit grad_out with unit pixel stride and 16-byte aligned rows
   float* gw; float* gb;                          // [O,C,3,3] / [O] fp32, accumulated into
   int C, pass;
 };
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_wgrad_kernel(const WgPa
       const uint32_t gbuf = (uint32_t)it & 1u;
       int b, ty0, tx0;
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      const TG* src = reinterpret_cast<const TG*>(q.gout) + b * q.g_sn + (long long)o * q.g_sc + (long long)ty0 * q.g_sh + tx0;
+      const TG* src = reinterpret_cast<const TG*>(q.gout) + b * q.g_sn + (long long)o * q.g_sc + (long long)ty0 * q.g_sh + (long long)tx0 * q.g_sw;
       const int rows = min(TC_TH, p.H - ty0), cols = min(TC_TW, p.W - tx0);
       mbar_wait_ns<V6_NS_HELP>(smem_u32(&s.gout_empty[gbuf]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // the MMAs of tile it - 2 are done
       tc_fence_after();
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_wgrad_kernel(const WgPa
           const int y = y4 + yy;
           const TG* row = src + (long long)y * q.g_sh;
           if (live && y < rows) {
-            if (sizeof(TG) == 2) {                              // 16 pixels = 32 contiguous bytes (W % 8 == 0: cols is 8 or 16)
+            if (sizeof(TG) == 2 && q.g_vec) {                   // 16 pixels = 32 contiguous bytes (W % 8 == 0: cols is 8 or 16)
               const uint4 lo = __ldg(reinterpret_cast<const uint4*>(row));
               const uint4 hi = cols > 8 ? __ldg(reinterpret_cast<const uint4*>(row + 8)) : make_uint4(0u, 0u, 0u, 0u);
               r[yy][0] = lo.x; r[yy][1] = lo.y; r[yy][2] = lo.z; r[yy][3] = lo.w;
@@ -212,8 +213,9 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_wgrad_kernel(const WgPa
             } else {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float f0 = 2 * i < cols ? to_f32<TG>(__ldg(row + 2 * i)) : 0.0f;
-                const float f1 = 2 * i + 1 < cols ? to_f32<TG>(__ldg(row + 2 * i + 1)) : 0.0f;
+                // channels_last grad_out lands here: lanes are consecutive channels, so a warp reads 64 contiguous bytes
+                const float f0 = 2 * i < cols ? to_f32<TG>(__ldg(row + (2 * i) * q.g_sw)) : 0.0f;
+                const float f1 = 2 * i + 1 < cols ? to_f32<TG>(__ldg(row + (2 * i + 1) * q.g_sw)) : 0.0f;
                 const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
                 r[yy][i] = *reinterpret_cast<const uint32_t*>(&h);
               }
