@@ -456,6 +456,36 @@ def test_dcn_weight_grad_tensor_core(B, H, W, sigma, gdt):
     assert relerr(w.grad, ref2[3]) <= 2e-2 and relerr(b.grad, ref2[4]) <= 2e-2 and relerr(x.grad, ref2[0]) <= 2e-2
 
 
+@pytest.mark.parametrize("B,H,W,sigma", [(1, 8, 16, 1.5), (2, 24, 40, 1.5), (1, 40, 64, 6.0), (2, 32, 48, 0.0), (1, 9, 13, 3.0)])
+def test_dcn_data_grads_from_column_gradient(B, H, W, sigma):
+    """grad_x / grad_offset / grad_mask of the bf16 training path: column gradient by a dense GEMM, then the
+    channels-last gather / vector-reduction kernel (vfi_dcn_bwd_data_cols), against the fp32 oracle on bf16-rounded
+    operands.  9 x 13 has a ragged last CTA and an odd width; sigma = 6 sends samples outside the image; sigma = 0 puts
+    every sample on an integer position (lh = lw = 0 corner weights)."""
+    z = rand_dcn(B, 67, 67, H, W, sigma, seed=131 + H)
+    bf = torch.bfloat16
+    x = cu(z["x"], bf).requires_grad_(True)
+    off = cu(z["offset"], bf).requires_grad_(True)
+    m = cu(z["mask"], bf).requires_grad_(True)
+    w = cu(z["weight"], bf)
+    out = vfi_b200.deform_conv2d(x, off, w, cu(z["bias"], bf), stride=1, padding=1, dilation=1, mask=m, math="bf16_tc")
+    out.backward(cu(z["grad_out"], bf))
+    ref = oracle.dcn_bwd(bf16_round(z["grad_out"]), bf16_round(z["x"]), bf16_round(z["offset"]), bf16_round(z["mask"]),
+                         bf16_round(z["weight"]))
+    assert x.grad.shape == x.shape and off.grad.shape == off.shape and m.grad.shape == m.shape
+    assert relerr(x.grad, ref[0]) <= 2e-2
+    assert relerr(off.grad, ref[1]) <= 2e-2
+    assert relerr(m.grad, ref[2]) <= 2e-2
+    # the fp32 CUDA-core kernel on the same operands agrees to the same bar
+    x2 = cu(z["x"], bf).float().requires_grad_(True)
+    off2 = cu(z["offset"], bf).float().requires_grad_(True)
+    m2 = cu(z["mask"], bf).float().requires_grad_(True)
+    out2 = vfi_b200.deform_conv2d(x2, off2, w.float(), cu(z["bias"], bf).float(), stride=1, padding=1, dilation=1, mask=m2,
+                                  math="fp32")
+    out2.backward(cu(z["grad_out"], bf).float())
+    assert relerr(x.grad, x2.grad) <= 2e-2 and relerr(off.grad, off2.grad) <= 2e-2 and relerr(m.grad, m2.grad) <= 2e-2
+
+
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
     """Full 1080p frame: tcgen05 result against this library's fp32 parity kernel on the same bf16-rounded inputs."""
     g = torch.Generator(device=DEV).manual_seed(41)

@@ -1,0 +1,182 @@
+// dcn_bwd_cols.cuh -- included by dcn_tc.cu inside namespace vfi::{anonymous}.
+//
+// Backward of the modulated deformable convolution with respect to the input, the offsets and the mask
+// (torchvision::_deform_conv2d_backward's grad_input / grad_offset / grad_mask, reached from
+// /root/reference/src/models/ema_vfi.py:60 through autograd; arithmetic: SURVEY.md Appendix B) for the bf16 training
+// path, split the way the arithmetic splits:
+//
+//   1. gcol[p, (k, c)] = sum_o gout[p, o] * W[o, c, k]        a plain dense GEMM [P, 72] x [72, 648] with no gather in
+//      it: the caller makes it with its BLAS (bf16 operands, fp32 accumulation, bf16 result, 1.3 KB per pixel);
+//   2. this kernel: everything that depends on the sampling positions.  Per (pixel p, tap k), with v_j the four corner
+//      rows of x (64 + 3 channels, channels-last planes) and D_j = <gcol[p, k, :], v_j>:
+//        grad_mask[p, k]     = live ? sum_j w_j D_j : 0
+//        grad_offset[p, 2k]  = m * (lw (D11 - D01) + hw (D10 - D00))         (y),   2k + 1 likewise in x
+//        grad_x[corner_j, :] += gcol[p, k, :] * m * w_j                      (live samples, corners inside the image)
+//
+// Mapping: a CTA owns 32 consecutive pixels of one image (288 pixel-taps).  Phase A, one thread per pixel-tap (lanes =
+// consecutive pixels, so the NCHW offset / mask reads and the grad_offset / grad_mask writes coalesce): sampling
+// geometry once per pixel-tap, plus the three tail channels.  Phase B, one half-warp per pixel-tap with lane = four
+// consecutive channels: 8-byte loads that make full 128-byte rows (gcol and the four corners), a 16-lane shuffle
+// reduction for the three dot products, and grad_x as four `red.global.add.v4.f32` per lane into a channels-last fp32
+// accumulator -- 36 x 17 vector reductions per pixel where the NCHW kernel (dcn_simt.cu) issues 36 x 67 scalar ones.
+// Phase C writes grad_offset / grad_mask.  HBM/L2-bound by the reductions; no tensor-core work in here.
+
+constexpr int BC_PIX = 32;                    // pixels per CTA
+constexpr int BC_PT = BC_PIX * 9;             // pixel-taps per CTA
+constexpr int BC_THREADS = BC_PT;             // 9 warps
+constexpr int BC_TAP_LD = 72;                 // gcol columns per tap: 64 main, 3 tail, 5 zero
+
+struct BcParams {
+  const uint8_t* x_main; const uint8_t* x_tail;            // planes [P][64] / [P][8] bf16 (tail: channels 64.. in the low half)
+  const void* offset; const void* mask;
+  long long f_sn, f_sc, f_sh, f_sw, m_sn, m_sc, m_sh, m_sw;
+  const __nv_bfloat16* gcol; long long gcol_ld;            // [P][gcol_ld], column k * 72 + c
+  float* gx; long long gx_ld;                              // [P][gx_ld] fp32 accumulator, channel c at column c (may be null)
+  float* goff; long long gf_sn, gf_sc, gf_sh, gf_sw;       // [B,18,H,W] f32 (may be null)
+  float* gmask; long long gm_sn, gm_sc, gm_sh, gm_sw;      // [B,9,H,W] f32 (may be null)
+  int B, H, W;
+};
+
+struct BcGeo {
+  int pix00;                    // linear pixel index (b, y0, x0) of the upper-left corner; only dereferenced when its flag is set
+  int flags;                    // bit 0..3: corner 00, 01, 10, 11 inside the image; bit 4: sample live; bit 5: pixel exists
+  float lh, lw, mk;
+};
+
+struct BcSmem {
+  BcGeo geo[BC_PT];             // [k * 32 + pixel]
+  float part[3][BC_PT];         // (mask, dy, dx) partial sums: tail channels from phase A, + main channels from phase B
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint2 ldg_u2_if(const uint8_t* p, bool ok) {
+  return ok ? __ldg(reinterpret_cast<const uint2*>(p)) : make_uint2(0u, 0u);
+}
+// <four bf16 of g, four bf16 of v>
+__device__ __forceinline__ float dot4(const float (&g)[4], uint2 v) {
+  float d = g[0] * bf_lo(v.x);
+  d = fmaf(g[1], bf_hi(v.x), d);
+  d = fmaf(g[2], bf_lo(v.y), d);
+  return fmaf(g[3], bf_hi(v.y), d);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(BC_THREADS) dcn_bwd_cols_kernel(const BcParams q) {
+  __shared__ BcSmem s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const long long HW = (long long)q.H * q.W;
+  const long long p0 = (long long)blockIdx.x * BC_PIX;
+  const long long img0 = (long long)b * HW;                    // linear index of this image's first pixel
+
+  // ------------------------------------------------------------------ phase A: geometry + tail channels, thread = (tap, pixel)
+  {
+    const int k = warp, pxl = lane;
+    const long long pp = p0 + pxl;
+    BcGeo g; g.pix00 = 0; g.flags = 0; g.lh = g.lw = g.mk = 0.0f;
+    float t_m = 0.0f, t_dy = 0.0f, t_dx = 0.0f;
+    if (pp < HW) {
+      const int y = (int)(pp / q.W), x = (int)(pp % q.W);
+      const TO* off = reinterpret_cast<const TO*>(q.offset) + b * q.f_sn + y * q.f_sh + x * q.f_sw;
+      const TO* msk = reinterpret_cast<const TO*>(q.mask) + b * q.m_sn + y * q.m_sh + x * q.m_sw;
+      const float dy = to_f32<TO>(__ldg(off + (2 * k) * q.f_sc));
+      const float dx = to_f32<TO>(__ldg(off + (2 * k + 1) * q.f_sc));
+      g.mk = to_f32<TO>(__ldg(msk + k * q.m_sc));
+      float py = __fadd_rn((float)(y - 1 + k / 3), dy);
+      float px = __fadd_rn((float)(x - 1 + k % 3), dx);
+      const bool live = (py > -1.0f) && (py < (float)q.H) && (px > -1.0f) && (px < (float)q.W);
+      if (!(py > -2.0f && py < (float)q.H + 1.0f)) py = -2.0f;  // no valid corner out there; keeps the cast defined
+      if (!(px > -2.0f && px < (float)q.W + 1.0f)) px = -2.0f;
+      const float fy = floorf(py), fx = floorf(px);
+      const int y0 = (int)fy, x0 = (int)fx;
+      g.lh = py - fy; g.lw = px - fx;
+      const bool r0 = (unsigned)y0 < (unsigned)q.H, r1 = (unsigned)(y0 + 1) < (unsigned)q.H;
+      const bool c0 = (unsigned)x0 < (unsigned)q.W, c1 = (unsigned)(x0 + 1) < (unsigned)q.W;
+      g.flags = (r0 && c0 ? 1 : 0) | (r0 && c1 ? 2 : 0) | (r1 && c0 ? 4 : 0) | (r1 && c1 ? 8 : 0) | (live ? 16 : 0) | 32;
+      g.pix00 = (int)(img0 + (long long)y0 * q.W + x0);
+      // tail channels (64..66): 8 bytes of gcol, 8 bytes per corner
+      const uint2 gt = __ldg(reinterpret_cast<const uint2*>(q.gcol + (size_t)(img0 + pp) * q.gcol_ld + k * BC_TAP_LD + 64));
+      const float gc[4] = {bf_lo(gt.x), bf_hi(gt.x), bf_lo(gt.y), bf_hi(gt.y)};
+      const uint8_t* xt = q.x_tail + (long long)g.pix00 * 16;
+      const uint2 v00 = ldg_u2_if(xt, g.flags & 1), v01 = ldg_u2_if(xt + 16, g.flags & 2);
+      const uint2 v10 = ldg_u2_if(xt + (long long)q.W * 16, g.flags & 4), v11 = ldg_u2_if(xt + (long long)q.W * 16 + 16, g.flags & 8);
+      const float d00 = dot4(gc, v00), d01 = dot4(gc, v01), d10 = dot4(gc, v10), d11 = dot4(gc, v11);
+      const float hh = 1.0f - g.lh, hw = 1.0f - g.lw;
+      const float w00 = hh * hw, w01 = hh * g.lw, w10 = g.lh * hw, w11 = g.lh * g.lw;
+      t_m = live ? (w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11) : 0.0f;
+      t_dy = g.mk * (g.lw * (d11 - d01) + hw * (d10 - d00));
+      t_dx = g.mk * (g.lh * (d11 - d10) + hh * (d01 - d00));
+      if (q.gx && live) {
+        float* gp = q.gx + (long long)g.pix00 * q.gx_ld + 64;
+        const float m0 = gc[0] * g.mk, m1 = gc[1] * g.mk, m2 = gc[2] * g.mk;
+        if (g.flags & 1) red_add_v4(gp, m0 * w00, m1 * w00, m2 * w00, 0.0f);
+        if (g.flags & 2) red_add_v4(gp + q.gx_ld, m0 * w01, m1 * w01, m2 * w01, 0.0f);
+        if (g.flags & 4) red_add_v4(gp + (long long)q.W * q.gx_ld, m0 * w10, m1 * w10, m2 * w10, 0.0f);
+        if (g.flags & 8) red_add_v4(gp + ((long long)q.W + 1) * q.gx_ld, m0 * w11, m1 * w11, m2 * w11, 0.0f);
+      }
+    }
+    s.geo[tid] = g;
+    s.part[0][tid] = t_m; s.part[1][tid] = t_dy; s.part[2][tid] = t_dx;
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase B: main channels, half-warp = pixel-tap, lane = 4 channels
+  {
+    const int half = lane >> 4, l16 = lane & 15;
+#pragma unroll 2
+    for (int it = 0; it < BC_PT / 18; ++it) {
+      const int pt = it * 18 + warp * 2 + half;                 // consecutive half-warps: consecutive taps of one pixel
+      const int pxl = pt / 9, k = pt - pxl * 9;
+      const int idx = k * 32 + pxl;
+      const BcGeo g = s.geo[idx];
+      const bool exists = (g.flags & 32) != 0, live = (g.flags & 16) != 0;
+      const uint2 gv = ldg_u2_if(reinterpret_cast<const uint8_t*>(q.gcol + (size_t)(img0 + p0 + pxl) * q.gcol_ld + k * BC_TAP_LD) + 8 * l16,
+                                 exists);
+      const float gc[4] = {bf_lo(gv.x), bf_hi(gv.x), bf_lo(gv.y), bf_hi(gv.y)};
+      const uint8_t* xm = q.x_main + (long long)g.pix00 * 128 + 8 * l16;
+      const uint2 v00 = ldg_u2_if(xm, g.flags & 1), v01 = ldg_u2_if(xm + 128, g.flags & 2);
+      const uint2 v10 = ldg_u2_if(xm + (long long)q.W * 128, g.flags & 4), v11 = ldg_u2_if(xm + (long long)q.W * 128 + 128, g.flags & 8);
+      const float d00 = dot4(gc, v00), d01 = dot4(gc, v01), d10 = dot4(gc, v10), d11 = dot4(gc, v11);
+      const float hh = 1.0f - g.lh, hw = 1.0f - g.lw;
+      const float w00 = hh * hw, w01 = hh * g.lw, w10 = g.lh * hw, w11 = g.lh * g.lw;
+      float r_m = live ? (w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11) : 0.0f;
+      float r_dy = g.mk * (g.lw * (d11 - d01) + hw * (d10 - d00));
+      float r_dx = g.mk * (g.lh * (d11 - d10) + hh * (d01 - d00));
+      if (q.gx && live) {
+        float* gp = q.gx + (long long)g.pix00 * q.gx_ld + 4 * l16;
+        const float m0 = gc[0] * g.mk, m1 = gc[1] * g.mk, m2 = gc[2] * g.mk, m3 = gc[3] * g.mk;
+        if (g.flags & 1) red_add_v4(gp, m0 * w00, m1 * w00, m2 * w00, m3 * w00);
+        if (g.flags & 2) red_add_v4(gp + q.gx_ld, m0 * w01, m1 * w01, m2 * w01, m3 * w01);
+        if (g.flags & 4) red_add_v4(gp + (long long)q.W * q.gx_ld, m0 * w10, m1 * w10, m2 * w10, m3 * w10);
+        if (g.flags & 8) red_add_v4(gp + ((long long)q.W + 1) * q.gx_ld, m0 * w11, m1 * w11, m2 * w11, m3 * w11);
+      }
+#pragma unroll
+      for (int sh = 8; sh >= 1; sh >>= 1) {                     // stays inside the half-warp
+        r_m += __shfl_xor_sync(0xffffffffu, r_m, sh);
+        r_dy += __shfl_xor_sync(0xffffffffu, r_dy, sh);
+        r_dx += __shfl_xor_sync(0xffffffffu, r_dx, sh);
+      }
+      if (l16 == 0) { s.part[0][idx] += r_m; s.part[1][idx] += r_dy; s.part[2][idx] += r_dx; }
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase C: grad_mask / grad_offset, thread = (tap, pixel)
+  {
+    const int k = warp;
+    const long long pp = p0 + lane;
+    if (pp < HW) {
+      const int y = (int)(pp / q.W), x = (int)(pp % q.W);
+      if (q.gmask) q.gmask[b * q.gm_sn + k * q.gm_sc + y * q.gm_sh + x * q.gm_sw] = s.part[0][tid];
+      if (q.goff) {
+        float* go = q.goff + b * q.gf_sn + y * q.gf_sh + x * q.gf_sw;
+        go[(2 * k) * q.gf_sc] = s.part[1][tid];
+        go[(2 * k + 1) * q.gf_sc] = s.part[2][tid];
+      }
+    }
+  }
+}

@@ -682,6 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
 
 #include "dcn_tc6.cuh"   // v6: TMEM-resident A operand, source box staged in shared memory
 #include "dcn_tc6_wgrad.cuh"   // weight / bias gradient on tcgen05 (pixel-reduction GEMM, accumulators persistent in TMEM)
+#include "dcn_bwd_cols.cuh"    // grad_x / grad_offset / grad_mask from the column gradient (channels-last, vector reductions)
 
 // ------------------------------------------------------------------------------------------------ UMMA self test
 // D[128, 80] = A[128, K] * Bm[80, K]^T with A, Bm row-major bf16 in global memory, K a multiple of 64.  Uses exactly
@@ -1043,6 +1044,49 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
 #undef VFI_WG_LAUNCH
     VFI_LAUNCH_CHECK("dcn_tc6_wgrad_kernel");
   }
+  return VFI_OK;
+}
+
+// grad_x / grad_offset / grad_mask from the column gradient gcol = grad_out x W (see dcn_bwd_cols.cuh).
+int dcn_tc_bwd_data_cols(const void* gcol, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
+                         float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset, const vfi_tensor* grad_mask,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const char* who = "vfi_dcn_bwd_data_cols";
+  VFI_REQUIRE(gcol && x && offset && mask, VFI_ERR_INVALID, "%s: null pointer", who);
+  VFI_REQUIRE(x->c > 0 && x->c <= TC_CMAIN + 4, VFI_ERR_UNSUPPORTED, "%s: supports C <= %d", who, TC_CMAIN + 4);
+  VFI_REQUIRE(offset->n == x->n && offset->c == 18 && offset->h == x->h && offset->w == x->w && mask->n == x->n && mask->c == 9 &&
+                  mask->h == x->h && mask->w == x->w, VFI_ERR_INVALID, "%s: shape mismatch", who);
+  VFI_REQUIRE(offset->dtype == mask->dtype, VFI_ERR_UNSUPPORTED, "%s: offset and mask must share a dtype", who);
+  VFI_REQUIRE(gcol_ld >= 9 * BC_TAP_LD && gcol_ld % 4 == 0 && aligned(gcol, 16), VFI_ERR_INVALID,
+              "%s: gcol rows must hold 9 x %d bf16 columns, 8-byte aligned", who, BC_TAP_LD);
+  if (gx_rows) VFI_REQUIRE(gx_ld >= TC_CMAIN + 4 && gx_ld % 4 == 0 && aligned(gx_rows, 16), VFI_ERR_INVALID,
+                           "%s: grad_x rows must hold >= %d floats, 16-byte aligned", who, TC_CMAIN + 4);
+  if (grad_offset) VFI_REQUIRE(grad_offset->data && grad_offset->dtype == VFI_F32 && same_shape(grad_offset, offset), VFI_ERR_INVALID,
+                               "%s: grad_offset must be f32 [B,18,H,W]", who);
+  if (grad_mask) VFI_REQUIRE(grad_mask->data && grad_mask->dtype == VFI_F32 && same_shape(grad_mask, mask), VFI_ERR_INVALID,
+                             "%s: grad_mask must be f32 [B,9,H,W]", who);
+  const long long P = (long long)x->n * x->h * x->w;
+  if (P == 0 || (!gx_rows && !grad_offset && !grad_mask)) return VFI_OK;
+  VFI_REQUIRE(P < 2147483647LL / 2 && x->n <= 65535, VFI_ERR_UNSUPPORTED, "%s: more than 2^30 pixels or 65535 images per call", who);
+  const size_t need = dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
+              "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = dcn_tc_pack_input(x, ws + ws_main_off(), ws + ws_tail_off(P), st);
+  if (rc) return rc;
+  BcParams q{};
+  q.x_main = ws + ws_main_off(); q.x_tail = ws + ws_tail_off(P);
+  q.offset = offset->data; q.mask = mask->data;
+  q.f_sn = offset->sn; q.f_sc = offset->sc; q.f_sh = offset->sh; q.f_sw = offset->sw;
+  q.m_sn = mask->sn; q.m_sc = mask->sc; q.m_sh = mask->sh; q.m_sw = mask->sw;
+  q.gcol = reinterpret_cast<const __nv_bfloat16*>(gcol); q.gcol_ld = gcol_ld;
+  q.gx = gx_rows; q.gx_ld = gx_ld;
+  if (grad_offset) { q.goff = (float*)grad_offset->data; q.gf_sn = grad_offset->sn; q.gf_sc = grad_offset->sc; q.gf_sh = grad_offset->sh; q.gf_sw = grad_offset->sw; }
+  if (grad_mask) { q.gmask = (float*)grad_mask->data; q.gm_sn = grad_mask->sn; q.gm_sc = grad_mask->sc; q.gm_sh = grad_mask->sh; q.gm_sw = grad_mask->sw; }
+  q.B = (int)x->n; q.H = (int)x->h; q.W = (int)x->w;
+  dim3 grid(ceil_div((long long)x->h * x->w, BC_PIX), (unsigned)x->n);
+  VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO><<<grid, BC_THREADS, 0, st>>>(q); });
+  VFI_LAUNCH_CHECK("dcn_bwd_cols_kernel");
   return VFI_OK;
 }
 
