@@ -284,6 +284,7 @@ struct TcParams {
   const float* bias;                               // [80]
   void* out; void* out_tail;                       // out_tail != null: planes out (main [P][64], tail [P][8] bf16)
   long long o_sn, o_sc, o_sh, o_sw;                // generic strided output otherwise
+  int out_rows;                                    // generic output is a dense channels-last 16-bit tensor ([P][O] rows): staged stores
   int B, H, W, O;
   int tiles_x, tiles_y, num_tiles;
   int experiment;                                  // VFI_DCN_EXPERIMENT (diagnostics only, results are wrong when non-zero)
@@ -832,12 +833,16 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
                 "%s: plane output needs out [B,64,H,W] and out_tail [B,O-64,H,W] as dense channels-last bf16 planes "
                 "(pixel strides 64 and 8 elements)", who);
     p.out = out->data; p.out_tail = out_tail->data;
-    p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0;
+    p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0; p.out_rows = 0;
   } else {
     VFI_REQUIRE(out->n == x->n && out->c == O && out->h == x->h && out->w == x->w, VFI_ERR_INVALID,
                 "%s: out must be [B,O,H,W]", who);
     p.out = out->data; p.out_tail = nullptr;
     p.o_sn = out->sn; p.o_sc = out->sc; p.o_sh = out->sh; p.o_sw = out->sw;
+    // channels_last result of a 16-bit forward (what ops.py allocates): every tile row is one contiguous, 16-byte aligned
+    // run of 16 x O elements, written from a staged copy of the tile instead of 2-byte stores 2 O bytes apart
+    p.out_rows = (dtype_size(out->dtype) == 2 && out->sc == 1 && out->sw == O && out->sh == out->w * O && out->sn % 8 == 0 &&
+                  out->w % 8 == 0 && O <= TC_CMAX && aligned(out->data, 16)) ? 1 : 0;
   }
   if (x_tail) {
     VFI_REQUIRE(x_tail->data && x->c == TC_CMAIN && x_tail->c <= TC_CTAIL && x_tail->n == x->n && x_tail->h == x->h &&
@@ -1015,7 +1020,7 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
   p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
   p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
   p.wpacked = nullptr; p.bias = nullptr; p.out = nullptr; p.out_tail = nullptr;
-  p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0;
+  p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0; p.out_rows = 0;
   p.B = (int)x->n; p.H = (int)x->h; p.W = (int)x->w; p.O = (int)O;
   p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y;

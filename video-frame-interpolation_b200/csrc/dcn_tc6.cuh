@@ -95,7 +95,7 @@ struct __align__(1024) V6Smem {
   uint8_t box_main[2][V6_BOX_PX * V6_MAIN_PX];         // 2 x 59,904 B
   uint8_t box_tail[2][V6_BOX_PX * V6_TAIL_PX];         // 2 x  7,488 B
   uint4 geo[2][9][TC_M];                               // x: box byte offset | V6_SLOW, y/z: 4 bf16 weights, w: global pixel (slow)
-  uint8_t ostage[TC_M * 128];                          // epilogue staging tile (chunk j of row r at j ^ (r & 7))
+  uint8_t ostage[TC_M * TC_CMAX * 2];                  // epilogue staging tile: planes use 128 B rows (chunk j of row r at j ^ (r & 7)), channels-last rows O x 2 B
   uint16_t raw[27][TC_M];                              // offset / mask values of the next tile (cp.async), [channel][tile row]
   unsigned long long full[V6_NA], done[V6_NDONE];      // per K block n: operands ready (slot n % 8) / MMAs complete (slot n % 16)
   unsigned long long acc_full[2], acc_empty[2], geo_first[2], geo_full[2], geo_empty[2], box_full[2], box_empty[2];
@@ -111,6 +111,9 @@ __device__ __forceinline__ uint2 lds8(uint32_t saddr) {
   uint2 r;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
   return r;
+}
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
 __device__ __forceinline__ void sts16(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -642,6 +645,13 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
               *reinterpret_cast<uint4*>(ot) = w4;                      // 16 B records of neighbouring pixels coalesce
             }
           }
+        } else if (sizeof(TOUT) == 2 && p.out_rows) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {                  // packed rows of O elements: a tile row is one contiguous run
+            const int c = c16 * 16 + i;
+            const TOUT v = from_f32<TOUT>(__uint_as_float(d[i]));
+            if (c < p.O) sts_u16(ostage + (uint32_t)(row * p.O + c) * 2, *reinterpret_cast<const uint16_t*>(&v));
+          }
         } else if (inside) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -649,6 +659,17 @@ __global__ void __launch_bounds__(V6_THREADS, 1) dcn_tc6_fwd_kernel(const TcPara
             if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]));
           }
         }
+      }
+      if (!PLANES && sizeof(TOUT) == 2 && p.out_rows) {
+        epi_bar_sync();
+        const int cols = min(TC_TW, p.W - tx0);
+        const int seg16 = cols * p.O / 8;                  // 16-byte units per tile row (W % 8 == 0)
+        const uint32_t pitch = (uint32_t)(TC_TW * p.O * 2);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)b * p.o_sn + ((size_t)ty0 * p.W + tx0) * p.O) * 2;
+        for (int i = 0; i < TC_TH && ty0 + i < p.H; ++i)
+          for (int j = etid; j < seg16; j += 128)
+            *reinterpret_cast<uint4*>(dst + (size_t)i * p.W * p.O * 2 + 16 * j) = lds16(ostage + i * pitch + 16 * j);
+        epi_bar_sync();
       }
       if (PLANES) {
         // main plane: the staged tile leaves as full 128-byte lines (8 lanes per pixel, 4 pixels per warp store)

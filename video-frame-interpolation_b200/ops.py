@@ -243,6 +243,14 @@ class _DcnFn(torch.autograd.Function):
         bias_c = None if bias is None else bias.contiguous()
         lib = _lib.load()
         tc = math in (_lib.MATH_BF16_TC, _lib.MATH_BF16_TC_HQ) or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
+        if tc and offset.dtype != torch.float32:
+            # the staged-box kernels (forward v6, weight gradient) stream offset / mask rows with bulk copies: unit pixel
+            # stride.  A channels_last offset_conv output (layers 2 and 3 under channels_last training) costs one 54 B/px copy
+            # here instead of the slower generic kernels.
+            if offset.stride(3) != 1:
+                offset = offset.contiguous()
+            if mask.stride(3) != 1:
+                mask = mask.contiguous()
         # tensor-core results of low-precision inputs come back channels_last (what cuDNN wants next); fp32 stays NCHW
         fmt = torch.channels_last if (tc and x.dtype != torch.float32) else torch.contiguous_format
         out = torch.empty((B, O, H, W), dtype=x.dtype, device=dev, memory_format=fmt)
