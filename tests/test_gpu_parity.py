@@ -476,6 +476,15 @@ def test_dcn_data_grads_from_column_gradient(B, H, W, sigma):
     assert relerr(x.grad, ref[0]) <= 2e-2
     assert relerr(off.grad, ref[1]) <= 2e-2
     assert relerr(m.grad, ref[2]) <= 2e-2
+    # channels_last leaves (what layers 2 and 3 see in channels_last training): same gradients up to reduction order
+    cl = torch.channels_last
+    x3 = cu(z["x"], bf).contiguous(memory_format=cl).requires_grad_(True)
+    off3 = cu(z["offset"], bf).contiguous(memory_format=cl).requires_grad_(True)
+    m3 = cu(z["mask"], bf).contiguous(memory_format=cl).requires_grad_(True)
+    out3 = vfi_b200.deform_conv2d(x3, off3, w, cu(z["bias"], bf), stride=1, padding=1, dilation=1, mask=m3, math="bf16_tc")
+    assert torch.equal(out3, out)
+    out3.backward(cu(z["grad_out"], bf).contiguous(memory_format=cl))
+    assert relerr(x3.grad, x.grad) <= 1e-2 and relerr(off3.grad, off.grad) <= 1e-3 and relerr(m3.grad, m.grad) <= 1e-3
     # the fp32 CUDA-core kernel on the same operands agrees to the same bar
     x2 = cu(z["x"], bf).float().requires_grad_(True)
     off2 = cu(z["offset"], bf).float().requires_grad_(True)

@@ -250,12 +250,13 @@ template <typename TX>
 __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long long sc, long long sh, long long sw, int B,
                                   int C, int H, int W, __nv_bfloat16* __restrict__ main_plane,
                                   __nv_bfloat16* __restrict__ tail_plane) {
-  // one thread per (pixel, 8-channel chunk); lanes run over pixels so NCHW reads coalesce
+  // one thread per (pixel, 8-channel chunk); lanes run over pixels so NCHW reads coalesce -- over chunks when the channel
+  // is the unit-stride dimension (channels_last), so a warp reads a contiguous run of ~3.5 pixel rows
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long npix = (long long)B * H * W;
   if (idx >= npix * (TC_CMAX / 8)) return;
-  int chunk = (int)(idx / npix);
-  long long pix = idx % npix;
+  int chunk = sc == 1 ? (int)(idx % (TC_CMAX / 8)) : (int)(idx / npix);
+  long long pix = sc == 1 ? idx / (TC_CMAX / 8) : idx % npix;
   int xx = (int)(pix % W);
   long long t = pix / W;
   int y = (int)(t % H);
