@@ -41,6 +41,10 @@ def main():
         for tag, rd, rw in (("bwd_data", True, False), ("bwd_weight", False, True)):
             out, gg = run(rd, rw)
             res[f"{name}_{tag}_ms"] = timed(lambda: out.backward(gg, retain_graph=True), n=3)
+    # the tensor-core weight gradient alone, grad_out NCHW-contiguous vs channels_last
+    xb, ob, mb = x, off, msk
+    for tag, gg in (("nchw", go.contiguous()), ("channels_last", go.contiguous(memory_format=torch.channels_last))):
+        res[f"wgrad_tc_{tag}_ms"] = timed(lambda: ops.dcn_weight_grad_tc(gg, xb, ob, mb, C))
     print(json.dumps(res))
 
 
