@@ -161,18 +161,20 @@ int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tensor* x, const
                           int64_t O, float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes,
                           vfi_stream_t stream);
 
-/* grad_x / grad_offset / grad_mask of the bf16 training path, second half.  torchvision::_deform_conv2d_backward
- * (reference call site src/models/ema_vfi.py:60 via autograd) splits into a dense product and a position-dependent part:
- *   gcol[p, k*72 + c] = sum_o grad_out[p, o] * weight[o, c, k]      (plain GEMM [P,72] x [72,648]: the caller's BLAS; bf16 rows
- *                                                                   of gcol_ld >= 648 elements, gcol_ld % 4 == 0, columns
- *                                                                   c >= C of every tap zero)
+/* grad_x / grad_offset / grad_mask, column-gradient form.  torchvision::_deform_conv2d_backward (reference call site
+ * src/models/ema_vfi.py:60 via autograd) splits into a dense product and a position-dependent part:
+ *   gcol[p, k*72 + c] = sum_o grad_out[p, o] * weight[o, c, k]      (plain GEMM [P,72] x [72,648]: the caller's BLAS; rows of
+ *                                                                   gcol_ld >= 648 elements, gcol_ld % 4 == 0, columns
+ *                                                                   c >= C of every tap zero; gcol_dtype VFI_BF16 or VFI_F32)
  * and this call, which gathers the four corner rows of x per (pixel, tap), reduces <gcol, corner> to grad_mask [B,9,H,W] and
  * grad_offset [B,18,H,W] (f32, any strides) and adds gcol * mask * corner weight into grad_x_rows: a CHANNELS-LAST f32
  * accumulator [B*H*W][grad_x_ld] (grad_x_ld >= 68, % 4 == 0, 16-byte aligned, zero-filled by the caller; column c = channel
- * c), i.e. grad_x = grad_x_rows[:, :C] viewed as [B,H,W,C].  x: any [B,C,H,W] tensor, C <= 68, packed to planes in the
- * workspace (vfi_dcn_workspace_bytes(..., VFI_DCN_MATH_BF16_TC)); offset / mask: any dtype and strides.  Any of the three
- * outputs may be NULL.  Semantics (liveness, corner validity, ungated offset gradient) are vfi_dcn_bwd_data's. */
-int vfi_dcn_bwd_data_cols(const void* gcol_bf16, int64_t gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
+ * c), i.e. grad_x = grad_x_rows[:, :C] viewed as [B,H,W,C].  x: any [B,C,H,W] tensor, C <= 68, packed to channels-last planes
+ * of gcol's dtype in the workspace (vfi_dcn_bwd_data_cols_workspace_bytes; bf16 gcol rounds x to bf16, f32 gcol keeps fp32
+ * arithmetic throughout: tolerance of vfi_dcn_bwd_data); offset / mask: any dtype and strides.  Any of the three outputs may
+ * be NULL.  Semantics (liveness, corner validity, ungated offset gradient) are vfi_dcn_bwd_data's. */
+size_t vfi_dcn_bwd_data_cols_workspace_bytes(int64_t B, int64_t H, int64_t W, int32_t gcol_dtype);
+int vfi_dcn_bwd_data_cols(const void* gcol, int32_t gcol_dtype, int64_t gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
                           const vfi_tensor* mask, float* grad_x_rows, int64_t grad_x_ld, const vfi_tensor* grad_offset,
                           const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
 

@@ -32,9 +32,10 @@ int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel);
 int dcn_tc_abort_info(unsigned long long* info);
 int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
                       long long O, float* gw, float* gb, void* workspace, size_t workspace_bytes, cudaStream_t st);
-int dcn_tc_bwd_data_cols(const void* gcol, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
-                         float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset, const vfi_tensor* grad_mask,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t dcn_tc_bwd_data_cols_workspace_bytes(long long B, long long H, long long W, int gcol_dtype);
+int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
+                         const vfi_tensor* mask, float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset,
+                         const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 unsigned long long* dcn_tc_debug_buffer();
 int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
@@ -122,11 +123,16 @@ extern "C" int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tenso
   return dcn_tc_bwd_weight(grad_out, x, offset, mask, O, grad_weight, grad_bias, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int vfi_dcn_bwd_data_cols(const void* gcol_bf16, int64_t gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
-                                     const vfi_tensor* mask, float* grad_x_rows, int64_t grad_x_ld, const vfi_tensor* grad_offset,
-                                     const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, vfi_stream_t stream) {
-  return dcn_tc_bwd_data_cols(gcol_bf16, gcol_ld, x, offset, mask, grad_x_rows, grad_x_ld, grad_offset, grad_mask, workspace,
-                              workspace_bytes, (cudaStream_t)stream);
+extern "C" size_t vfi_dcn_bwd_data_cols_workspace_bytes(int64_t B, int64_t H, int64_t W, int32_t gcol_dtype) {
+  return dcn_tc_bwd_data_cols_workspace_bytes(B, H, W, gcol_dtype);
+}
+
+extern "C" int vfi_dcn_bwd_data_cols(const void* gcol, int32_t gcol_dtype, int64_t gcol_ld, const vfi_tensor* x,
+                                     const vfi_tensor* offset, const vfi_tensor* mask, float* grad_x_rows, int64_t grad_x_ld,
+                                     const vfi_tensor* grad_offset, const vfi_tensor* grad_mask, void* workspace,
+                                     size_t workspace_bytes, vfi_stream_t stream) {
+  return dcn_tc_bwd_data_cols(gcol, gcol_dtype, gcol_ld, x, offset, mask, grad_x_rows, grad_x_ld, grad_offset, grad_mask,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int vfi_debug_abort_info(uint64_t* info36) { return dcn_tc_abort_info(reinterpret_cast<unsigned long long*>(info36)); }

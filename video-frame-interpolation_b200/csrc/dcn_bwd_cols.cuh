@@ -16,7 +16,7 @@
 // Mapping: a CTA owns 32 consecutive pixels of one image (288 pixel-taps).  Phase A, one thread per pixel-tap (lanes =
 // consecutive pixels, so the NCHW offset / mask reads and the grad_offset / grad_mask writes coalesce): sampling
 // geometry once per pixel-tap, plus the three tail channels.  Phase B, one half-warp per pixel-tap with lane = four
-// consecutive channels: 8-byte loads that make full 128-byte rows (gcol and the four corners), a 16-lane shuffle
+// consecutive channels: 8- or 16-byte loads that make full rows (gcol and the four corners), a 16-lane shuffle
 // reduction for the three dot products, and grad_x as four `red.global.add.v4.f32` per lane into a channels-last fp32
 // accumulator -- 36 x 17 vector reductions per pixel where the NCHW kernel (dcn_simt.cu) issues 36 x 67 scalar ones.
 // Phase C writes grad_offset / grad_mask.  HBM/L2-bound by the reductions; no tensor-core work in here.
@@ -27,10 +27,10 @@ constexpr int BC_THREADS = BC_PT;             // 9 warps
 constexpr int BC_TAP_LD = 72;                 // gcol columns per tap: 64 main, 3 tail, 5 zero
 
 struct BcParams {
-  const uint8_t* x_main; const uint8_t* x_tail;            // planes [P][64] / [P][8] bf16 (tail: channels 64.. in the low half)
+  const uint8_t* x_main; const uint8_t* x_tail;            // planes [P][64] / [P][8] of TP (bf16 or f32; tail: channels 64.. first)
   const void* offset; const void* mask;
   long long f_sn, f_sc, f_sh, f_sw, m_sn, m_sc, m_sh, m_sw;
-  const __nv_bfloat16* gcol; long long gcol_ld;            // [P][gcol_ld], column k * 72 + c
+  const void* gcol; long long gcol_ld;                     // [P][gcol_ld] of TP, column k * 72 + c
   float* gx; long long gx_ld;                              // [P][gx_ld] fp32 accumulator, channel c at column c (may be null)
   float* goff; long long gf_sn, gf_sc, gf_sh, gf_sw;       // [B,18,H,W] f32 (may be null)
   float* gmask; long long gm_sn, gm_sc, gm_sh, gm_sw;      // [B,9,H,W] f32 (may be null)
@@ -53,19 +53,28 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-__device__ __forceinline__ uint2 ldg_u2_if(const uint8_t* p, bool ok) {
-  return ok ? __ldg(reinterpret_cast<const uint2*>(p)) : make_uint2(0u, 0u);
+// Four consecutive channels of a plane / gcol row as fp32 (zeros when the corner is outside the image).
+template <typename TP> __device__ __forceinline__ void load4(const uint8_t* p, bool ok, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const uint8_t* p, bool ok, float (&v)[4]) {
+  const uint2 r = ok ? __ldg(reinterpret_cast<const uint2*>(p)) : make_uint2(0u, 0u);
+  v[0] = bf_lo(r.x); v[1] = bf_hi(r.x); v[2] = bf_lo(r.y); v[3] = bf_hi(r.y);
 }
-// <four bf16 of g, four bf16 of v>
-__device__ __forceinline__ float dot4(const float (&g)[4], uint2 v) {
-  float d = g[0] * bf_lo(v.x);
-  d = fmaf(g[1], bf_hi(v.x), d);
-  d = fmaf(g[2], bf_lo(v.y), d);
-  return fmaf(g[3], bf_hi(v.y), d);
+template <> __device__ __forceinline__ void load4<float>(const uint8_t* p, bool ok, float (&v)[4]) {
+  const float4 r = ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+__device__ __forceinline__ float dot4(const float (&g)[4], const float (&v)[4]) {
+  float d = g[0] * v[0];
+  d = fmaf(g[1], v[1], d);
+  d = fmaf(g[2], v[2], d);
+  return fmaf(g[3], v[3], d);
 }
 
-template <typename TO>
+// TO: dtype of offset / mask; TP: dtype of gcol and of the x planes (bf16: the tensor-core training path; f32: the fp32 path).
+template <typename TO, typename TP>
 __global__ void __launch_bounds__(BC_THREADS) dcn_bwd_cols_kernel(const BcParams q) {
+  constexpr int ES = (int)sizeof(TP), MAIN_PX = 64 * ES, TAIL_PX = 8 * ES;
+  const uint8_t* gcol = reinterpret_cast<const uint8_t*>(q.gcol);
   __shared__ BcSmem s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -98,12 +107,12 @@ __global__ void __launch_bounds__(BC_THREADS) dcn_bwd_cols_kernel(const BcParams
       const bool c0 = (unsigned)x0 < (unsigned)q.W, c1 = (unsigned)(x0 + 1) < (unsigned)q.W;
       g.flags = (r0 && c0 ? 1 : 0) | (r0 && c1 ? 2 : 0) | (r1 && c0 ? 4 : 0) | (r1 && c1 ? 8 : 0) | (live ? 16 : 0) | 32;
       g.pix00 = (int)(img0 + (long long)y0 * q.W + x0);
-      // tail channels (64..66): 8 bytes of gcol, 8 bytes per corner
-      const uint2 gt = __ldg(reinterpret_cast<const uint2*>(q.gcol + (size_t)(img0 + pp) * q.gcol_ld + k * BC_TAP_LD + 64));
-      const float gc[4] = {bf_lo(gt.x), bf_hi(gt.x), bf_lo(gt.y), bf_hi(gt.y)};
-      const uint8_t* xt = q.x_tail + (long long)g.pix00 * 16;
-      const uint2 v00 = ldg_u2_if(xt, g.flags & 1), v01 = ldg_u2_if(xt + 16, g.flags & 2);
-      const uint2 v10 = ldg_u2_if(xt + (long long)q.W * 16, g.flags & 4), v11 = ldg_u2_if(xt + (long long)q.W * 16 + 16, g.flags & 8);
+      // tail channels (64..66): four elements of gcol, four per corner
+      float gc[4], v00[4], v01[4], v10[4], v11[4];
+      load4<TP>(gcol + ((size_t)(img0 + pp) * q.gcol_ld + k * BC_TAP_LD + 64) * ES, true, gc);
+      const uint8_t* xt = q.x_tail + (long long)g.pix00 * TAIL_PX;
+      load4<TP>(xt, g.flags & 1, v00); load4<TP>(xt + TAIL_PX, g.flags & 2, v01);
+      load4<TP>(xt + (long long)q.W * TAIL_PX, g.flags & 4, v10); load4<TP>(xt + ((long long)q.W + 1) * TAIL_PX, g.flags & 8, v11);
       const float d00 = dot4(gc, v00), d01 = dot4(gc, v01), d10 = dot4(gc, v10), d11 = dot4(gc, v11);
       const float hh = 1.0f - g.lh, hw = 1.0f - g.lw;
       const float w00 = hh * hw, w01 = hh * g.lw, w10 = g.lh * hw, w11 = g.lh * g.lw;
@@ -112,11 +121,11 @@ __global__ void __launch_bounds__(BC_THREADS) dcn_bwd_cols_kernel(const BcParams
       t_dx = g.mk * (g.lh * (d11 - d10) + hh * (d01 - d00));
       if (q.gx && live) {
         float* gp = q.gx + (long long)g.pix00 * q.gx_ld + 64;
-        const float m0 = gc[0] * g.mk, m1 = gc[1] * g.mk, m2 = gc[2] * g.mk;
-        if (g.flags & 1) red_add_v4(gp, m0 * w00, m1 * w00, m2 * w00, 0.0f);
-        if (g.flags & 2) red_add_v4(gp + q.gx_ld, m0 * w01, m1 * w01, m2 * w01, 0.0f);
-        if (g.flags & 4) red_add_v4(gp + (long long)q.W * q.gx_ld, m0 * w10, m1 * w10, m2 * w10, 0.0f);
-        if (g.flags & 8) red_add_v4(gp + ((long long)q.W + 1) * q.gx_ld, m0 * w11, m1 * w11, m2 * w11, 0.0f);
+        const float m0 = gc[0] * g.mk, m1 = gc[1] * g.mk, m2 = gc[2] * g.mk, m3 = gc[3] * g.mk;   // gcol column 67 is zero when C < 68
+        if (g.flags & 1) red_add_v4(gp, m0 * w00, m1 * w00, m2 * w00, m3 * w00);
+        if (g.flags & 2) red_add_v4(gp + q.gx_ld, m0 * w01, m1 * w01, m2 * w01, m3 * w01);
+        if (g.flags & 4) red_add_v4(gp + (long long)q.W * q.gx_ld, m0 * w10, m1 * w10, m2 * w10, m3 * w10);
+        if (g.flags & 8) red_add_v4(gp + ((long long)q.W + 1) * q.gx_ld, m0 * w11, m1 * w11, m2 * w11, m3 * w11);
       }
     }
     s.geo[tid] = g;
@@ -134,12 +143,11 @@ __global__ void __launch_bounds__(BC_THREADS) dcn_bwd_cols_kernel(const BcParams
       const int idx = k * 32 + pxl;
       const BcGeo g = s.geo[idx];
       const bool exists = (g.flags & 32) != 0, live = (g.flags & 16) != 0;
-      const uint2 gv = ldg_u2_if(reinterpret_cast<const uint8_t*>(q.gcol + (size_t)(img0 + p0 + pxl) * q.gcol_ld + k * BC_TAP_LD) + 8 * l16,
-                                 exists);
-      const float gc[4] = {bf_lo(gv.x), bf_hi(gv.x), bf_lo(gv.y), bf_hi(gv.y)};
-      const uint8_t* xm = q.x_main + (long long)g.pix00 * 128 + 8 * l16;
-      const uint2 v00 = ldg_u2_if(xm, g.flags & 1), v01 = ldg_u2_if(xm + 128, g.flags & 2);
-      const uint2 v10 = ldg_u2_if(xm + (long long)q.W * 128, g.flags & 4), v11 = ldg_u2_if(xm + (long long)q.W * 128 + 128, g.flags & 8);
+      float gc[4], v00[4], v01[4], v10[4], v11[4];
+      load4<TP>(gcol + ((size_t)(img0 + p0 + pxl) * q.gcol_ld + k * BC_TAP_LD + 4 * l16) * ES, exists, gc);
+      const uint8_t* xm = q.x_main + (long long)g.pix00 * MAIN_PX + 4 * ES * l16;
+      load4<TP>(xm, g.flags & 1, v00); load4<TP>(xm + MAIN_PX, g.flags & 2, v01);
+      load4<TP>(xm + (long long)q.W * MAIN_PX, g.flags & 4, v10); load4<TP>(xm + ((long long)q.W + 1) * MAIN_PX, g.flags & 8, v11);
       const float d00 = dot4(gc, v00), d01 = dot4(gc, v01), d10 = dot4(gc, v10), d11 = dot4(gc, v11);
       const float hh = 1.0f - g.lh, hw = 1.0f - g.lw;
       const float w00 = hh * hw, w01 = hh * g.lw, w10 = g.lh * hw, w11 = g.lh * g.lw;

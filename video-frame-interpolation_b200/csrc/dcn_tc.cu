@@ -273,6 +273,32 @@ __global__ void pack_input_kernel(const TX* __restrict__ x, long long sn, long l
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(v);
 }
 
+// Same planes in fp32 (main [P][64], tail [P][8] = channels 64..71), for the fp32 column-gradient backward.
+template <typename TX>
+__global__ void pack_input_f32_kernel(const TX* __restrict__ x, long long sn, long long sc, long long sh, long long sw, int B,
+                                      int C, int H, int W, float* __restrict__ main_plane, float* __restrict__ tail_plane) {
+  constexpr int CH = TC_CMAX / 4;                           // 18 chunks of four channels
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long npix = (long long)B * H * W;
+  if (idx >= npix * CH) return;
+  int chunk = sc == 1 ? (int)(idx % CH) : (int)(idx / npix);
+  long long pix = sc == 1 ? idx / CH : idx % npix;
+  int xx = (int)(pix % W);
+  long long t = pix / W;
+  int y = (int)(t % H);
+  int b = (int)(t / H);
+  const TX* src = x + b * sn + y * sh + xx * sw;
+  float4 v;
+  float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = chunk * 4 + i;
+    f[i] = c < C ? to_f32<TX>(__ldg(src + c * sc)) : 0.0f;
+  }
+  float* dst = chunk < 16 ? main_plane + pix * TC_CMAIN + chunk * 4 : tail_plane + pix * TC_CTAIL + (chunk - 16) * 4;
+  *reinterpret_cast<float4*>(dst) = v;
+}
+
 // ------------------------------------------------------------------------------------------------ main kernel
 struct TcParams {
   const uint8_t* x_main; const uint8_t* x_tail;   // planes (see file header)
@@ -1054,17 +1080,25 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
 }
 
 // grad_x / grad_offset / grad_mask from the column gradient gcol = grad_out x W (see dcn_bwd_cols.cuh).
-int dcn_tc_bwd_data_cols(const void* gcol, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask,
-                         float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset, const vfi_tensor* grad_mask,
-                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+static size_t cols_tail_off(long long P, size_t es) { return (((size_t)P * TC_CMAIN * es + 255) / 256) * 256; }
+size_t dcn_tc_bwd_data_cols_workspace_bytes(long long B, long long H, long long W, int gcol_dtype) {
+  const long long P = B * H * W;
+  const size_t es = gcol_dtype == VFI_F32 ? 4 : 2;
+  return cols_tail_off(P, es) + (((size_t)P * TC_CTAIL * es + 255) / 256) * 256 + 256;
+}
+
+int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
+                         const vfi_tensor* mask, float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset,
+                         const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const char* who = "vfi_dcn_bwd_data_cols";
   VFI_REQUIRE(gcol && x && offset && mask, VFI_ERR_INVALID, "%s: null pointer", who);
+  VFI_REQUIRE(gcol_dtype == VFI_BF16 || gcol_dtype == VFI_F32, VFI_ERR_UNSUPPORTED, "%s: gcol must be bf16 or f32", who);
   VFI_REQUIRE(x->c > 0 && x->c <= TC_CMAIN + 4, VFI_ERR_UNSUPPORTED, "%s: supports C <= %d", who, TC_CMAIN + 4);
   VFI_REQUIRE(offset->n == x->n && offset->c == 18 && offset->h == x->h && offset->w == x->w && mask->n == x->n && mask->c == 9 &&
                   mask->h == x->h && mask->w == x->w, VFI_ERR_INVALID, "%s: shape mismatch", who);
   VFI_REQUIRE(offset->dtype == mask->dtype, VFI_ERR_UNSUPPORTED, "%s: offset and mask must share a dtype", who);
   VFI_REQUIRE(gcol_ld >= 9 * BC_TAP_LD && gcol_ld % 4 == 0 && aligned(gcol, 16), VFI_ERR_INVALID,
-              "%s: gcol rows must hold 9 x %d bf16 columns, 8-byte aligned", who, BC_TAP_LD);
+              "%s: gcol rows must hold 9 x %d columns, row length a multiple of 4, 16-byte aligned", who, BC_TAP_LD);
   if (gx_rows) VFI_REQUIRE(gx_ld >= TC_CMAIN + 4 && gx_ld % 4 == 0 && aligned(gx_rows, 16), VFI_ERR_INVALID,
                            "%s: grad_x rows must hold >= %d floats, 16-byte aligned", who, TC_CMAIN + 4);
   if (grad_offset) VFI_REQUIRE(grad_offset->data && grad_offset->dtype == VFI_F32 && same_shape(grad_offset, offset), VFI_ERR_INVALID,
@@ -1074,24 +1108,42 @@ int dcn_tc_bwd_data_cols(const void* gcol, long long gcol_ld, const vfi_tensor* 
   const long long P = (long long)x->n * x->h * x->w;
   if (P == 0 || (!gx_rows && !grad_offset && !grad_mask)) return VFI_OK;
   VFI_REQUIRE(P < 2147483647LL / 2 && x->n <= 65535, VFI_ERR_UNSUPPORTED, "%s: more than 2^30 pixels or 65535 images per call", who);
-  const size_t need = dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  const size_t need = dcn_tc_bwd_data_cols_workspace_bytes(x->n, x->h, x->w, gcol_dtype);
   VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
               "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  int rc = dcn_tc_pack_input(x, ws + ws_main_off(), ws + ws_tail_off(P), st);
-  if (rc) return rc;
+  const size_t es = gcol_dtype == VFI_F32 ? 4 : 2;
+  uint8_t* main_plane = ws;
+  uint8_t* tail_plane = ws + cols_tail_off(P, es);
+  if (gcol_dtype == VFI_F32) {
+    VFI_REQUIRE(x->data, VFI_ERR_INVALID, "%s: null data pointer", who);
+    const long long total = P * (TC_CMAX / 4);
+    VFI_DISPATCH(x->dtype, TX, {
+      pack_input_f32_kernel<TX><<<ceil_div(total, 256), 256, 0, st>>>(
+          reinterpret_cast<const TX*>(x->data), x->sn, x->sc, x->sh, x->sw, (int)x->n, (int)x->c, (int)x->h, (int)x->w,
+          reinterpret_cast<float*>(main_plane), reinterpret_cast<float*>(tail_plane));
+    });
+    VFI_LAUNCH_CHECK("pack_input_f32_kernel");
+  } else {
+    int rc = dcn_tc_pack_input(x, main_plane, tail_plane, st);
+    if (rc) return rc;
+  }
   BcParams q{};
-  q.x_main = ws + ws_main_off(); q.x_tail = ws + ws_tail_off(P);
+  q.x_main = main_plane; q.x_tail = tail_plane;
   q.offset = offset->data; q.mask = mask->data;
   q.f_sn = offset->sn; q.f_sc = offset->sc; q.f_sh = offset->sh; q.f_sw = offset->sw;
   q.m_sn = mask->sn; q.m_sc = mask->sc; q.m_sh = mask->sh; q.m_sw = mask->sw;
-  q.gcol = reinterpret_cast<const __nv_bfloat16*>(gcol); q.gcol_ld = gcol_ld;
+  q.gcol = gcol; q.gcol_ld = gcol_ld;
   q.gx = gx_rows; q.gx_ld = gx_ld;
   if (grad_offset) { q.goff = (float*)grad_offset->data; q.gf_sn = grad_offset->sn; q.gf_sc = grad_offset->sc; q.gf_sh = grad_offset->sh; q.gf_sw = grad_offset->sw; }
   if (grad_mask) { q.gmask = (float*)grad_mask->data; q.gm_sn = grad_mask->sn; q.gm_sc = grad_mask->sc; q.gm_sh = grad_mask->sh; q.gm_sw = grad_mask->sw; }
   q.B = (int)x->n; q.H = (int)x->h; q.W = (int)x->w;
   dim3 grid(ceil_div((long long)x->h * x->w, BC_PIX), (unsigned)x->n);
-  VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO><<<grid, BC_THREADS, 0, st>>>(q); });
+  if (gcol_dtype == VFI_F32) {
+    VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO, float><<<grid, BC_THREADS, 0, st>>>(q); });
+  } else {
+    VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO, __nv_bfloat16><<<grid, BC_THREADS, 0, st>>>(q); });
+  }
   VFI_LAUNCH_CHECK("dcn_bwd_cols_kernel");
   return VFI_OK;
 }

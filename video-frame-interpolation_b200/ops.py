@@ -192,41 +192,49 @@ _GX_LD = MAIN_C + 4                       # fp32 grad_x accumulator row
 _COLS_CHUNK_BYTES = 1 << 30               # bound on one materialised column-gradient block
 
 
-def _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need_mask):
-    """grad_x / grad_offset / grad_mask of the bf16 training path (torchvision::_deform_conv2d_backward, reference call
-    site src/models/ema_vfi.py:60): the dense half ``gcol = grad_out x W`` is a plain GEMM (cuBLAS through torch.matmul,
-    bf16 operands, fp32 accumulation), materialised one batch chunk at a time (1.3 KB per pixel); everything that depends
-    on the sampling positions is ``vfi_dcn_bwd_data_cols``.  Returns fp32 tensors (grad_x as a channels-last view)."""
+def _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need_mask, f32_math: bool):
+    """grad_x / grad_offset / grad_mask in column-gradient form (torchvision::_deform_conv2d_backward, reference call
+    site src/models/ema_vfi.py:60): the dense half ``gcol = grad_out x W`` is a plain GEMM (cuBLAS through torch.matmul),
+    materialised one batch chunk at a time; everything that depends on the sampling positions is
+    ``vfi_dcn_bwd_data_cols``.  ``f32_math``: fp32 operands and true fp32 GEMM arithmetic (TF32 off) for the parity path,
+    else bf16 operands with fp32 accumulation (1.3 KB per pixel).  Returns fp32 tensors (grad_x as a channels-last view)."""
     dev = x.device
     B, C, H, W = x.shape
     O = weight.shape[0]
     lib = _lib.load()
     TAP = MAIN_C + TAIL_C
+    cdt = torch.float32 if f32_math else torch.bfloat16
     f32 = dict(dtype=torch.float32, device=dev)
-    wt = torch.zeros((TAP, 9, TAP), dtype=torch.bfloat16, device=dev)       # [o][k][c], zero rows / columns beyond O / C
+    wt = torch.zeros((TAP, 9, TAP), dtype=cdt, device=dev)                  # [o][k][c], zero rows / columns beyond O / C
     wt[:O, :, :C] = weight.detach().reshape(O, C, 9).permute(0, 2, 1)
     wt = wt.view(TAP, _COLS_LD)
     hw = H * W
     gx_rows = torch.zeros((B * hw, _GX_LD), **f32) if need_x else None
     goff = torch.empty(offset.shape, **f32) if need_off else None
     gmask = torch.empty(mask.shape, **f32) if need_mask else None
-    step = max(1, _COLS_CHUNK_BYTES // max(1, hw * _COLS_LD * 2))
-    with torch.cuda.device(dev):
-        for b0 in range(0, B, step):
-            b1 = min(B, b0 + step)
-            n = (b1 - b0) * hw
-            if n == 0:
-                continue
-            g72 = torch.zeros((n, TAP), dtype=torch.bfloat16, device=dev)
-            g72[:, :O] = grad_out[b0:b1].permute(0, 2, 3, 1).reshape(n, O)
-            gcol = torch.matmul(g72, wt)
-            ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(b1 - b0, C, O, H, W, _lib.MATH_BF16_TC)))
-            check(lib.vfi_dcn_bwd_data_cols(gcol.data_ptr(), _COLS_LD, ref(desc(x[b0:b1])), ref(desc(offset[b0:b1])),
-                                            ref(desc(mask[b0:b1])),
-                                            gx_rows[b0 * hw:].data_ptr() if need_x else None, _GX_LD,
-                                            ref(desc(goff[b0:b1])) if need_off else None,
-                                            ref(desc(gmask[b0:b1])) if need_mask else None,
-                                            ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_bwd_data_cols")
+    step = max(1, _COLS_CHUNK_BYTES // max(1, hw * _COLS_LD * wt.element_size()))
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    try:
+        if f32_math:
+            torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.cuda.device(dev):
+            for b0 in range(0, B, step):
+                b1 = min(B, b0 + step)
+                n = (b1 - b0) * hw
+                if n == 0:
+                    continue
+                g72 = torch.zeros((n, TAP), dtype=cdt, device=dev)
+                g72[:, :O] = grad_out[b0:b1].permute(0, 2, 3, 1).reshape(n, O)
+                gcol = torch.matmul(g72, wt)
+                ws = _workspace(dev, int(lib.vfi_dcn_bwd_data_cols_workspace_bytes(b1 - b0, H, W, dtype_code(cdt))))
+                check(lib.vfi_dcn_bwd_data_cols(gcol.data_ptr(), dtype_code(cdt), _COLS_LD, ref(desc(x[b0:b1])),
+                                                ref(desc(offset[b0:b1])), ref(desc(mask[b0:b1])),
+                                                gx_rows[b0 * hw:].data_ptr() if need_x else None, _GX_LD,
+                                                ref(desc(goff[b0:b1])) if need_off else None,
+                                                ref(desc(gmask[b0:b1])) if need_mask else None,
+                                                ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_bwd_data_cols")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
     gx = gx_rows.view(B, H, W, _GX_LD)[..., :C].permute(0, 3, 1, 2) if need_x else None
     return gx, goff, gmask
 
@@ -279,12 +287,14 @@ class _DcnFn(torch.autograd.Function):
             grad_out = grad_out.to(x.dtype)
         lib = _lib.load()
         f32 = dict(dtype=torch.float32, device=dev)
-        cols = ctx.tc and x.dtype != torch.float32 and C <= MAIN_C + 4 and O <= MAIN_C + TAIL_C
+        # column-gradient form for every channel count the planes hold; fp32 arithmetic unless the forward ran on the tensor cores
+        cols = C <= MAIN_C + 4 and O <= MAIN_C + TAIL_C and B > 0 and H > 0 and W > 0
         gx = torch.zeros(x.shape, **f32) if need_x and not cols else None
         goff = torch.empty(offset.shape, **f32) if need_off and not cols else None
         gmask = torch.empty(mask.shape, **f32) if need_mask and not cols else None
         if cols and (need_x or need_off or need_mask):
-            gx, goff, gmask = _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need_mask)
+            gx, goff, gmask = _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need_mask,
+                                                  f32_math=not ctx.tc)
         with torch.cuda.device(dev):
             if (need_x or need_off or need_mask) and not cols:
                 ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, _lib.MATH_FP32)))
