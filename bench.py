@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "bf16_tc"])
     ap.add_argument("--dcn-kernel", default="", choices=["", "v4", "v6"], help="A/B switch for the tcgen05 DCN kernel variant")
+    ap.add_argument("--conv27-layout", default="nchw", choices=["nchw", "channels_last"],
+                    help="memory format of the three offset_conv outputs the DCN layers read")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -203,6 +205,8 @@ def main():
     frame2, flow, feat, convs = synthetic_inputs(B, H, W, dtype=dtype, device=dev, seed=1234 + topo.rank,
                                                  flow_sigma=flow_sigma, offset_sigma=off_sigma)
     feat = feat.contiguous(memory_format=torch.channels_last)
+    if args.conv27_layout == "channels_last":
+        convs = [c.contiguous(memory_format=torch.channels_last) for c in convs]
 
     def barrier():
         if world > 1:
@@ -301,6 +305,8 @@ def main():
     if not args.no_e2e:
         hf2, hflow, hfeat, hconvs = synthetic_inputs(B, H, W, dtype=dtype, seed=99 + topo.rank, flow_sigma=flow_sigma,
                                                      offset_sigma=off_sigma, pinned_host=True)
+        if args.conv27_layout == "channels_last":
+            hconvs = [c.contiguous(memory_format=torch.channels_last).pin_memory() for c in hconvs]
         hout = torch.empty((B, 67, H, W), dtype=dtype).pin_memory()
         h2d = sum(t.numel() * t.element_size() for t in (hf2, hflow, hfeat, *hconvs))
         d2h = hout.numel() * hout.element_size()
@@ -335,7 +341,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "height": H, "width": W, "math": args.math,
-                   "tensors": "frame2/flow/conv27 NCHW bf16, feat channels_last bf16, DCN weights [67,67,3,3] bf16",
+                   "tensors": f"frame2/flow NCHW bf16, conv27 {args.conv27_layout} bf16, feat channels_last bf16, DCN weights [67,67,3,3] bf16",
                    "l2": "per-step working set (~5.6 GB) exceeds the 126 MB L2, no flush between iterations",
                    "sharding": "independent frame pairs per rank, no data-path collective"},
         "gpu_launches": int(launches),

@@ -362,6 +362,10 @@ def test_dcn_fused_split_input_and_conv27(math, bar):
     assert relerr(out2.to_nchw(), ref2) <= bar
     out3 = ops.deform_conv2d_fused(torch.cat([feat, tail3], 1).to(DEV), None, c27.to(DEV), w.to(DEV), b.to(DEV), math=math)
     assert relerr(out3.to_nchw(), ref) <= bar
+    # a channels_last offset_conv output (what a channels_last model produces) is read as it lies: same bits out
+    c27_cl = c27.to(DEV).contiguous(memory_format=torch.channels_last)
+    out4 = ops.deform_conv2d_fused(src.main_nchw, src.tail_nchw(3), c27_cl, w.to(DEV), b.to(DEV), math=math)
+    assert torch.equal(out4.main, out.main) and torch.equal(out4.tail, out.tail)
 
 
 def test_umma_ts_selftest_matches_matmul():

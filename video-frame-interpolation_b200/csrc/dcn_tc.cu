@@ -307,6 +307,7 @@ struct TcParams {
   long long f_sn, f_sc, f_sh, f_sw;
   long long m_sn, m_sc, m_sh, m_sw;
   int fused27;                                     // 1: offset ch j -> conv27[j < 9 ? j : j + 9], mask = sigmoid(conv27[9 + k])
+  int geo_cl;                                      // fused27 input is dense channels-last ([P][27]): v6 copies tile rows as they lie
   const uint8_t* wpacked;                          // [11][80][128 B] swizzled
   const float* bias;                               // [80]
   void* out; void* out_tail;                       // out_tail != null: planes out (main [P][64], tail [P][8] bf16)
@@ -892,7 +893,10 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
     return (t->dtype == VFI_BF16 || t->dtype == VFI_F16) && t->sw == 1 && t->w % 8 == 0 && t->sh % 8 == 0 && t->sc % 8 == 0 &&
            t->sn % 8 == 0 && aligned(t->data, 16) && t->sh >= 0 && t->sc >= 0 && t->sn >= 0;
   };
-  const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4 && bulk_ok(offset) && bulk_ok(mask);
+  // ... or, for the fused form, a dense channels-last offset_conv output ([P][27], what a channels_last model hands over)
+  const bool geo_cl = conv27 && (conv27->dtype == VFI_BF16 || conv27->dtype == VFI_F16) && conv27->sc == 1 && conv27->sw == 27 &&
+                      conv27->sh == conv27->w * 27 && conv27->sn % 8 == 0 && conv27->w % 8 == 0 && aligned(conv27->data, 16);
+  const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4 && (geo_cl || (bulk_ok(offset) && bulk_ok(mask)));
   int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, use_v6 ? 6 : 4);
   if (rc) return rc;
   if (x_tail) {
@@ -905,7 +909,7 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
     p.x_tail = ws + ws_tail_off(P);
   }
   p.main_stride = TC_CMAIN * 2; p.tail_stride = TC_CTAIL * 2;
-  p.offset = offset->data; p.mask = mask->data; p.fused27 = conv27 ? 1 : 0;
+  p.offset = offset->data; p.mask = mask->data; p.fused27 = conv27 ? 1 : 0; p.geo_cl = (use_v6 && geo_cl) ? 1 : 0;
   p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
   p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
   p.wpacked = ws; p.bias = bias_ws;
@@ -1043,7 +1047,7 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
   TcParams& p = q.t;
   p.x_main = ws + ws_main_off(); p.x_tail = ws + ws_tail_off(P);
   p.main_stride = TC_CMAIN * 2; p.tail_stride = TC_CTAIL * 2;
-  p.offset = offset->data; p.mask = mask->data; p.fused27 = 0;
+  p.offset = offset->data; p.mask = mask->data; p.fused27 = 0; p.geo_cl = 0;
   p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
   p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
   p.wpacked = nullptr; p.bias = nullptr; p.out = nullptr; p.out_tail = nullptr;

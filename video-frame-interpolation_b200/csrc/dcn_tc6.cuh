@@ -327,10 +327,27 @@ __device__ __forceinline__ void v6_role_geometry(S& s, const TcParams& p, int ro
   // values arrive in shared memory by cp.async a further tile ahead, so no DRAM round trip sits in this warp.
   // Offsets and masks of a tile: 27 channels x 8 tile rows x 16 pixels = 432 chunks of 16 bytes of the NCHW tensor,
   // brought into raw[channel][tile row * 16 + x] by cp.async (four per thread, no registers held) one tile ahead.
+  // Channels-last offset_conv output (p.geo_cl, fused form only): a tile row is one contiguous run of 16 x 27 values, copied
+  // as it lies -- raw then holds [tile pixel][27 channels] and the taps below index it accordingly.  Same 432 chunks, but
+  // consecutive lanes copy consecutive 16 bytes (4 wavefronts per warp instruction instead of 32).
+  uint16_t* const raw_flat = &s.raw[0][0];
   auto fetch_raw = [&](int it) {
     int b, ty0, tx0;
     tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
     const int rows = min(TC_TH, p.H - ty0), cols = min(TC_TW, p.W - tx0);
+    if (FUSED27 && p.geo_cl) {
+      const int per_row = cols * 27 / 8;                  // 16-byte chunks of one tile row (W % 8 == 0)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = row + 128 * j, r = i / 54, jj = i - r * 54;
+        if (i < 8 * 54 && r < rows && jj < per_row) {
+          const TO* src = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + ((long long)(ty0 + r) * p.W + tx0) * 27 + jj * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(raw_flat + r * (TC_TW * 27) + jj * 8)), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = row + 128 * j, c = i >> 4, r = (i >> 1) & 7, x8 = (i & 1) * 8;
@@ -344,6 +361,12 @@ __device__ __forceinline__ void v6_role_geometry(S& s, const TcParams& p, int ro
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // kernel channel c (0..17: offsets dy/dx interleaved, 18..26: mask) of this thread's pixel
+  const bool geo_cl = FUSED27 && p.geo_cl;
+  auto rd = [&](int c) -> uint32_t {
+    if (geo_cl) return raw_flat[row * 27 + (c < 18 ? (c < 9 ? c : c + 9) : c - 9)];
+    return s.raw[c][row];
   };
   if (my_tiles > 0) fetch_raw(0);
   for (int it = 0; it < my_tiles; ++it) {
@@ -367,9 +390,9 @@ __device__ __forceinline__ void v6_role_geometry(S& s, const TcParams& p, int ro
         uint32_t raw[27];                                // [dy x9 | dx x9 | mask x9] as raw bits; only [K0, K1) is live
 #pragma unroll
         for (int k = K0; k < K1; ++k) {                  // tap k: channels 2k, 2k+1 of the offsets, channel k of the mask
-          raw[k] = s.raw[2 * k][row];
-          raw[9 + k] = s.raw[2 * k + 1][row];
-          raw[18 + k] = s.raw[18 + k][row];
+          raw[k] = rd(2 * k);
+          raw[9 + k] = rd(2 * k + 1);
+          raw[18 + k] = rd(18 + k);
         }
 #pragma unroll
         for (int k = K0; k < K1; ++k) {                  // straight-line code: the taps interleave
