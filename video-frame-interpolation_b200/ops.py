@@ -192,6 +192,17 @@ _GX_LD = MAIN_C + 4                       # fp32 grad_x accumulator row
 _COLS_CHUNK_BYTES = 1 << 30               # bound on one materialised column-gradient block
 
 
+def cols_weight_matrix(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[72, 648] matrix M with ``M[o, k*72 + c] = weight[o, c, k // 3, k % 3]`` (zero rows / columns beyond O / C): the
+    right-hand side of the column-gradient GEMM ``gcol = grad_out_rows @ M`` in the column order
+    ``vfi_dcn_bwd_data_cols`` reads (include/vfi_b200.h)."""
+    O, C = weight.shape[:2]
+    TAP = MAIN_C + TAIL_C
+    wt = torch.zeros((TAP, 9, TAP), dtype=dtype, device=weight.device)
+    wt[:O, :, :C] = weight.detach().reshape(O, C, 9).permute(0, 2, 1)
+    return wt.view(TAP, _COLS_LD)
+
+
 def _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need_mask, f32_math: bool):
     """grad_x / grad_offset / grad_mask in column-gradient form (torchvision::_deform_conv2d_backward, reference call
     site src/models/ema_vfi.py:60): the dense half ``gcol = grad_out x W`` is a plain GEMM (cuBLAS through torch.matmul),
@@ -205,9 +216,7 @@ def _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need
     TAP = MAIN_C + TAIL_C
     cdt = torch.float32 if f32_math else torch.bfloat16
     f32 = dict(dtype=torch.float32, device=dev)
-    wt = torch.zeros((TAP, 9, TAP), dtype=cdt, device=dev)                  # [o][k][c], zero rows / columns beyond O / C
-    wt[:O, :, :C] = weight.detach().reshape(O, C, 9).permute(0, 2, 1)
-    wt = wt.view(TAP, _COLS_LD)
+    wt = cols_weight_matrix(weight, cdt)
     hw = H * W
     gx_rows = torch.zeros((B * hw, _GX_LD), **f32) if need_x else None
     goff = torch.empty(offset.shape, **f32) if need_off else None
