@@ -460,12 +460,14 @@ def test_dcn_weight_grad_tensor_core(B, H, W, sigma, gdt):
     assert relerr(w.grad, ref2[3]) <= 2e-2 and relerr(b.grad, ref2[4]) <= 2e-2 and relerr(x.grad, ref2[0]) <= 2e-2
 
 
-@pytest.mark.parametrize("B,H,W,sigma", [(1, 8, 16, 1.5), (2, 24, 40, 1.5), (1, 40, 64, 6.0), (2, 32, 48, 0.0), (1, 9, 13, 3.0)])
+@pytest.mark.parametrize("B,H,W,sigma", [(1, 8, 16, 1.5), (2, 24, 40, 1.5), (1, 40, 64, 6.0), (2, 32, 48, 0.0), (1, 9, 13, 3.0),
+                                         (2, 16, 24, 0.2)])
 def test_dcn_data_grads_from_column_gradient(B, H, W, sigma):
     """grad_x / grad_offset / grad_mask of the bf16 training path: column gradient by a dense GEMM, then the
     channels-last gather / vector-reduction kernel (vfi_dcn_bwd_data_cols), against the fp32 oracle on bf16-rounded
     operands.  9 x 13 has a ragged last CTA and an odd width; sigma = 6 sends samples outside the image; sigma = 0 puts
-    every sample on an integer position (lh = lw = 0 corner weights)."""
+    every sample on an integer position (lh = lw = 0 corner weights); sigma = 0 and 0.2 make neighbouring taps share corners,
+    the case the kernel merges in registers."""
     z = rand_dcn(B, 67, 67, H, W, sigma, seed=131 + H)
     bf = torch.bfloat16
     x = cu(z["x"], bf).requires_grad_(True)

@@ -15,12 +15,16 @@
 //
 // Mapping: a CTA owns 32 consecutive pixels of one image (288 pixel-taps).  Phase A, one thread per pixel-tap (lanes =
 // consecutive pixels, so the NCHW offset / mask reads and the grad_offset / grad_mask writes coalesce): sampling
-// geometry once per pixel-tap, plus the three tail channels.  Phase B, one half-warp per pixel-tap with lane = four
+// geometry once per pixel-tap, plus the three tail channels.  Phase B, one half-warp per (pixel, kernel row) with lane = four
 // consecutive channels: 8- or 16-byte loads that make full rows (gcol and the four corners), a 16-lane shuffle
 // reduction for the three dot products, and grad_x as four `red.global.add.v4.f32` per lane into a channels-last fp32
-// accumulator -- 36 x 17 vector reductions per pixel where the NCHW kernel (dcn_simt.cu) issues 36 x 67 scalar ones.
+// accumulator -- at most 36 x 17 vector reductions per pixel (24 x 17 when neighbouring taps share corners, see phase B)
+// where the NCHW kernel (dcn_simt.cu) issues 36 x 67 scalar ones.
 // Phase C writes grad_offset / grad_mask.  HBM/L2-bound by the reductions; no tensor-core work in here.
 
+#ifndef BC_MERGE
+#define BC_MERGE 1
+#endif
 constexpr int BC_PIX = 32;                    // pixels per CTA
 constexpr int BC_PT = BC_PIX * 9;             // pixel-taps per CTA
 constexpr int BC_THREADS = BC_PT;             // 9 warps
@@ -133,42 +137,75 @@ __global__ void __launch_bounds__(BC_THREADS) dcn_bwd_cols_kernel(const BcParams
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ phase B: main channels, half-warp = pixel-tap, lane = 4 channels
-  {
+  // ------------------------------------------------------------------ phase B: main channels, half-warp = (pixel, kernel row), lane = 4 channels
+  // A half-warp walks the three taps of one kernel row.  With offsets that vary slowly from tap to tap (what a trained
+  // offset_conv produces) the right-hand corners of tap j are the left-hand corners of tap j + 1: their grad_x contributions
+  // are added in registers and leave as one reduction -- 8 instead of 12 per kernel row.  The test is on the pixel index,
+  // so arbitrary offsets are handled (nothing merges, nothing is lost).
+  if (warp < 8) {
     const int half = lane >> 4, l16 = lane & 15;
-#pragma unroll 2
-    for (int it = 0; it < BC_PT / 18; ++it) {
-      const int pt = it * 18 + warp * 2 + half;                 // consecutive half-warps: consecutive taps of one pixel
-      const int pxl = pt / 9, k = pt - pxl * 9;
-      const int idx = k * 32 + pxl;
-      const BcGeo g = s.geo[idx];
-      const bool exists = (g.flags & 32) != 0, live = (g.flags & 16) != 0;
-      float gc[4], v00[4], v01[4], v10[4], v11[4];
-      load4<TP>(gcol + ((size_t)(img0 + p0 + pxl) * q.gcol_ld + k * BC_TAP_LD + 4 * l16) * ES, exists, gc);
-      const uint8_t* xm = q.x_main + (long long)g.pix00 * MAIN_PX + 4 * ES * l16;
-      load4<TP>(xm, g.flags & 1, v00); load4<TP>(xm + MAIN_PX, g.flags & 2, v01);
-      load4<TP>(xm + (long long)q.W * MAIN_PX, g.flags & 4, v10); load4<TP>(xm + ((long long)q.W + 1) * MAIN_PX, g.flags & 8, v11);
-      const float d00 = dot4(gc, v00), d01 = dot4(gc, v01), d10 = dot4(gc, v10), d11 = dot4(gc, v11);
-      const float hh = 1.0f - g.lh, hw = 1.0f - g.lw;
-      const float w00 = hh * hw, w01 = hh * g.lw, w10 = g.lh * hw, w11 = g.lh * g.lw;
-      float r_m = live ? (w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11) : 0.0f;
-      float r_dy = g.mk * (g.lw * (d11 - d01) + hw * (d10 - d00));
-      float r_dx = g.mk * (g.lh * (d11 - d10) + hh * (d01 - d00));
-      if (q.gx && live) {
-        float* gp = q.gx + (long long)g.pix00 * q.gx_ld + 4 * l16;
-        const float m0 = gc[0] * g.mk, m1 = gc[1] * g.mk, m2 = gc[2] * g.mk, m3 = gc[3] * g.mk;
-        if (g.flags & 1) red_add_v4(gp, m0 * w00, m1 * w00, m2 * w00, m3 * w00);
-        if (g.flags & 2) red_add_v4(gp + q.gx_ld, m0 * w01, m1 * w01, m2 * w01, m3 * w01);
-        if (g.flags & 4) red_add_v4(gp + (long long)q.W * q.gx_ld, m0 * w10, m1 * w10, m2 * w10, m3 * w10);
-        if (g.flags & 8) red_add_v4(gp + ((long long)q.W + 1) * q.gx_ld, m0 * w11, m1 * w11, m2 * w11, m3 * w11);
-      }
+    struct Pending { float v[4]; int pix; bool on; };
+    const auto flush = [&](Pending& pd) {
+      if (pd.on) red_add_v4(q.gx + (long long)pd.pix * q.gx_ld + 4 * l16, pd.v[0], pd.v[1], pd.v[2], pd.v[3]);
+      pd.on = false;
+    };
+    // left-hand corner `pix` with weight w: absorbs the pending right-hand corner of the previous tap when it is the same pixel
+    const auto left = [&](Pending& pd, bool ok, int pix, float w, const float (&m)[4]) {
+      float a[4] = {m[0] * w, m[1] * w, m[2] * w, m[3] * w};
+      if (BC_MERGE && pd.on && ok && pd.pix == pix) {
 #pragma unroll
-      for (int sh = 8; sh >= 1; sh >>= 1) {                     // stays inside the half-warp
-        r_m += __shfl_xor_sync(0xffffffffu, r_m, sh);
-        r_dy += __shfl_xor_sync(0xffffffffu, r_dy, sh);
-        r_dx += __shfl_xor_sync(0xffffffffu, r_dx, sh);
+        for (int c = 0; c < 4; ++c) a[c] += pd.v[c];
+        pd.on = false;
       }
-      if (l16 == 0) { s.part[0][idx] += r_m; s.part[1][idx] += r_dy; s.part[2][idx] += r_dx; }
+      flush(pd);
+      if (ok) red_add_v4(q.gx + (long long)pix * q.gx_ld + 4 * l16, a[0], a[1], a[2], a[3]);
+    };
+    const auto right = [&](Pending& pd, bool ok, int pix, float w, const float (&m)[4]) {
+      pd.on = ok; pd.pix = pix;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pd.v[c] = m[c] * w;
+    };
+#pragma unroll 1
+    for (int it = 0; it < (BC_PIX * 3) / 16; ++it) {
+      const int unit = it * 16 + warp * 2 + half;               // consecutive half-warps: the three kernel rows of one pixel
+      const int pxl = unit / 3, krow = unit - pxl * 3;
+      Pending top, bot;
+      top.on = bot.on = false; top.pix = bot.pix = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) top.v[c] = bot.v[c] = 0.0f;
+#pragma unroll
+      for (int kj = 0; kj < 3; ++kj) {
+        const int k = krow * 3 + kj;
+        const int idx = k * 32 + pxl;
+        const BcGeo g = s.geo[idx];
+        const bool exists = (g.flags & 32) != 0, live = (g.flags & 16) != 0;
+        float gc[4], v00[4], v01[4], v10[4], v11[4];
+        load4<TP>(gcol + ((size_t)(img0 + p0 + pxl) * q.gcol_ld + k * BC_TAP_LD + 4 * l16) * ES, exists, gc);
+        const uint8_t* xm = q.x_main + (long long)g.pix00 * MAIN_PX + 4 * ES * l16;
+        load4<TP>(xm, g.flags & 1, v00); load4<TP>(xm + MAIN_PX, g.flags & 2, v01);
+        load4<TP>(xm + (long long)q.W * MAIN_PX, g.flags & 4, v10); load4<TP>(xm + ((long long)q.W + 1) * MAIN_PX, g.flags & 8, v11);
+        const float d00 = dot4(gc, v00), d01 = dot4(gc, v01), d10 = dot4(gc, v10), d11 = dot4(gc, v11);
+        const float hh = 1.0f - g.lh, hw = 1.0f - g.lw;
+        const float w00 = hh * hw, w01 = hh * g.lw, w10 = g.lh * hw, w11 = g.lh * g.lw;
+        float r_m = live ? (w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11) : 0.0f;
+        float r_dy = g.mk * (g.lw * (d11 - d01) + hw * (d10 - d00));
+        float r_dx = g.mk * (g.lh * (d11 - d10) + hh * (d01 - d00));
+        if (q.gx) {
+          const float m[4] = {gc[0] * g.mk, gc[1] * g.mk, gc[2] * g.mk, gc[3] * g.mk};
+          left(top, live && (g.flags & 1), g.pix00, w00, m);
+          left(bot, live && (g.flags & 4), g.pix00 + q.W, w10, m);
+          right(top, live && (g.flags & 2), g.pix00 + 1, w01, m);
+          right(bot, live && (g.flags & 8), g.pix00 + q.W + 1, w11, m);
+        }
+#pragma unroll
+        for (int sh = 8; sh >= 1; sh >>= 1) {                   // stays inside the half-warp
+          r_m += __shfl_xor_sync(0xffffffffu, r_m, sh);
+          r_dy += __shfl_xor_sync(0xffffffffu, r_dy, sh);
+          r_dx += __shfl_xor_sync(0xffffffffu, r_dx, sh);
+        }
+        if (l16 == 0) { s.part[0][idx] += r_m; s.part[1][idx] += r_dy; s.part[2][idx] += r_dx; }
+      }
+      if (q.gx) { flush(top); flush(bot); }
     }
   }
   __syncthreads();
