@@ -1,8 +1,10 @@
 // dcn_simt.cu -- modulated deformable convolution (DCNv2, 3x3 / s1 / p1 / d1 / one group) in fp32 on the CUDA cores.
 //
 // This is the PARITY path (VFI_DCN_MATH_FP32): fp32 gather in torchvision's operation order and an fp32 FFMA
-// contraction, so results sit within ~1e-6 of torchvision's fp32 kernels (bar: max-abs 1e-5).  It is also the
-// only backward implementation in this round.  The throughput path is dcn_tc.cu (bf16 operands, tcgen05/TMEM).
+// contraction, so results sit within ~1e-6 of torchvision's fp32 kernels (bar: max-abs 1e-5).  It holds the fp32 forward,
+// the fp32 weight gradient and the generic (any C <= 72, any strides) data gradient; the Python host prefers the
+// column-gradient form of the data gradient (dcn_bwd_cols.cuh) whenever C <= 68.  The throughput path is dcn_tc.cu
+// (bf16 operands, tcgen05/TMEM).
 //
 // Replaces torchvision::deform_conv2d / _deform_conv2d_backward as reached from
 // /root/reference/src/models/ema_vfi.py:60 (geometry :45-51).  Arithmetic: SURVEY.md Appendix B.

@@ -1,5 +1,14 @@
-// dcn_tc.cu -- DCNv2 forward as a tcgen05 / TMEM implicit GEMM for sm_100a (bf16 operands, fp32 accumulate).
+// dcn_tc.cu -- DCNv2 on the tensor cores of sm_100a (bf16 operands, fp32 accumulate): the translation unit of the throughput path.
 //
+// What lives here:   host side of every tensor-core entry point (dispatch, argument checks, workspace layout), the weight and
+//                    input packers, the v4 forward kernel described below, and the tcgen05 self test;
+// dcn_tc6.cuh        the DEFAULT forward kernel (v6): A operand written to tensor memory by the gather warps, source box
+//                    staged in shared memory -- its header describes the design; v4 is kept for the HQ blend, C > 68 and
+//                    offset tensors v6 cannot stream;
+// dcn_tc6_wgrad.cuh  weight / bias gradient (pixel-reduction GEMM, accumulators persistent in tensor memory);
+// dcn_bwd_cols.cuh   input / offset / mask gradients from the column gradient (no tensor-core work; shares the packers).
+//
+// ---- v4 forward kernel (this file) ----
 // Replaces torchvision::deform_conv2d (call site /root/reference/src/models/ema_vfi.py:60) on the throughput path.
 // torchvision materialises columns[603, P] in HBM (40 GB fp32 at 1080p batch 8) and calls a BLAS GEMM; here the
 // modulated bilinear im2col is the A-operand PRODUCER of the GEMM and never leaves the SM:
