@@ -501,6 +501,42 @@ def test_dcn_data_grads_from_column_gradient(B, H, W, sigma):
     assert relerr(x.grad, x2.grad) <= 2e-2 and relerr(off.grad, off2.grad) <= 2e-2 and relerr(m.grad, m2.grad) <= 2e-2
 
 
+def test_dcn_training_gradients_config3_full_size_vs_stock_torchvision_cuda():
+    """BASELINE config 3 at full size (16 x 67 x 256 x 256, forward + backward of one DCNv2 layer): all five gradients of
+    (a) the fp32 path and (b) the bf16 tensor-core training path (tcgen05 forward and weight gradient, column-gradient
+    data backward, channels_last tensors) against stock torchvision's CUDA kernels in fp32 on the same bf16-rounded
+    operands.  Stock grad_x uses fp32 atomics in a different order, hence the relative bars."""
+    B, C, H, W = 16, 67, 256, 256
+    g = torch.Generator(device=DEV).manual_seed(303)
+    bf = torch.bfloat16
+    x = torch.randn(B, C, H, W, device=DEV, generator=g).to(bf)
+    off = (1.5 * torch.randn(B, 18, H, W, device=DEV, generator=g)).to(bf)
+    m = torch.sigmoid(torch.randn(B, 9, H, W, device=DEV, generator=g)).to(bf)
+    w = ((torch.rand(C, C, 3, 3, device=DEV, generator=g) * 2 - 1) / 603 ** 0.5).to(bf)
+    b = ((torch.rand(C, device=DEV, generator=g) * 2 - 1) / 603 ** 0.5).to(bf)
+    go = torch.randn(B, C, H, W, device=DEV, generator=g).to(bf)
+
+    def grads(fn, dt, fmt):
+        leaves = [t.to(dt).contiguous(memory_format=fmt).requires_grad_(True) if t.dim() == 4 and t.shape[-1] == W
+                  else t.to(dt).requires_grad_(True) for t in (x, off, m, w, b)]
+        out = fn(*leaves)
+        out.backward(go.to(dt).contiguous(memory_format=fmt))
+        return out.detach().float(), [t.grad.float() for t in leaves]
+
+    ref_out, ref = grads(lambda x_, o_, m_, w_, b_: torch_ref.dcn_stock(x_, o_, m_, w_, b_), torch.float32, torch.contiguous_format)
+    out32, g32 = grads(lambda x_, o_, m_, w_, b_: vfi_b200.deform_conv2d(x_, o_, w_, b_, stride=1, padding=1, dilation=1, mask=m_,
+                                                                          math="fp32"), torch.float32, torch.contiguous_format)
+    out16, g16 = grads(lambda x_, o_, m_, w_, b_: vfi_b200.deform_conv2d(x_, o_, w_, b_, stride=1, padding=1, dilation=1, mask=m_,
+                                                                          math="bf16_tc"), bf, torch.channels_last)
+    names = ("grad_x", "grad_offset", "grad_mask", "grad_weight", "grad_bias")
+    assert maxabs(out32, ref_out) <= 1e-5 * max(1.0, float(ref_out.abs().max()))
+    assert relerr(out16, ref_out) <= 1e-2
+    for a, r, n in zip(g32, ref, names):
+        assert relerr(a, r) <= 1e-4, n          # summation order over 1 M pixels (weights) / atomics (x)
+    for a, r, n in zip(g16, ref, names):
+        assert relerr(a, r) <= 2e-2, n
+
+
 def test_dcn_tensor_core_path_1080p_vs_fp32_kernel():
     """Full 1080p frame: tcgen05 result against this library's fp32 parity kernel on the same bf16-rounded inputs."""
     g = torch.Generator(device=DEV).manual_seed(41)
