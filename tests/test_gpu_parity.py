@@ -179,6 +179,26 @@ def test_warp_full_size_properties_1080p_batch8_and_4k():
         torch.cuda.empty_cache()
 
 
+def test_warp_backward_config3_full_size_vs_stock_cuda():
+    """BASELINE config 3 at full size (16 x 3 x 256 x 256, forward + backward): grad_flow and grad_frame against autograd
+    through the stock aten::grid_sampler_2d kernels driven the way the reference drives them (oracle/torch_ref.warp on
+    CUDA).  division="reciprocal" replays the CUDA path's coordinate arithmetic, so the bar is the fp32 one; the flow
+    gradient is a difference of neighbouring pixels times grad_out, scaled by max|ref|."""
+    g = torch.Generator(device=DEV).manual_seed(77)
+    src = torch.randn(16, 3, 256, 256, device=DEV, generator=g)
+    flow = 6.0 * torch.randn(16, 2, 256, 256, device=DEV, generator=g)
+    go = torch.randn(16, 3, 256, 256, device=DEV, generator=g)
+    s1, f1 = src.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    out = vfi_b200.warp(s1, f1, division="reciprocal")
+    out.backward(go)
+    s2, f2 = src.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    ref = torch_ref.warp(s2, f2)
+    ref.backward(go)
+    assert maxabs(out, ref) <= 1e-5
+    assert maxabs(f1.grad, f2.grad) <= tol(f2.grad, 2e-5)
+    assert maxabs(s1.grad, s2.grad) <= tol(s2.grad, 2e-5)
+
+
 # ------------------------------------------------------------------------------------------------------------ DCN
 def run_dcn(z, dtype=torch.float32, math="auto", grads=True):
     t = {k: cu(z[k], dtype if k in ("x", "offset", "mask", "weight", "bias", "grad_out") else None) for k in z}
