@@ -511,6 +511,16 @@ def test_dcn_data_grads_from_column_gradient(B, H, W, sigma):
     assert torch.equal(out3, out)
     out3.backward(cu(z["grad_out"], bf).contiguous(memory_format=cl))
     assert relerr(x3.grad, x.grad) <= 1e-2 and relerr(off3.grad, off.grad) <= 1e-3 and relerr(m3.grad, m.grad) <= 1e-3
+    # fp32 tensors with math="bf16_tc" (the unmodified fp32 model opting into the tensor cores): operands are rounded inside
+    # (activations / weights to bf16, offsets / mask to fp16), gradients come back fp32 and take the same kernels
+    leaves = [cu(z[k]).requires_grad_(True) for k in ("x", "offset", "mask", "weight", "bias")]
+    out5 = vfi_b200.deform_conv2d(leaves[0], leaves[1], leaves[3], leaves[4], stride=1, padding=1, dilation=1, mask=leaves[2],
+                                  math="bf16_tc")
+    out5.backward(cu(z["grad_out"]))
+    f16 = lambda a: torch.from_numpy(a).half().float().numpy()     # the oracle samples where the kernels sample
+    ref5 = oracle.dcn_bwd(bf16_round(z["grad_out"]), bf16_round(z["x"]), f16(z["offset"]), f16(z["mask"]), bf16_round(z["weight"]))
+    for t, r in zip(leaves, ref5):
+        assert t.grad.dtype == torch.float32 and relerr(t.grad, r) <= 2e-2
     # the fp32 CUDA-core kernel on the same operands agrees to the same bar
     x2 = cu(z["x"], bf).float().requires_grad_(True)
     off2 = cu(z["offset"], bf).float().requires_grad_(True)

@@ -254,12 +254,19 @@ class _DcnFn(torch.autograd.Function):
         dev = require_cuda(x, offset, mask, weight, bias)
         B, C, H, W = x.shape
         O = weight.shape[0]
+        ctx.offset_dtype, ctx.mask_dtype = offset.dtype, mask.dtype       # gradients go back in the callers' dtypes
         if offset.dtype != mask.dtype:
             mask = mask.to(offset.dtype)
         weight_c = weight.contiguous()
         bias_c = None if bias is None else bias.contiguous()
         lib = _lib.load()
         tc = math in (_lib.MATH_BF16_TC, _lib.MATH_BF16_TC_HQ) or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
+        if tc and math != _lib.MATH_BF16_TC_HQ and offset.dtype == torch.float32:
+            # The staged-box kernels (forward v6, weight gradient) read 16-bit offsets / masks.  fp16 keeps a sampling position
+            # to 2^-11 of the offset (0.004 px at 8 px) -- far inside what rounding the activations to bf16 costs -- and is what
+            # the reference's own autocast path hands over; the HQ mode keeps fp32 offsets and the v4 kernel.
+            offset = offset.clamp(-30000.0, 30000.0).half()
+            mask = mask.half()
         if tc and offset.dtype != torch.float32:
             # the staged-box kernels (forward v6, weight gradient) stream offset / mask rows with bulk copies: unit pixel
             # stride.  A channels_last offset_conv output (layers 2 and 3 under channels_last training) costs one 54 B/px copy
@@ -333,8 +340,8 @@ class _DcnFn(torch.autograd.Function):
                 check(lib.vfi_dcn_bwd_weight(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O,
                                              gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
                                              stream_handle(dev)), "vfi_dcn_bwd_weight")
-        return (gx.to(x.dtype) if need_x else None, goff.to(offset.dtype) if need_off else None,
-                gmask.to(mask.dtype) if need_mask else None, gw.to(weight.dtype) if need_w else None,
+        return (gx.to(x.dtype) if need_x else None, goff.to(ctx.offset_dtype) if need_off else None,
+                gmask.to(ctx.mask_dtype) if need_mask else None, gw.to(weight.dtype) if need_w else None,
                 gb.to(ctx.bias_dtype) if need_b else None, None)
 
 
