@@ -197,6 +197,11 @@ def test_warp_backward_config3_full_size_vs_stock_cuda():
     assert maxabs(out, ref) <= 1e-5
     assert maxabs(f1.grad, f2.grad) <= tol(f2.grad, 2e-5)
     assert maxabs(s1.grad, s2.grad) <= tol(s2.grad, 2e-5)
+    # the model path differentiates with respect to the flow only: that takes the fast kernel (clamped 2 x 2 patch,
+    # re-slotted corners) -- bit-identical to the generic kernel's grad_flow, edges included (|flow| up to ~25 px here)
+    f3 = flow.clone().requires_grad_(True)
+    vfi_b200.warp(src, f3, division="reciprocal").backward(go)
+    assert torch.equal(f3.grad, f1.grad)
 
 
 # ------------------------------------------------------------------------------------------------------------ DCN

@@ -342,6 +342,54 @@ __global__ void __launch_bounds__(256) warp_bwd_kernel(const WarpBwdParams q) {
   gf[q.gf_sc] = __fmul_rn(p.ay.recip ? __fmul_rn(ggy, p.ay.inv_denom) : __fdiv_rn(ggy, p.ay.denom), 2.0f);
 }
 
+// ------------------------------------------------------------------------------------------------ backward, fast path
+// grad_flow of the model path (EMA_VFI.warp is differentiated with respect to the flow only: frame2 is an input image):
+// C = 3 planar frames, unit pixel strides, no grad_src.  Same treatment as the forward fast path -- lanes are consecutive
+// pixels, the 2 x 2 patch is clamped into the frame as a whole so all twelve gathers are unconditional and in flight
+// together; corners outside the frame are then ZEROED by re-slotting (the generic kernel skips their loads), so the
+// expression below is the generic kernel's, operand for operand.
+template <typename TS, typename TF, typename TG, bool RECIP>
+__global__ void __launch_bounds__(WARPF_BLOCK) warp_bwd_fast_kernel(const WarpBwdParams q) {
+  const WarpParams& p = q.f;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = blockIdx.x * WARPF_BLOCK + threadIdx.x;
+  if (x >= p.W) return;
+  const int H = p.H, W = p.W, pitch = (int)p.s_sh;
+  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn + (long long)y * p.f_sh + x;
+  const float ix = warp_coord_t<RECIP>(x, to_f32<TF>(__ldcs(fl)), p.ax);
+  const float iy = warp_coord_t<RECIP>(y, to_f32<TF>(__ldcs(fl + p.f_sc)), p.ay);
+  const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);
+  const float x0f = (float)x0, y0f = (float)y0;
+  const float wx1 = ix - x0f, wx0 = (x0f + 1.0f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.0f) - iy;
+  const int xc = min(max(x0, 0), W - 2), yc = min(max(y0, 0), H - 2);
+  const int dx = x0 - xc, dy = y0 - yc;       // 0 inside; -1 / +1: the patch hangs over the low / high edge by one pixel
+  const unsigned o = (unsigned)(yc * pitch + xc);
+  const TS* s0 = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
+  const TG* go = reinterpret_cast<const TG*>(q.gout) + b * q.go_sn + (long long)y * q.go_sh + x;
+  float v[3][4], g[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const TS* q0 = s0 + c * p.s_sc + o;
+    v[c][0] = ldg_f32(q0); v[c][1] = ldg_f32(q0 + 1); v[c][2] = ldg_f32(q0 + pitch); v[c][3] = ldg_f32(q0 + pitch + 1);
+    g[c] = to_f32<TG>(__ldcs(go + c * q.go_sc));
+  }
+  float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // rows first (top / bottom of the true patch), then columns
+    const float tl = dy == 0 ? v[c][0] : (dy == 1 ? v[c][2] : 0.0f), tr = dy == 0 ? v[c][1] : (dy == 1 ? v[c][3] : 0.0f);
+    const float bl = dy == 0 ? v[c][2] : (dy == -1 ? v[c][0] : 0.0f), br = dy == 0 ? v[c][3] : (dy == -1 ? v[c][1] : 0.0f);
+    const float nw = dx == 0 ? tl : (dx == 1 ? tr : 0.0f), ne = dx == 0 ? tr : (dx == -1 ? tl : 0.0f);
+    const float sw = dx == 0 ? bl : (dx == 1 ? br : 0.0f), se = dx == 0 ? br : (dx == -1 ? bl : 0.0f);
+    gix += ((ne - nw) * wy0 + (se - sw) * wy1) * g[c];
+    giy += ((sw - nw) * wx0 + (se - ne) * wx1) * g[c];
+  }
+  float* gf = q.gflow + b * q.gf_sn + (long long)y * q.gf_sh + x;
+  const float ggx = __fmul_rn(q.mult_x, gix), ggy = __fmul_rn(q.mult_y, giy);
+  __stcs(gf, __fmul_rn(RECIP ? __fmul_rn(ggx, p.ax.inv_denom) : __fdiv_rn(ggx, p.ax.denom), 2.0f));
+  __stcs(gf + q.gf_sc, __fmul_rn(RECIP ? __fmul_rn(ggy, p.ay.inv_denom) : __fdiv_rn(ggy, p.ay.denom), 2.0f));
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int check_common(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, const char* who) {
   VFI_REQUIRE(src && flow && out, VFI_ERR_INVALID, "%s: null tensor descriptor", who);
@@ -513,6 +561,25 @@ extern "C" int vfi_warp_bwd(const vfi_tensor* grad_out, const vfi_tensor* src, c
   long long total = (long long)src->n * src->h * src->w;
   int blocks = ceil_div(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fast = !grad_src && src->c == 3 && src->sw == 1 && flow->sw == 1 && grad_out->sw == 1 && grad_flow->sw == 1 &&
+                    src->h >= 2 && src->w >= 2 && src->sh >= 0 && src->n <= 65535 && src->h <= 65535;
+  if (fast) {
+    dim3 grid(ceil_div(src->w, WARPF_BLOCK), (unsigned)src->h, (unsigned)src->n);
+    const bool recip = q.f.ax.recip != 0;
+    VFI_DISPATCH(src->dtype, TS, {
+      VFI_DISPATCH(grad_out->dtype, TG, {
+        if (flow->dtype == VFI_F32) {
+          if (recip) warp_bwd_fast_kernel<TS, float, TG, true><<<grid, WARPF_BLOCK, 0, st>>>(q);
+          else warp_bwd_fast_kernel<TS, float, TG, false><<<grid, WARPF_BLOCK, 0, st>>>(q);
+        } else {
+          if (recip) warp_bwd_fast_kernel<TS, TS, TG, true><<<grid, WARPF_BLOCK, 0, st>>>(q);
+          else warp_bwd_fast_kernel<TS, TS, TG, false><<<grid, WARPF_BLOCK, 0, st>>>(q);
+        }
+      });
+    });
+    VFI_LAUNCH_CHECK("warp_bwd_fast_kernel");
+    return VFI_OK;
+  }
   VFI_DISPATCH(src->dtype, TS, {
     VFI_DISPATCH(grad_out->dtype, TG, {
       if (flow->dtype == VFI_F32) warp_bwd_kernel<TS, float, TG><<<blocks, 256, 0, st>>>(q);
