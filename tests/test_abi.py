@@ -85,6 +85,24 @@ def test_abi_argument_validation_without_a_gpu():
     rc = lib.vfi_dcn_fwd(ctypes.byref(x), ctypes.byref(off), ctypes.byref(m), 1, 0, None, 0, ctypes.byref(out), 100,
                          _lib.MATH_FP32, 1, 1 << 20, None)
     assert rc == 2 and b"at most 72" in lib.vfi_last_error()
+    # the training entry points reject what they do not take before touching the device
+    x67 = _lib.VfiTensor(256, 2, 0, 1, 67, 8, 16, 67 * 128, 128, 16, 1)           # bf16 [1,67,8,16]
+    off16 = _lib.VfiTensor(256, 2, 0, 1, 18, 8, 16, 18 * 128, 128, 16, 1)
+    m16 = _lib.VfiTensor(256, 2, 0, 1, 9, 8, 16, 9 * 128, 128, 16, 1)
+    rc = lib.vfi_dcn_bwd_data_cols(256, 1, 640, ctypes.byref(x67), ctypes.byref(off16), ctypes.byref(m16), None, 68, None, None,
+                                   None, 0, None)
+    assert rc == 1 and b"gcol rows must hold 9 x 72" in lib.vfi_last_error()
+    rc = lib.vfi_dcn_bwd_data_cols(256, 2, 648, ctypes.byref(x67), ctypes.byref(off16), ctypes.byref(m16), None, 68, None, None,
+                                   None, 0, None)                            # f16 columns
+    assert rc == 2 and b"gcol must be bf16 or f32" in lib.vfi_last_error()
+    rc = lib.vfi_dcn_bwd_data_cols(256, 1, 648, ctypes.byref(x67), ctypes.byref(off16), ctypes.byref(m16), 256, 68,
+                                   None, None, None, 0, None)
+    assert rc != 0 and b"workspace" in lib.vfi_last_error()
+    assert lib.vfi_dcn_bwd_data_cols_workspace_bytes(1, 8, 16, 0) >= 128 * 72 * 4 > lib.vfi_dcn_bwd_data_cols_workspace_bytes(1, 8, 16, 1) >= 128 * 72 * 2
+    xf = _lib.VfiTensor(256, 2, 0, 1, 100, 8, 16, 100 * 128, 128, 16, 1)
+    rc = lib.vfi_dcn_bwd_weight_tc(ctypes.byref(xf), ctypes.byref(xf), ctypes.byref(off16), ctypes.byref(m16), 100, None, None,
+                                   None, 0, None)
+    assert rc == 2 and b"supports C <=" in lib.vfi_last_error()
 
 
 def test_dropin_patches_and_restores_both_seams():
