@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "fp16_offsets or smoke" 2>&1 | tail -3
+[ -n "$SKIP_TESTS" ] || timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "fp16_offsets or smoke" 2>&1 | tail -3
 for w in cfg4 cfg1; do
   timeout 600 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo "$w exit $?"
   python -c "
