@@ -280,6 +280,30 @@ def main():
         planar_ms[name] = e0.elapsed_time(e1) / 20
         del f2, fl
 
+    # same kernel, SURVEY section 8d flow class (i): the flow a random-init EMA_VFI produces, N(0, 0.03^2) px.  The
+    # headline flow above (class ii, 0.25 px/px of shear) spreads one request over ~7 source rows; this one streams.
+    model_like = {}
+    try:
+        gm = torch.Generator(device=dev).manual_seed(77)
+        fl32 = 0.03 * torch.randn(B, 2, H, W, device=dev, generator=gm)
+        for name, dt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
+            f2, fl = frame2.to(dt), fl32.to(dt)
+            for _ in range(3):
+                orig_warp(f2, fl)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(20):
+                orig_warp(f2, fl)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            model_like[name] = e0.elapsed_time(e1) / 20
+            del f2, fl
+        del fl32
+    except Exception as exc:   # an extra evidence line must never break the headline
+        print(f"bench: model-like-flow warp timing skipped: {exc}", file=sys.stderr)
+        model_like = {}
+
     # the fused warp + blend extension (no reference counterpart): two frames, two flows, one mask, bf16
     blend_ms = None
     try:
@@ -368,6 +392,14 @@ def main():
                                       "ms_per_launch": warp_ms, "achieved": warp_gbs, "frac": warp_gbs / pk["hbm"]}},
         "clocks": clocks,
     }
+    if model_like.get("bf16") and model_like.get("f32"):
+        wb = P * WARP_BYTES_PER_PX_BF16
+        line["roofline_warp"]["model_like_flow"] = {
+            "flow": "iid N(0, 0.03^2) px (SURVEY 8d class i: what a random-init model produces), 20 launches each",
+            "bf16": {"ms_per_launch": model_like["bf16"], "achieved": wb / (model_like["bf16"] * 1e-3) / 1e9,
+                     "frac": wb / (model_like["bf16"] * 1e-3) / 1e9 / pk["hbm"]},
+            "f32": {"ms_per_launch": model_like["f32"], "achieved": 2 * wb / (model_like["f32"] * 1e-3) / 1e9,
+                    "frac": 2 * wb / (model_like["f32"] * 1e-3) / 1e9 / pk["hbm"]}}
     if blend_ms:
         bl_bytes = P * (2 * 3 + 2 * 2 + 1 + 3) * 2
         line["roofline_blend"] = {"bound": "hbm", "kernel": "warp_blend (two planar bf16 frames + two flows + mask -> blended frame, 20 launches)",

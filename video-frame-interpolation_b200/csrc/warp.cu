@@ -147,7 +147,13 @@ __global__ void __launch_bounds__(WARP_BLOCK) warp_fwd_kernel(const WarpParams p
 //     are re-slotted / zeroed for patches hanging over an edge (zeros padding), so all twelve gathers of a pixel are
 //     unconditional, in flight together, and ten of them use immediate offsets.
 // Arithmetic per corner and the coordinate replay are those of the generic kernel (warp_math.h), bit for bit.
-constexpr int WARPF_BLOCK = 128;
+#ifndef VFI_WARPF_BLOCK
+#define VFI_WARPF_BLOCK 128
+#endif
+#ifndef VFI_WARPF_PPT
+#define VFI_WARPF_PPT 2
+#endif
+constexpr int WARPF_BLOCK = VFI_WARPF_BLOCK;
 
 template <bool RECIP> __device__ __forceinline__ float warp_coord_t(int pix, float disp, const WarpAxis& ax) {
   float g = VFI_MUL(2.0f, VFI_ADD((float)pix, disp));
@@ -186,7 +192,7 @@ __device__ __forceinline__ void sample3(const TS* s0, const TS* s1, const TS* s2
   r[0] = lerp(s0); r[1] = lerp(s1); r[2] = lerp(s2);
 }
 
-constexpr int WARPF_PPT = 2;                      // pixels per thread, one block apart (x, x + 128)
+constexpr int WARPF_PPT = VFI_WARPF_PPT;                      // pixels per thread, one block apart (x, x + 128)
 
 // Lanes are CONSECUTIVE pixels: the 2-byte gathers of a warp then span ~64 bytes + the flow's variation, i.e. one or two
 // 128-byte lines per request.  (A thread owning two ADJACENT pixels halves the flow / store requests but doubles that span;
