@@ -1,0 +1,276 @@
+"""Frame-pair streaming around the hot path (BASELINE config 5).
+
+The reference's video loop (/root/reference/inference.py:160-199) runs the model on one pair at a time, converts every
+frame on the CPU (`process_frame`, :45-49: ToTensor + Normalize), and blocks on a device->host copy per written frame
+(`denormalize_frame`, :52-58).  With the hot path on the GPU that loop is host-bound.  This module keeps its *output
+stream* -- the same frames, in the same order, bit for bit -- and changes how it is produced:
+
+* ``plan_stream`` restates the loop's control flow as data: which frame pairs go through the model and what is written in
+  which order (including the reference's quirks: the prediction of a pair is written ``interpolation_factor`` times, the
+  first frame of a pair is written *after* its predictions and as the normalise -> denormalise round trip of the frame,
+  the very last frame is written raw).
+* ``PairStreamer`` shards the pairs over ranks (independent units, no collective: ``shard.shard_pairs``), batches them,
+  moves uint8 frames through pinned double buffers on a copy stream, does normalise / denormalise on the device in the
+  reference's arithmetic (fp32 ToTensor + Normalize; float64 de-normalisation as numpy does at :55-57), and reads results
+  back as uint8 on a second copy stream, so H2D of batch i+1, the model on batch i and D2H of batch i-1 overlap and the
+  only host synchronisation is one event per batch.
+
+The model is whatever the caller hands over (the reference's ``EMA_VFI`` with ``vfi_b200.install()`` applied, in
+practice).  Nothing here computes the hot path: the warp / DCN kernels are reached through the model's own call sites.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import shard
+
+MEAN = (0.485, 0.456, 0.406)          # inference.py:38-41 (applied to the channels as cv2 delivers them)
+STD = (0.229, 0.224, 0.225)
+
+PRED, ROUND_TRIP, RAW = "pred", "round_trip", "raw"
+
+
+@dataclass(frozen=True)
+class Emit:
+    """One written frame: ``pred`` = model output of pair ``index``; ``round_trip`` = denormalise(normalise(frame
+    ``index``)) (inference.py:184-185, :195); ``raw`` = frame ``index`` as read (:166)."""
+    kind: str
+    index: int
+
+
+def plan_stream(num_frames: int, frame_interval: int = 1, interpolation_factor: int = 1) -> Tuple[List[Tuple[int, int]], List[Emit]]:
+    """Control flow of inference.py:139-199 for a video of ``num_frames`` readable frames, as data.
+
+    Returns ``(pairs, emits)``: ``pairs[k] = (i, j)`` are the frame indices of the k-th model call's inputs; ``emits`` is the
+    output stream in writing order.  ``interpolation_factor`` is what :103-117 derive from the frame rates.
+    """
+    if num_frames < 0 or frame_interval < 1 or interpolation_factor < 0:
+        raise ValueError("num_frames >= 0, frame_interval >= 1, interpolation_factor >= 0 required")
+    pairs: List[Tuple[int, int]] = []
+    emits: List[Emit] = []
+    if num_frames == 0:                       # :146-150 "video is empty": nothing is written
+        return pairs, emits
+    first, frame_num, nxt = 0, 0, 1           # frame1 index, the loop counter, the next frame cap.read() returns
+    while True:
+        frame_num += 1
+        ok = nxt < num_frames
+        if frame_num % frame_interval == 0:
+            if not ok:
+                emits.append(Emit(RAW, first))                    # :166 out.write(frame1)
+                break
+            pairs.append((first, nxt))
+            emits.extend(Emit(PRED, len(pairs) - 1) for _ in range(interpolation_factor))   # :172-182
+            emits.append(Emit(ROUND_TRIP, first))                 # :184-185
+            first = nxt
+        else:
+            if not ok:
+                emits.append(Emit(ROUND_TRIP, first))             # :195-196
+                break
+            first = nxt                                           # :190-193: the frame is skipped
+        nxt += 1
+    return pairs, emits
+
+
+def normalize_u8(frames_u8: torch.Tensor) -> torch.Tensor:
+    """[N,H,W,3] uint8 -> [N,3,H,W] fp32, the arithmetic of ToTensor (x / 255) + Normalize ((x - mean) / std)."""
+    # division by a device TENSOR: torch's CUDA kernel for a Python-scalar divisor multiplies by 1/255 instead, which is
+    # one ulp away from ToTensor's IEEE division for some levels (measured on the B200: 1 LSB in the written frames)
+    x = frames_u8.permute(0, 3, 1, 2).to(torch.float32)
+    x = x.div_(torch.full((), 255.0, dtype=torch.float32, device=x.device))
+    mean = torch.tensor(MEAN, dtype=torch.float32, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(STD, dtype=torch.float32, device=x.device).view(1, 3, 1, 1)
+    return x.sub_(mean).div_(std)
+
+
+def denormalize_u8(x: torch.Tensor) -> torch.Tensor:
+    """[N,3,H,W] any float dtype -> [N,H,W,3] uint8 as inference.py:52-58: fp32 values times float64 constants, clip, * 255,
+    truncation."""
+    y = x.float().permute(0, 2, 3, 1).to(torch.float64)
+    std = torch.tensor(STD, dtype=torch.float64, device=x.device)
+    mean = torch.tensor(MEAN, dtype=torch.float64, device=x.device)
+    y = (y * std + mean).clamp_(0, 1).mul_(255)
+    return y.to(torch.uint8)
+
+
+def _rows(t: torch.Tensor, idx: List[int]) -> torch.Tensor:
+    """Rows ``idx`` of ``t``: a view when they are consecutive (the usual case: pairs (i, i+1), (i+1, i+2), ...), so no index
+    tensor has to cross to the device; a gather otherwise."""
+    if idx and idx == list(range(idx[0], idx[0] + len(idx))):
+        return t[idx[0]:idx[0] + len(idx)]
+    return t[torch.tensor(idx, dtype=torch.long, device=t.device)]
+
+
+class _Slot:
+    """One pinned staging area: uint8 frames in, uint8 results out, and the events that guard their reuse."""
+
+    def __init__(self, n_in: int, n_out: int, H: int, W: int, cuda: bool):
+        mk = (lambda *s: torch.empty(s, dtype=torch.uint8).pin_memory()) if cuda else (lambda *s: torch.empty(s, dtype=torch.uint8))
+        self.h_in = mk(n_in, H, W, 3)
+        self.h_out = mk(n_out, H, W, 3)
+        self.done: Optional[torch.cuda.Event] = None
+
+
+class PairStreamer:
+    """Runs ``model(frame1, frame2)`` over the pairs of a frame sequence and yields the reference's output stream.
+
+    ``frames``: a sequence of [H,W,3] uint8 arrays (already resized, inference.py:47).  ``batch_pairs`` pairs per model
+    call (the reference uses 1).  ``topology``: this rank's place in a ``world``-rank job; each rank computes a
+    contiguous chunk of the pairs; ``run`` yields only the written frames this rank owns, ``run_all`` returns the full
+    stream on every rank after one host-side object gather.
+    """
+
+    def __init__(self, model: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], device, *, batch_pairs: int = 8,
+                 topology: Optional[shard.Topology] = None, autocast_dtype: Optional[torch.dtype] = None):
+        self.model = model
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        if batch_pairs < 1:
+            raise ValueError("batch_pairs must be >= 1")
+        self.batch_pairs = batch_pairs
+        self.topo = topology or shard.Topology(0, 1, 0)
+        self.autocast_dtype = autocast_dtype
+        self._streams = None
+        self.stats: Dict[str, int] = {"model_calls": 0, "h2d_bytes": 0, "d2h_bytes": 0, "frames_uploaded": 0}
+
+    # ------------------------------------------------------------------------------------------ ownership
+    def owned_pairs(self, num_pairs: int) -> List[int]:
+        return shard.shard_pairs(num_pairs, self.topo.rank, self.topo.world, mode="contiguous")
+
+    @staticmethod
+    def emit_owner(e: Emit, start_of: Dict[int, int], owner_of_pair: Sequence[int]) -> int:
+        """Rank that produces an emit: predictions and the round trip of a pair's first frame belong to the pair's owner;
+        the closing frame (no pair starts at it) belongs to the owner of the last pair, or rank 0 when there is none.
+        ``start_of[f]`` = the pair whose first frame is ``f``."""
+        if e.kind == PRED:
+            return owner_of_pair[e.index]
+        if e.index in start_of:
+            return owner_of_pair[start_of[e.index]]
+        return owner_of_pair[-1] if owner_of_pair else 0
+
+    # ------------------------------------------------------------------------------------------ the loop
+    def _model(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        self.stats["model_calls"] += 1
+        with torch.no_grad():
+            if self.autocast_dtype is not None:
+                with torch.autocast(self.device.type, dtype=self.autocast_dtype):
+                    return self.model(a, b)
+            return self.model(a, b)
+
+    def run(self, frames: Sequence[np.ndarray], frame_interval: int = 1, interpolation_factor: int = 1) -> Iterator[Tuple[int, np.ndarray]]:
+        """Yields ``(position, frame)`` for every emit this rank owns, in increasing position (= index into the reference's
+        output stream)."""
+        pairs, emits = plan_stream(len(frames), frame_interval, interpolation_factor)
+        world = self.topo.world
+        owner_of_pair = [0] * len(pairs)
+        for r in range(world):
+            for k in shard.shard_pairs(len(pairs), r, world, mode="contiguous"):
+                owner_of_pair[k] = r
+        start_of = {i: k for k, (i, _) in enumerate(pairs)}
+        mine = [(pos, e) for pos, e in enumerate(emits) if self.emit_owner(e, start_of, owner_of_pair) == self.topo.rank]
+        if not mine:
+            return
+        H, W = frames[0].shape[:2]
+        my_pairs = [k for k in range(len(pairs)) if owner_of_pair[k] == self.topo.rank]
+        # emits grouped by the batch that produces them: a batch = up to batch_pairs consecutive owned pairs
+        batches = list(shard.batches(my_pairs, self.batch_pairs)) or [[]]
+        batch_of_pair = {k: bi for bi, ks in enumerate(batches) for k in ks}
+        per_batch: List[List[Tuple[int, Emit]]] = [[] for _ in batches]
+        for pos, e in mine:
+            if e.kind == PRED:
+                per_batch[batch_of_pair[e.index]].append((pos, e))
+            else:
+                k = start_of.get(e.index)
+                per_batch[batch_of_pair[k] if k in batch_of_pair else len(batches) - 1].append((pos, e))
+
+        n_in_max = 2 * self.batch_pairs + 1
+        slots = [_Slot(n_in_max, n_in_max + self.batch_pairs, H, W, self.cuda) for _ in range(2)]
+        if self.cuda and self._streams is None:
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        pending: Optional[Tuple[_Slot, List[Tuple[int, int]]]] = None       # (slot, [(position, row of h_out)])
+
+        def drain(p):
+            slot, rows = p
+            if slot.done is not None:
+                slot.done.synchronize()              # the one host wait per batch
+            for pos, row in rows:
+                yield pos, slot.h_out[row].numpy().copy()
+
+        for bi, ks in enumerate(batches):
+            slot = slots[bi % 2]
+            # frames this batch touches: the pairs' inputs plus any raw / round-trip frame it writes, each uploaded once
+            need: List[int] = []
+            for k in ks:
+                need.extend(pairs[k])
+            need.extend(e.index for _, e in per_batch[bi] if e.kind != PRED)
+            uniq = sorted(set(need))
+            row_of = {f: i for i, f in enumerate(uniq)}
+            for f, i in row_of.items():
+                fr = frames[f]
+                if fr.shape != (H, W, 3) or fr.dtype != np.uint8:
+                    raise ValueError(f"frame {f}: expected uint8 [{H},{W},3], got {fr.dtype} {fr.shape}")
+                slot.h_in[i].copy_(torch.from_numpy(np.ascontiguousarray(fr)))
+            n_in = len(uniq)
+            self.stats["frames_uploaded"] += n_in
+            self.stats["h2d_bytes"] += n_in * H * W * 3
+            if self.cuda:
+                s_in, s_out = self._streams
+                cur = torch.cuda.current_stream(self.device)
+                with torch.cuda.stream(s_in):
+                    d_u8 = slot.h_in[:n_in].to(self.device, non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record(s_in)
+                cur.wait_event(up)
+                d_u8.record_stream(cur)
+            else:
+                d_u8 = slot.h_in[:n_in].clone()
+            x = normalize_u8(d_u8)
+            outs: List[torch.Tensor] = []
+            rows: List[Tuple[int, int]] = []
+            if ks:
+                a = _rows(x, [row_of[pairs[k][0]] for k in ks])
+                b = _rows(x, [row_of[pairs[k][1]] for k in ks])
+                pred = denormalize_u8(self._model(a, b))
+                outs.append(pred)
+            pred_row = {k: i for i, k in enumerate(ks)}
+            rt_frames = sorted({e.index for _, e in per_batch[bi] if e.kind == ROUND_TRIP})
+            if rt_frames:
+                outs.append(denormalize_u8(_rows(x, [row_of[f] for f in rt_frames])))
+            rt_row = {f: len(ks) + i for i, f in enumerate(rt_frames)}
+            raw_frames = sorted({e.index for _, e in per_batch[bi] if e.kind == RAW})
+            if raw_frames:
+                outs.append(_rows(d_u8, [row_of[f] for f in raw_frames]))
+            raw_row = {f: len(ks) + len(rt_frames) + i for i, f in enumerate(raw_frames)}
+            for pos, e in per_batch[bi]:
+                rows.append((pos, pred_row[e.index] if e.kind == PRED else rt_row[e.index] if e.kind == ROUND_TRIP else raw_row[e.index]))
+            res = torch.cat(outs, 0) if outs else None
+            # drain the previous batch only now: its D2H ran while this batch was staged and enqueued
+            if pending is not None:
+                yield from drain(pending)
+                pending = None
+            if res is not None:
+                n_out = res.shape[0]
+                self.stats["d2h_bytes"] += n_out * H * W * 3
+                if self.cuda:
+                    ready = torch.cuda.Event()
+                    ready.record(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ready)
+                        slot.h_out[:n_out].copy_(res, non_blocking=True)
+                        res.record_stream(s_out)
+                        slot.done = torch.cuda.Event()
+                        slot.done.record(s_out)
+                else:
+                    slot.h_out[:n_out].copy_(res)
+                pending = (slot, sorted(rows))
+        if pending is not None:
+            yield from drain(pending)
+
+    def run_all(self, frames: Sequence[np.ndarray], frame_interval: int = 1, interpolation_factor: int = 1) -> List[np.ndarray]:
+        """The whole output stream on every rank (host-side gather by position; single process: no communication)."""
+        local = dict(self.run(frames, frame_interval, interpolation_factor))
+        merged = shard.gather_by_index(local, self.topo.world)
+        return [merged[i] for i in range(len(merged))]
