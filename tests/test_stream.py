@@ -214,3 +214,25 @@ def test_stream_on_device_equals_reference_loop():
     diff = max(int(np.abs(g.astype(np.int16) - w.astype(np.int16)).max()) for g, w in zip(got, want))
     assert diff == 0, diff
     assert s.stats["model_calls"] == 5 and s.stats["d2h_bytes"] > 0, s.stats
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
+def test_stream_with_the_reference_model_on_cpu():
+    """The unmodified EMA_VFI (random init, eval, CPU) through the streamer against the reference loop: batch 1 performs the
+    same model calls, so the written frames are identical; batches of 3 may pick different CPU conv kernels (at most one
+    uint8 level)."""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.ema_vfi import EMA_VFI
+    finally:
+        sys.path.remove("/root/reference")
+    torch.manual_seed(0)
+    model = EMA_VFI().eval()
+    frames = _frames(5, 24, 32, seed=8)
+    want = reference_loop(frames, model, 1, 1)
+    got1 = stream.PairStreamer(model, "cpu", batch_pairs=1).run_all(frames, 1, 1)
+    assert len(got1) == len(want) and all(np.array_equal(a, b) for a, b in zip(got1, want))
+    got3 = stream.PairStreamer(model, "cpu", batch_pairs=3).run_all(frames, 1, 1)
+    worst = max(int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max()) for a, b in zip(got3, want))
+    assert worst <= 1, worst
