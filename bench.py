@@ -34,7 +34,10 @@ WORKLOADS = {
     "cfg2": (8, 1080, 1920, 8.0, 1.5, "cfg2: 1080p (1920x1080) frame pairs, batch 8 per GPU, bf16, warp + concat + 3 x DCNv2 fwd"),
     "cfg4": (1, 2160, 3840, 64.0, 1.5, "cfg4: 4K (3840x2160) frame pair, batch 1, bf16, large-displacement flow"),
     "cfg1": (1, 256, 256, 8.0, 1.5, "cfg1 geometry: 256x256, batch 1 (hot path only)"),
+    # cfg2's shapes; the e2e leg streams STREAM_PAIRS independent pairs from pinned host memory, sharded over the ranks
+    "cfg5": (8, 1080, 1920, 8.0, 1.5, "cfg5: stream of 256 independent 1080p frame pairs in batches of 8, sharded over the ranks, bf16"),
 }
+STREAM_PAIRS = 256
 FLOP_PER_PX = 2 * 603 * 67          # one DCNv2 layer, algorithmic; padding not counted
 WARP_BYTES_PER_PX_BF16 = (3 + 2 + 3) * 2
 
@@ -335,6 +338,9 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in (hf2, hflow, hfeat, *hconvs))
         d2h = hout.numel() * hout.element_size()
         n_e2e = args.e2e_steps or min(args.steps, 5)
+        if args.workload == "cfg5":
+            # every rank streams its contiguous share of the pairs (vfi_b200.shard.shard_pairs), one run_host call per batch
+            n_e2e = max(1, -(-len(shard.shard_pairs(STREAM_PAIRS, topo.rank, world, "contiguous")) // B))
         path.run_host(hf2, hflow, hfeat, hconvs, hout)          # warm-up (stream creation, allocator)
         barrier()
         t0 = time.perf_counter()
