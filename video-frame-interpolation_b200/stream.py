@@ -16,7 +16,10 @@ stream* -- the same frames, in the same order, bit for bit -- and changes how it
   only host synchronisation is one event per batch.
 
 The model is whatever the caller hands over (the reference's ``EMA_VFI`` with ``vfi_b200.install()`` applied, in
-practice).  Nothing here computes the hot path: the warp / DCN kernels are reached through the model's own call sites.
+practice).  Nothing here computes the hot path: the warp / DCN kernels are reached through the model's own call sites,
+and they refuse CPU tensors (``ops.require_cuda``).  This module is host plumbing only -- scheduling, staging, ordering --
+which is why it also accepts ``device="cpu"``: that is how tests/test_stream.py covers the N > 1 ownership logic over gloo
+without a GPU, with a stand-in model; it is not a fallback for the kernels.
 """
 from __future__ import annotations
 
