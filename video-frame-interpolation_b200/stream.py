@@ -17,7 +17,7 @@ stream* -- the same frames, in the same order, bit for bit -- and changes how it
 
 The model is whatever the caller hands over (the reference's ``EMA_VFI`` with ``vfi_b200.install()`` applied, in
 practice).  Nothing here computes the hot path: the warp / DCN kernels are reached through the model's own call sites,
-and they refuse CPU tensors (``ops.require_cuda``).  This module is host plumbing only -- scheduling, staging, ordering --
+and they refuse CPU tensors (``_lib.require_cuda``).  This module is host plumbing only -- scheduling, staging, ordering --
 which is why it also accepts ``device="cpu"``: that is how tests/test_stream.py covers the N > 1 ownership logic over gloo
 without a GPU, with a stand-in model; it is not a fallback for the kernels.
 """
