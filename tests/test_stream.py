@@ -236,3 +236,27 @@ def test_stream_with_the_reference_model_on_cpu():
     got3 = stream.PairStreamer(model, "cpu", batch_pairs=3).run_all(frames, 1, 1)
     worst = max(int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max()) for a, b in zip(got3, want))
     assert worst <= 1, worst
+
+
+def test_fuzz_plan_ownership_and_stream():
+    """Random (frames, interval, factor, batch, world): the union of the ranks' shares is the reference's stream."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(n=st.integers(0, 14), interval=st.integers(1, 4), factor=st.integers(0, 3), batch=st.integers(1, 5),
+               world=st.integers(1, 4), seed=st.integers(0, 99))
+    def check(n, interval, factor, batch, world, seed):
+        frames = _frames(n, 4, 6, seed=seed)
+        want = reference_loop(frames, fake_model, interval, factor)
+        merged = {}
+        for r in range(world):
+            s = stream.PairStreamer(fake_model, "cpu", batch_pairs=batch, topology=shard.Topology(r, world, r))
+            got = list(s.run(frames, interval, factor))
+            assert [p for p, _ in got] == sorted(p for p, _ in got)         # each rank yields in stream order
+            assert not (set(p for p, _ in got) & set(merged))
+            merged.update(got)
+        assert sorted(merged) == list(range(len(want)))
+        assert all(np.array_equal(merged[i], want[i]) for i in range(len(want)))
+
+    check()
