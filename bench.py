@@ -37,6 +37,9 @@ WORKLOADS = {
     # cfg2's shapes; the e2e leg streams STREAM_PAIRS independent pairs from pinned host memory, sharded over the ranks
     "cfg5": (8, 1080, 1920, 8.0, 1.5, "cfg5: stream of 256 independent 1080p frame pairs in batches of 8, sharded over the ranks, bf16"),
 }
+# SURVEY 8d (iii), worst-case locality: per-pixel independent displacements (not timed in round 1)
+WORKLOADS["cfg4_iid"] = (1, 2160, 3840, 64.0, 1.5, "cfg4, incoherent variant: 4K frame pair, batch 1, bf16, iid N(0, 64^2) px flow")
+FLOW_KIND = {"cfg4_iid": "iid"}          # everything else: the smooth field of hotpath.synthetic_inputs
 STREAM_PAIRS = 256
 FLOP_PER_PX = 2 * 603 * 67          # one DCNv2 layer, algorithmic; padding not counted
 WARP_BYTES_PER_PX_BF16 = (3 + 2 + 3) * 2
@@ -206,7 +209,8 @@ def main():
     ws, bs = synthetic_weights(dtype=dtype, device=dev)
     path = HotPath(ws, bs, math=args.math)
     frame2, flow, feat, convs = synthetic_inputs(B, H, W, dtype=dtype, device=dev, seed=1234 + topo.rank,
-                                                 flow_sigma=flow_sigma, offset_sigma=off_sigma)
+                                                 flow_sigma=flow_sigma, offset_sigma=off_sigma,
+                                                 flow_kind=FLOW_KIND.get(args.workload, "smooth"))
     feat = feat.contiguous(memory_format=torch.channels_last)
     if args.conv27_layout == "channels_last":
         convs = [c.contiguous(memory_format=torch.channels_last) for c in convs]
@@ -331,7 +335,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         hf2, hflow, hfeat, hconvs = synthetic_inputs(B, H, W, dtype=dtype, seed=99 + topo.rank, flow_sigma=flow_sigma,
-                                                     offset_sigma=off_sigma, pinned_host=True)
+                                                     offset_sigma=off_sigma, pinned_host=True,
+                                                     flow_kind=FLOW_KIND.get(args.workload, "smooth"))
         if args.conv27_layout == "channels_last":
             hconvs = [c.contiguous(memory_format=torch.channels_last).pin_memory() for c in hconvs]
         hout = torch.empty((B, 67, H, W), dtype=dtype).pin_memory()
