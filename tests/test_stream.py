@@ -214,6 +214,8 @@ def test_stream_on_device_equals_reference_loop():
     diff = max(int(np.abs(g.astype(np.int16) - w.astype(np.int16)).max()) for g, w in zip(got, want))
     assert diff == 0, diff
     assert s.stats["model_calls"] == 5 and s.stats["d2h_bytes"] > 0, s.stats
+    it = dict(stream.PairStreamer(model, "cuda:0", batch_pairs=4).run_iter(iter(frames), 1, 2))     # same loop, planned as it arrives
+    assert sorted(it) == list(range(len(want))) and all(np.array_equal(it[i], want[i]) for i in range(len(want)))
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
@@ -260,3 +262,62 @@ def test_fuzz_plan_ownership_and_stream():
         assert all(np.array_equal(merged[i], want[i]) for i in range(len(want)))
 
     check()
+
+
+@pytest.mark.parametrize("batch_pairs", [1, 3, 8])
+@pytest.mark.parametrize("interval,factor", [(1, 1), (1, 2), (2, 1), (3, 2), (1, 0)])
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 12])
+def test_unbounded_stream_equals_reference_loop(n, interval, factor, batch_pairs):
+    frames = _frames(n, seed=20 + n)
+    want = reference_loop(frames, fake_model, interval, factor)
+    s = stream.PairStreamer(fake_model, "cpu", batch_pairs=batch_pairs)
+    got = list(s.run_iter((f for f in frames), interval, factor))          # a generator: no len(), one pass
+    assert [p for p, _ in got] == list(range(len(want)))
+    assert all(np.array_equal(g, w) for (_, g), w in zip(got, want))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("n,interval", [(1, 1), (2, 1), (9, 1), (11, 2), (30, 1)])
+def test_unbounded_stream_ranks_partition_by_batches(n, interval, world):
+    frames = _frames(n, seed=n + 1)
+    want = reference_loop(frames, fake_model, interval, 2)
+    merged = {}
+    for r in range(world):
+        s = stream.PairStreamer(fake_model, "cpu", batch_pairs=2, topology=shard.Topology(r, world, r))
+        mine = dict(s.run_iter(iter(frames), interval, 2))
+        assert not (set(mine) & set(merged))
+        merged.update(mine)
+    assert sorted(merged) == list(range(len(want)))
+    assert all(np.array_equal(merged[i], want[i]) for i in range(len(want)))
+
+
+def test_unbounded_stream_holds_a_bounded_number_of_frames():
+    import gc
+    import weakref
+    refs, peak = [], [0]
+
+    def source(n):
+        rng = np.random.default_rng(0)
+        for _ in range(n):
+            gc.collect()
+            peak[0] = max(peak[0], sum(r() is not None for r in refs))
+            f = rng.integers(0, 256, size=(4, 6, 3), dtype=np.uint8)
+            refs.append(weakref.ref(f))
+            yield f
+            del f
+
+    s = stream.PairStreamer(fake_model, "cpu", batch_pairs=3)
+    n_out = sum(1 for _ in s.run_iter(source(60), 1, 1))
+    assert n_out == 59 * 2 + 1
+    assert peak[0] <= 2 * 3 + 1, peak[0]                 # the batch being executed (batch_pairs + 1) + the open one, which share a frame
+
+
+def test_planner_is_incremental():
+    pl = stream.StreamPlanner(2, 1)
+    assert pl.push(0) == (None, [])
+    assert pl.push(1) == (None, [])                       # frame_num 1: skipped, replaces frame1
+    pair, out = pl.push(2)                                # frame_num 2: a pair (1, 2)
+    assert pair == (1, 2) and [(p, e.kind, e.index) for p, e in out] == [(0, stream.PRED, 0), (1, stream.ROUND_TRIP, 1)]
+    assert [(p, e.kind, e.index) for p, e in pl.finish()] == [(2, stream.ROUND_TRIP, 2)]
+    with pytest.raises(ValueError):
+        stream.StreamPlanner(0, 1)

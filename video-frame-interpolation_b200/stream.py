@@ -45,36 +45,68 @@ class Emit:
     index: int
 
 
+class StreamPlanner:
+    """The control flow of inference.py:139-199, one read frame at a time (so a stream of unknown length can be planned as it
+    arrives).  ``push(i)`` stands for a successful ``cap.read()`` returning frame ``i``; ``finish()`` for the failed read that
+    ends the video.  Both return what the loop writes at that point as ``(position, Emit)``; ``push`` also returns the frame
+    pair handed to the model, if any.  Pairs are numbered in the order they appear (``Emit(PRED, k)`` = the k-th pair)."""
+
+    def __init__(self, frame_interval: int = 1, interpolation_factor: int = 1):
+        if frame_interval < 1 or interpolation_factor < 0:
+            raise ValueError("frame_interval >= 1, interpolation_factor >= 0 required")
+        self.interval, self.factor = frame_interval, interpolation_factor
+        self.first: Optional[int] = None      # index of the loop's frame1
+        self.frame_num = 0                    # the loop counter (:161)
+        self.n_pairs = 0
+        self.position = 0                     # frames written so far
+
+    def _emit(self, out: List[Tuple[int, "Emit"]], kind: str, index: int) -> None:
+        out.append((self.position, Emit(kind, index)))
+        self.position += 1
+
+    def push(self, index: int) -> Tuple[Optional[Tuple[int, int]], List[Tuple[int, "Emit"]]]:
+        out: List[Tuple[int, Emit]] = []
+        if self.first is None:                                    # :139-144, the read before the loop
+            self.first = index
+            return None, out
+        self.frame_num += 1
+        if self.frame_num % self.interval:                        # :188-193: the frame replaces frame1, nothing is written
+            self.first = index
+            return None, out
+        pair = (self.first, index)
+        for _ in range(self.factor):                              # :172-182
+            self._emit(out, PRED, self.n_pairs)
+        self._emit(out, ROUND_TRIP, self.first)                   # :184-185
+        self.n_pairs += 1
+        self.first = index
+        return pair, out
+
+    def finish(self) -> List[Tuple[int, "Emit"]]:
+        out: List[Tuple[int, Emit]] = []
+        if self.first is None:                                    # :146-150 "video is empty": nothing is written
+            return out
+        self.frame_num += 1
+        self._emit(out, ROUND_TRIP if self.frame_num % self.interval else RAW, self.first)   # :195-196 / :166
+        return out
+
+
 def plan_stream(num_frames: int, frame_interval: int = 1, interpolation_factor: int = 1) -> Tuple[List[Tuple[int, int]], List[Emit]]:
     """Control flow of inference.py:139-199 for a video of ``num_frames`` readable frames, as data.
 
     Returns ``(pairs, emits)``: ``pairs[k] = (i, j)`` are the frame indices of the k-th model call's inputs; ``emits`` is the
     output stream in writing order.  ``interpolation_factor`` is what :103-117 derive from the frame rates.
     """
-    if num_frames < 0 or frame_interval < 1 or interpolation_factor < 0:
-        raise ValueError("num_frames >= 0, frame_interval >= 1, interpolation_factor >= 0 required")
+    if num_frames < 0:
+        raise ValueError("num_frames >= 0 required")
+    planner = StreamPlanner(frame_interval, interpolation_factor)
     pairs: List[Tuple[int, int]] = []
     emits: List[Emit] = []
-    if num_frames == 0:                       # :146-150 "video is empty": nothing is written
-        return pairs, emits
-    first, frame_num, nxt = 0, 0, 1           # frame1 index, the loop counter, the next frame cap.read() returns
-    while True:
-        frame_num += 1
-        ok = nxt < num_frames
-        if frame_num % frame_interval == 0:
-            if not ok:
-                emits.append(Emit(RAW, first))                    # :166 out.write(frame1)
-                break
-            pairs.append((first, nxt))
-            emits.extend(Emit(PRED, len(pairs) - 1) for _ in range(interpolation_factor))   # :172-182
-            emits.append(Emit(ROUND_TRIP, first))                 # :184-185
-            first = nxt
-        else:
-            if not ok:
-                emits.append(Emit(ROUND_TRIP, first))             # :195-196
-                break
-            first = nxt                                           # :190-193: the frame is skipped
-        nxt += 1
+    for i in range(num_frames):
+        pair, out = planner.push(i)
+        if pair is not None:
+            pairs.append(pair)
+        emits.extend(e for _, e in out)
+    emits.extend(e for _, e in planner.finish())
     return pairs, emits
 
 
@@ -176,7 +208,6 @@ class PairStreamer:
         mine = [(pos, e) for pos, e in enumerate(emits) if self.emit_owner(e, start_of, owner_of_pair) == self.topo.rank]
         if not mine:
             return
-        H, W = frames[0].shape[:2]
         my_pairs = [k for k in range(len(pairs)) if owner_of_pair[k] == self.topo.rank]
         # emits grouped by the batch that produces them: a batch = up to batch_pairs consecutive owned pairs
         batches = list(shard.batches(my_pairs, self.batch_pairs)) or [[]]
@@ -189,8 +220,53 @@ class PairStreamer:
                 k = start_of.get(e.index)
                 per_batch[batch_of_pair[k] if k in batch_of_pair else len(batches) - 1].append((pos, e))
 
-        n_in_max = 2 * self.batch_pairs + 1
-        slots = [_Slot(n_in_max, n_in_max + self.batch_pairs, H, W, self.cuda) for _ in range(2)]
+        items = []
+        for bi, ks in enumerate(batches):
+            local = {k: i for i, k in enumerate(ks)}
+            items.append(([pairs[k] for k in ks],
+                          [(pos, Emit(PRED, local[e.index]) if e.kind == PRED else e) for pos, e in per_batch[bi]], frames))
+        yield from self._execute(items)
+
+    def run_iter(self, frames, frame_interval: int = 1, interpolation_factor: int = 1) -> Iterator[Tuple[int, np.ndarray]]:
+        """``run`` for a stream of unknown length: ``frames`` is any iterable of [H,W,3] uint8 arrays, planned as it arrives
+        (``StreamPlanner``), so at most ``2 * batch_pairs + 1`` frames are held (the batch in flight and the open one).  Without the total, ranks take *batches* of
+        ``batch_pairs`` consecutive pairs round-robin (batch b -> rank b % world); every rank walks the whole iterable and stages
+        only its own batches.  The closing frame goes with the last batch."""
+        planner = StreamPlanner(frame_interval, interpolation_factor)
+        rank, world = self.topo.rank, self.topo.world
+
+        def items():
+            held: Dict[int, np.ndarray] = {}
+            plist: List[Tuple[int, int]] = []
+            elist: List[Tuple[int, Emit]] = []
+            batch_no, last_owner = 0, 0
+            for idx, fr in enumerate(frames):
+                held[idx] = fr
+                pair, out = planner.push(idx)
+                if pair is not None:
+                    plist.append(pair)
+                    elist.extend((pos, Emit(PRED, len(plist) - 1) if e.kind == PRED else e) for pos, e in out)
+                    if len(plist) == self.batch_pairs:
+                        last_owner = batch_no % world
+                        if last_owner == rank:
+                            yield plist, elist, dict(held)
+                        batch_no += 1
+                        plist, elist = [], []
+                keep = {planner.first} | {f for pr in plist for f in pr}
+                for f in [f for f in held if f not in keep]:
+                    del held[f]
+            closing = planner.finish()
+            owner = batch_no % world if plist else last_owner
+            if owner == rank and (plist or closing):
+                yield plist, elist + closing, held
+
+        yield from self._execute(items())
+
+    def _execute(self, items) -> Iterator[Tuple[int, np.ndarray]]:
+        """The double-buffered loop.  ``items`` yields ``(pairs, emits, frames)`` per batch: frame-index pairs for one model call,
+        the ``(position, Emit)`` this batch writes (``Emit(PRED, i)`` = the i-th pair of the batch), and a frame lookup."""
+        slots: Optional[List[_Slot]] = None
+        H = W = 0
         if self.cuda and self._streams is None:
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         pending: Optional[Tuple[_Slot, List[Tuple[int, int]]]] = None       # (slot, [(position, row of h_out)])
@@ -202,17 +278,21 @@ class PairStreamer:
             for pos, row in rows:
                 yield pos, slot.h_out[row].numpy().copy()
 
-        for bi, ks in enumerate(batches):
-            slot = slots[bi % 2]
+        for bi, (plist, elist, lookup) in enumerate(items):
             # frames this batch touches: the pairs' inputs plus any raw / round-trip frame it writes, each uploaded once
             need: List[int] = []
-            for k in ks:
-                need.extend(pairs[k])
-            need.extend(e.index for _, e in per_batch[bi] if e.kind != PRED)
+            for pr in plist:
+                need.extend(pr)
+            need.extend(e.index for _, e in elist if e.kind != PRED)
             uniq = sorted(set(need))
+            if slots is None:
+                H, W = lookup[uniq[0]].shape[:2]
+                n_in_max = 2 * self.batch_pairs + 1
+                slots = [_Slot(n_in_max, n_in_max + self.batch_pairs, H, W, self.cuda) for _ in range(2)]
+            slot = slots[bi % 2]
             row_of = {f: i for i, f in enumerate(uniq)}
             for f, i in row_of.items():
-                fr = frames[f]
+                fr = lookup[f]
                 if fr.shape != (H, W, 3) or fr.dtype != np.uint8:
                     raise ValueError(f"frame {f}: expected uint8 [{H},{W},3], got {fr.dtype} {fr.shape}")
                 slot.h_in[i].copy_(torch.from_numpy(np.ascontiguousarray(fr)))
@@ -233,22 +313,21 @@ class PairStreamer:
             x = normalize_u8(d_u8)
             outs: List[torch.Tensor] = []
             rows: List[Tuple[int, int]] = []
-            if ks:
-                a = _rows(x, [row_of[pairs[k][0]] for k in ks])
-                b = _rows(x, [row_of[pairs[k][1]] for k in ks])
+            if plist:
+                a = _rows(x, [row_of[i] for i, _ in plist])
+                b = _rows(x, [row_of[j] for _, j in plist])
                 pred = denormalize_u8(self._model(a, b))
                 outs.append(pred)
-            pred_row = {k: i for i, k in enumerate(ks)}
-            rt_frames = sorted({e.index for _, e in per_batch[bi] if e.kind == ROUND_TRIP})
+            rt_frames = sorted({e.index for _, e in elist if e.kind == ROUND_TRIP})
             if rt_frames:
                 outs.append(denormalize_u8(_rows(x, [row_of[f] for f in rt_frames])))
-            rt_row = {f: len(ks) + i for i, f in enumerate(rt_frames)}
-            raw_frames = sorted({e.index for _, e in per_batch[bi] if e.kind == RAW})
+            rt_row = {f: len(plist) + i for i, f in enumerate(rt_frames)}
+            raw_frames = sorted({e.index for _, e in elist if e.kind == RAW})
             if raw_frames:
                 outs.append(_rows(d_u8, [row_of[f] for f in raw_frames]))
-            raw_row = {f: len(ks) + len(rt_frames) + i for i, f in enumerate(raw_frames)}
-            for pos, e in per_batch[bi]:
-                rows.append((pos, pred_row[e.index] if e.kind == PRED else rt_row[e.index] if e.kind == ROUND_TRIP else raw_row[e.index]))
+            raw_row = {f: len(plist) + len(rt_frames) + i for i, f in enumerate(raw_frames)}
+            for pos, e in elist:
+                rows.append((pos, e.index if e.kind == PRED else rt_row[e.index] if e.kind == ROUND_TRIP else raw_row[e.index]))
             res = torch.cat(outs, 0) if outs else None
             # drain the previous batch only now: its D2H ran while this batch was staged and enqueued
             if pending is not None:
