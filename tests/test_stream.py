@@ -321,3 +321,67 @@ def test_planner_is_incremental():
     assert [(p, e.kind, e.index) for p, e in pl.finish()] == [(2, stream.ROUND_TRIP, 2)]
     with pytest.raises(ValueError):
         stream.StreamPlanner(0, 1)
+
+
+def test_choose_interpolation_factor_follows_the_script():
+    assert stream.choose_interpolation_factor(30.0, None, 4) == (1, 60.0)
+    assert stream.choose_interpolation_factor(24.0, None, 4)[0] == 1          # |48-60| = |72-60|: the first wins
+    assert stream.choose_interpolation_factor(15.0, None, 4) == (3, 60.0)
+    assert stream.choose_interpolation_factor(25.0, 100.0, 4) == (3, 100.0)
+    assert stream.choose_interpolation_factor(25.0, 60.0, 4) == (1, 50.0)     # round(1.4) = 1, target capped at 50
+
+
+def _read_video(path):
+    import cv2
+    cap, frames = cv2.VideoCapture(str(path)), []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    fps = cap.get(cv2.CAP_PROP_FPS)
+    cap.release()
+    return fps, frames
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("interval,n_frames", [(1, 6), (2, 7)])
+def test_stream_video_writes_what_the_unmodified_inference_script_writes(tmp_path, interval, n_frames):
+    """The reference's inference.py, run byte-for-byte unmodified (runpy, --device cpu, random-init checkpoint), against
+    ``stream_video`` with the same model: the two output files decode to identical frames at the same frame rate."""
+    import runpy
+    import sys
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    src = tmp_path / "in.avi"
+    w = cv2.VideoWriter(str(src), cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (64, 48))
+    base = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    for i in range(n_frames):
+        w.write(np.roll(base, 3 * i, axis=1))
+    w.release()
+
+    sys.path.insert(0, "/root/reference")
+    argv, dont = sys.argv, sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        from src.models.ema_vfi import EMA_VFI
+        torch.manual_seed(1)
+        model = EMA_VFI().eval()
+        ckpt = tmp_path / "m.pth"
+        torch.save(model.state_dict(), ckpt)
+        ref_out = tmp_path / "ref.avi"
+        sys.argv = ["inference.py", "--input_video", str(src), "--output_video", str(ref_out), "--model_path", str(ckpt),
+                    "--device", "cpu", "--codec", "MJPG", "--frame_interval", str(interval), "--scale", "0.5"]
+        runpy.run_path("/root/reference/inference.py", run_name="__main__")
+    finally:
+        sys.argv, sys.dont_write_bytecode = argv, dont
+        sys.path.remove("/root/reference")
+
+    ours_out = tmp_path / "ours.avi"
+    n = stream.stream_video(str(src), str(ours_out), model, "cpu", codec="MJPG", frame_interval=interval, scale=0.5, batch_pairs=1)
+    fps_r, fr = _read_video(ref_out)
+    fps_o, fo = _read_video(ours_out)
+    assert len(fr) > n_frames // interval and n == len(fo) == len(fr) and fps_r == fps_o
+    assert all(np.array_equal(a, b) for a, b in zip(fr, fo))
+    with pytest.raises(ValueError):
+        stream.stream_video(str(tmp_path / "missing.avi"), str(ours_out), model, "cpu")

@@ -356,3 +356,113 @@ class PairStreamer:
         local = dict(self.run(frames, frame_interval, interpolation_factor))
         merged = shard.gather_by_index(local, self.topo.world)
         return [merged[i] for i in range(len(merged))]
+
+
+# ------------------------------------------------------------------------------------------------ video in / video out
+def choose_interpolation_factor(fps: float, target_fps: Optional[float], max_interpolation_factor: int = 4) -> Tuple[int, float]:
+    """inference.py:103-123: the factor whose output rate is closest to 60 fps when no target is given (first wins on ties),
+    ``round(target / fps - 1)`` otherwise; the target is capped at what the factor can deliver."""
+    if target_fps is None:
+        best, best_diff = 0, float("inf")
+        for k in range(1, max_interpolation_factor + 1):
+            diff = abs(fps * (k + 1) - 60)
+            if diff < best_diff:
+                best, best_diff = k, diff
+        factor, target_fps = best, fps * (best + 1)
+    else:
+        factor = round(target_fps / fps - 1)
+    return factor, min(target_fps, fps * (factor + 1))
+
+
+def stream_video(input_video_path: str, output_video_path: str, model, device, *, target_fps: Optional[float] = None,
+                 max_interpolation_factor: int = 4, frame_interval: int = 1, codec: str = "mp4v", scale: float = 0.5,
+                 batch_pairs: int = 8, autocast_dtype: Optional[torch.dtype] = None, queue_depth: int = 32) -> int:
+    """``interpolate_video`` of inference.py:60-205 with the frame loop replaced by ``PairStreamer.run_iter``: same arguments
+    (the model object instead of a checkpoint path), same file written.  Decoding + resizing (:47) and encoding run in
+    their own threads behind bounded queues, so they overlap the copies and the model.  Returns the number of frames written.
+    A video that cannot be opened raises ``ValueError`` (the reference logs the same message and returns)."""
+    import queue
+    import threading
+
+    import cv2
+
+    cap = cv2.VideoCapture(input_video_path)
+    if not cap.isOpened():
+        raise ValueError(f"cannot open video file: {input_video_path}")
+    fps = cap.get(cv2.CAP_PROP_FPS)
+    new_w = int(int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) * scale)        # :86-93
+    new_h = int(int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)) * scale)
+    factor, target_fps = choose_interpolation_factor(fps, target_fps, max_interpolation_factor)
+    out = cv2.VideoWriter(output_video_path, cv2.VideoWriter_fourcc(*codec), target_fps, (new_w, new_h))   # :127-128
+
+    END = object()
+    q_in: "queue.Queue" = queue.Queue(maxsize=queue_depth)
+    q_out: "queue.Queue" = queue.Queue(maxsize=queue_depth)
+    errors: List[BaseException] = []
+    stop = threading.Event()
+
+    def put(q, item) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def decode():
+        try:
+            while not stop.is_set():
+                ok, frame = cap.read()
+                if not ok:
+                    break
+                if not put(q_in, cv2.resize(frame, (new_w, new_h))):
+                    return
+        except BaseException as e:  # noqa: BLE001 - handed to the caller's thread
+            errors.append(e)
+        finally:
+            put(q_in, END)
+
+    def encode():
+        try:
+            while True:
+                item = q_out.get()
+                if item is END:
+                    return
+                out.write(item)
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            stop.set()
+
+    def frames():
+        while True:
+            item = q_in.get()
+            if item is END:
+                return
+            yield item
+
+    t_dec, t_enc = threading.Thread(target=decode, daemon=True), threading.Thread(target=encode, daemon=True)
+    t_dec.start()
+    t_enc.start()
+    written = 0
+    try:
+        streamer = PairStreamer(model, device, batch_pairs=batch_pairs, autocast_dtype=autocast_dtype)
+        for _, frame in streamer.run_iter(frames(), frame_interval, factor):
+            if not put(q_out, frame):
+                break
+            written += 1
+    finally:
+        if not put(q_out, END):
+            stop.set()
+            try:
+                q_out.put_nowait(END)
+            except queue.Full:
+                pass
+        t_enc.join(timeout=60)
+        stop.set()
+        t_dec.join(timeout=10)
+        cap.release()
+        out.release()
+    if errors:
+        raise errors[0]
+    return written
