@@ -1,0 +1,243 @@
+// Gather-only microbenchmark of the DCNv2 forward's A-operand producers (csrc/dcn_tc6.cuh): what does the SM's load/store
+// data path give when NOTHING but the compulsory gather runs, and what does each further producer step cost on top?
+//
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o gather_floor gather_floor.cu && ./gather_floor
+//
+// Same staging as the kernel: a zero-padded 18 x 26 pixel source box of 128-byte (64 x bf16) rows in shared memory, the
+// same thread <-> data mapping (lane = (g, u): pixels g and g + 8 of a 16-pixel half, 16-byte chunks u and u + 4 of each
+// of the four bilinear corners, odd g swapped so that every LDS.128 is bank-conflict free), 16 LDS.128 per lane and
+// half = one pixel-tap per lane-pair ... i.e. 36 x 128 B per output pixel for the nine taps.  One persistent CTA per SM.
+//
+// Modes (cumulative):
+//   0 gather   16 LDS.128 per half at pseudo-random box positions, results XOR-folded (no other work)
+//   1 +entry   the sampling position / weights come from 16-byte geometry entries in shared memory (2 LDS.128 per half,
+//              four lanes per entry) as in the kernel
+//   2 +lerp    the packed HFMA2.BF16 blend of the four corners (64 HFMA2 per half)
+//   3 +tmem    results written to tensor memory with tcgen05.st.16x256b.x4, tcgen05.wait::st once per K block
+//   4 +copy    a 21st warp streams the next box (36 bulk copies of 3.3 KB + 0.4 KB) into the other buffer meanwhile
+// Output: clocks per output pixel (nine taps) and the time of one cfg2 layer (16,588,800 px over 148 SMs) at the clock
+// measured during the run, next to the 36 clk/px = 128 B/clk/SM arithmetic floor.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+constexpr int BOX_H = 18, BOX_W = 26, BOX_PX = BOX_H * BOX_W;
+constexpr int MAIN_PX = 128, MAIN_ROW = BOX_W * MAIN_PX;
+constexpr int TAIL_PX = 16;
+constexpr int TILE_PX = 128;
+
+struct __align__(1024) Smem {
+  uint8_t box[2][BOX_PX * MAIN_PX];
+  uint8_t tail[2][BOX_PX * TAIL_PX];
+  uint4 geo[2][9][TILE_PX];
+  unsigned long long bar[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int OFF> __device__ __forceinline__ uint4 lds16o(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a), "n"(OFF));
+  return r;
+}
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const uint2& w) {
+  const __nv_bfloat162 w0 = as_bf162(__byte_perm(w.x, 0, 0x1010)), w1 = as_bf162(__byte_perm(w.x, 0, 0x3232));
+  const __nv_bfloat162 w2 = as_bf162(__byte_perm(w.y, 0, 0x1010)), w3 = as_bf162(__byte_perm(w.y, 0, 0x3232));
+  auto f = [&](uint32_t va, uint32_t vb, uint32_t vc, uint32_t vd) {
+    __nv_bfloat162 r = __hmul2(w0, as_bf162(va));
+    r = __hfma2(w1, as_bf162(vb), r);
+    r = __hfma2(w2, as_bf162(vc), r);
+    r = __hfma2(w3, as_bf162(vd), r);
+    return *reinterpret_cast<uint32_t*>(&r);
+  };
+  return make_uint4(f(a.x, b.x, c.x, d.x), f(a.y, b.y, c.y, d.y), f(a.z, b.z, c.z, d.z), f(a.w, b.w, c.w, d.w));
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// MODE as above; PAT: 0 = i.i.d. positions (sigma ~ 1.5 px around the tap), 1 = all samples of a half in one box row
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) gather_kernel(const uint8_t* __restrict__ gsrc, unsigned long long* out, int kblocks,
+                                                          int producer_warps) {
+  extern __shared__ uint8_t raw[];
+  Smem& s = *reinterpret_cast<Smem*>(raw + ((1024 - (smem_u32(raw) & 1023)) & 1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 2 * BOX_PX * MAIN_PX / 16; i += blockDim.x) reinterpret_cast<uint4*>(&s.box[0][0])[i] = make_uint4(i, i * 3, i * 5, i * 7);
+  // geometry entries: pixel r of the tile (8 x 16) samples tap k near its own position, +- a few pixels (hash)
+  for (int i = tid; i < 2 * 9 * TILE_PX; i += blockDim.x) {
+    const int r = i % TILE_PX, k = (i / TILE_PX) % 9;
+    uint32_t h = (uint32_t)i * 2654435761u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const int dy = (int)(h & 7) - 3, dx = (int)((h >> 3) & 7) - 3;           // [-3, 4]
+    int ry = 4 + r / 16 + k / 3 + dy, rx = 4 + r % 16 + k % 3 + dx;
+    ry = min(max(ry, 0), BOX_H - 2); rx = min(max(rx, 0), BOX_W - 2);
+    reinterpret_cast<uint4*>(&s.geo[0][0][0])[i] = make_uint4((uint32_t)(ry * BOX_W + rx) * MAIN_PX, 0x3e803e80u, 0x3e803e80u, 0u);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s.bar[i])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (MODE >= 3 && warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = MODE >= 3 ? s.tmem_base : 0u;
+  uint32_t acc = 0;
+  const long long t0 = clock64();
+  if (warp < producer_warps) {
+    const int q = warp & 3, g = lane >> 2, u = lane & 3;
+    const bool par = (g & 1) != 0;
+    const uint32_t c_first = (uint32_t)(u + (par ? 4 : 0)) * 16, c_second = (uint32_t)(u + (par ? 0 : 4)) * 16;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t hsh = (uint32_t)(blockIdx.x * 977 + warp * 131 + g * 17) * 2654435761u;
+    for (int n = 0; n < kblocks; ++n) {
+      const int gb = (n / 10) & 1, kb = (n + warp) % 9;
+      const uint32_t bF = smem_u32(&s.box[gb][0]) + c_first, bS = smem_u32(&s.box[gb][0]) + c_second;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 e0, e1;
+        if (MODE >= 1) {
+          e0 = s.geo[gb][kb][q * 32 + h * 16 + g];
+          e1 = s.geo[gb][kb][q * 32 + h * 16 + g + 8];
+        } else {
+          hsh = hsh * 1664525u + 1013904223u;
+          const uint32_t p0 = ((hsh >> 8) & 0xffffu) * (uint32_t)((BOX_H - 1) * BOX_W - 1) >> 16;
+          const uint32_t p1 = ((hsh >> 16) & 0xffffu) * (uint32_t)((BOX_H - 1) * BOX_W - 1) >> 16;
+          e0 = make_uint4(p0 * MAIN_PX, 0x3e803e80u, 0x3e803e80u, 0u);
+          e1 = make_uint4(p1 * MAIN_PX, 0x3e803e80u, 0x3e803e80u, 0u);
+        }
+        uint4 f[4], gg[4], f1[4], g1[4];
+        {
+          const uint32_t aF = bF + e0.x, aS = bS + e0.x;
+          f[0] = lds16o<0>(aF); f[1] = lds16o<MAIN_PX>(aF); f[2] = lds16o<MAIN_ROW>(aF); f[3] = lds16o<MAIN_ROW + MAIN_PX>(aF);
+          gg[0] = lds16o<0>(aS); gg[1] = lds16o<MAIN_PX>(aS); gg[2] = lds16o<MAIN_ROW>(aS); gg[3] = lds16o<MAIN_ROW + MAIN_PX>(aS);
+        }
+        {
+          const uint32_t aF = bF + e1.x, aS = bS + e1.x;
+          f1[0] = lds16o<0>(aF); f1[1] = lds16o<MAIN_PX>(aF); f1[2] = lds16o<MAIN_ROW>(aF); f1[3] = lds16o<MAIN_ROW + MAIN_PX>(aF);
+          g1[0] = lds16o<0>(aS); g1[1] = lds16o<MAIN_PX>(aS); g1[2] = lds16o<MAIN_ROW>(aS); g1[3] = lds16o<MAIN_ROW + MAIN_PX>(aS);
+        }
+        if (MODE >= 2) {
+          const uint4 F0 = lerp_chunk(f[0], f[1], f[2], f[3], make_uint2(e0.y, e0.z));
+          const uint4 S0 = lerp_chunk(gg[0], gg[1], gg[2], gg[3], make_uint2(e0.y, e0.z));
+          const uint4 F1 = lerp_chunk(f1[0], f1[1], f1[2], f1[3], make_uint2(e1.y, e1.z));
+          const uint4 S1 = lerp_chunk(g1[0], g1[1], g1[2], g1[3], make_uint2(e1.y, e1.z));
+          const uint4 X0 = par ? S0 : F0, Y0 = par ? F0 : S0, X1 = par ? S1 : F1, Y1 = par ? F1 : S1;
+          const uint32_t r[16] = {X0.x, X0.y, X1.x, X1.y, X0.z, X0.w, X1.z, X1.w, Y0.x, Y0.y, Y1.x, Y1.y, Y0.z, Y0.w, Y1.z, Y1.w};
+          if (MODE >= 3) {
+            tmem_st_16x256b_x4(tmem_base + lane_base + ((uint32_t)(h * 16) << 16) + (uint32_t)(256 + (n & 7) * 32), r);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc ^= r[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc ^= f[i].x ^ f[i].w ^ gg[i].y ^ gg[i].z ^ f1[i].x ^ f1[i].w ^ g1[i].y ^ g1[i].z;
+        }
+      }
+      if (MODE >= 3) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+    }
+  } else if (MODE >= 4 && warp == producer_warps) {
+    // box streamer: one box per 36 warp-K-blocks of producer work, i.e. kblocks * producer_warps / 36 boxes in all
+    const int boxes = kblocks * producer_warps / 36;
+    for (int it = 0; it < boxes; ++it) {
+      const int sb = it & 1;
+      const uint32_t bar = smem_u32(&s.bar[sb]);
+      if (lane == 0)
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                     "r"((uint32_t)(BOX_PX * (MAIN_PX + TAIL_PX)))
+                     : "memory");
+      __syncwarp();
+      if (lane < BOX_H) {
+        const uint8_t* src = gsrc + ((size_t)((blockIdx.x * 131 + it * 7 + lane) % 4096)) * 4096;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(&s.box[sb][lane * MAIN_ROW])),
+                     "l"(src), "r"((uint32_t)MAIN_ROW), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(&s.tail[sb][lane * BOX_W * TAIL_PX])),
+                     "l"(src), "r"((uint32_t)(BOX_W * TAIL_PX)), "r"(bar)
+                     : "memory");
+      }
+      // wait for this box before issuing the next one into the other buffer (paces the stream like the kernel's double buffer)
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"((uint32_t)(it >> 1) & 1u), "r"(1000u)
+                     : "memory");
+    }
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) out[2] = acc;
+  if (warp < producer_warps && lane == 0) atomicMax(&out[0], (unsigned long long)(t1 - t0));
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (MODE >= 3 && warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+template <int MODE>
+void run(const char* name, const uint8_t* g, unsigned long long* out, int sms, double* floor_ms_out) {
+  const size_t smem = sizeof(Smem) + 1024;
+  cudaFuncSetAttribute(gather_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int warps : {16, 20, 24, 28}) {
+    const int kblocks = 1800;                                          // per warp; 32 pixel-taps each
+    const int threads = (warps + (MODE >= 4 ? 1 : 0)) * 32;
+    float best_ms = 1e30f;
+    unsigned long long cyc = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaMemset(out, 0, 32);
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0);
+      gather_kernel<MODE><<<sms, threads, smem>>>(g, out, kblocks, warps);
+      cudaEventRecord(e1);
+      cudaError_t err = cudaDeviceSynchronize();
+      if (err != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(err)); exit(1); }
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      unsigned long long h[2];
+      cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+      if (ms < best_ms) { best_ms = ms; cyc = h[0]; }
+    }
+    const double pixel_taps = (double)kblocks * warps * 32;            // per SM
+    const double clk_per_px = (double)cyc / pixel_taps * 9.0;
+    const double mhz = (double)cyc / (best_ms * 1e3);                 // clocks / us
+    const double px_per_sm = 16588800.0 / 148.0;
+    const double layer_ms = clk_per_px * px_per_sm / (mhz * 1e3);
+    printf("{\"mode\": \"%s\", \"producer_warps\": %d, \"clk_per_px\": %.2f, \"sm_mhz\": %.0f, \"cfg2_layer_ms\": %.3f, "
+           "\"floor_clk_per_px\": 36.0, \"frac_of_lsu_floor\": %.3f}\n",
+           name, warps, clk_per_px, mhz, layer_ms, 36.0 / clk_per_px);
+    if (floor_ms_out && warps == 20) *floor_ms_out = layer_ms;
+  }
+}
+
+int main() {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  uint8_t* g; unsigned long long* out;
+  cudaMalloc(&g, 4096 * 4096 + 8192); cudaMemset(g, 1, 4096 * 4096 + 8192); cudaMalloc(&out, 32);
+  run<0>("gather", g, out, sms, nullptr);
+  run<1>("gather+entry", g, out, sms, nullptr);
+  run<2>("gather+entry+lerp", g, out, sms, nullptr);
+  run<3>("gather+entry+lerp+tmem_st", g, out, sms, nullptr);
+  run<4>("gather+entry+lerp+tmem_st+box_copy", g, out, sms, nullptr);
+  return 0;
+}
