@@ -1,0 +1,12 @@
+# round 2, call F: batched barrier polling in the geometry / MMA roles; microbenchmark with fewer producer warps
+mkdir -p gpurun_out
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench', d['value'], d['ms_per_step'], d['roofline']['ms_per_launch'])"
+for e in 0 13; do
+  echo "== experiment $e"
+  VFI_DCN_EXPERIMENT=$e timeout 300 python scripts/dcn_debug7.py 2>&1 | tail -8
+done
+timeout 300 python scripts/dcn_ab.py > gpurun_out/dcn_ab5.log 2>&1; echo "dcn_ab exit $?"; grep -A3 mismatches gpurun_out/dcn_ab5.log | head
+true
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -p no:cacheprovider -k "cfg2_full or cfg4_4k or psnr" > gpurun_out/pytest_full.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/pytest_full.log

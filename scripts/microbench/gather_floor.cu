@@ -198,7 +198,7 @@ template <int MODE>
 void run(const char* name, const uint8_t* g, unsigned long long* out, int sms, double* floor_ms_out) {
   const size_t smem = sizeof(Smem) + 1024;
   cudaFuncSetAttribute(gather_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int warps : {16, 20, 24, 28}) {
+  for (int warps : {4, 8, 12, 16, 20, 28}) {
     const int kblocks = 1800;                                          // per warp; 32 pixel-taps each
     const int threads = (warps + (MODE >= 4 ? 1 : 0)) * 32;
     float best_ms = 1e30f;

@@ -604,6 +604,113 @@ def test_hot_path_bf16_tensor_core_vs_fp32_reference_psnr():
     assert relerr(out, x) <= 2e-2     # three chained bf16 layers
 
 
+def _stock_layer_frame(x67_bf16, conv27_bf16, w, b):
+    """One DCNv2 layer of one frame by STOCK torchvision CUDA in fp32 on the same bf16-rounded tensors (the bf16 oracle of
+    SURVEY.md section 8c): offsets / mask from the 27-channel tensor as ema_vfi.py:57-59 computes them, sigmoid in the tensor's
+    dtype (what torch.sigmoid on a bf16 tensor returns).  One frame at a time bounds torchvision's columns buffer (5 GB at
+    1080p, 20 GB at 4K)."""
+    off, m = torch_ref.pack_split(conv27_bf16)
+    return torch_ref.dcn_stock(x67_bf16.float(), off.float(), m.float(), w.float(), b.float())
+
+
+def test_hot_path_cfg2_full_size_vs_stock_torchvision_cuda():
+    """BASELINE config 2 at full size -- 8 x 1080p, bf16, exactly what bench.py times (HotPath.run: warp into tail records,
+    three fused tcgen05 layers on planes) -- against an INDEPENDENT oracle: stock aten grid_sample and stock torchvision
+    deform_conv2d CUDA kernels in fp32.  Every layer of every frame is checked on the layer's own (bf16) input at the
+    north star's bf16 bar, max|delta| / max|ref| <= 1e-2; the chain the bench runs is tied to those layers bit for bit."""
+    from vfi_b200 import ops
+    from vfi_b200.hotpath import HotPath, synthetic_inputs, synthetic_weights
+
+    B, H, W = 8, 1080, 1920
+    frame2, flow, feat, convs = synthetic_inputs(B, H, W, dtype=torch.bfloat16, device=DEV, seed=1234)
+    feat = feat.contiguous(memory_format=torch.channels_last)
+    ws, bs = synthetic_weights(dtype=torch.bfloat16, device=DEV)
+    out = HotPath(ws, bs, math="bf16_tc").run(frame2, flow, feat, convs)
+    # the same chain with every intermediate kept
+    src = ops.Planes(B, H, W, DEV, zero_tail=True)
+    ops.warp(frame2, flow, out=src.tail_nchw(3))
+    layers = [(feat, src.tail_nchw(3))]
+    for w, b, c27 in zip(ws, bs, convs):
+        y = ops.deform_conv2d_fused(layers[-1][0], layers[-1][1], c27, w, b, math="bf16_tc")
+        layers.append((y.main_nchw, y.tail_nchw()))
+    assert torch.equal(out.main, layers[-1][0].permute(0, 2, 3, 1)) and torch.equal(out.tail_nchw(), layers[-1][1])
+    worst = 0.0
+    for f in range(B):
+        warped = torch_ref.warp(frame2[f:f + 1].float(), flow[f:f + 1].float())     # stock CUDA grid_sample (reciprocal division)
+        got = src.tail_nchw(3)[f:f + 1].float()
+        assert float((got - warped).abs().max()) <= 1e-2 * float(warped.abs().max())
+        for i, (w, b, c27) in enumerate(zip(ws, bs, convs)):
+            x67 = torch.cat((layers[i][0][f:f + 1], layers[i][1][f:f + 1]), dim=1)
+            ref = _stock_layer_frame(x67, c27[f:f + 1], w, b)
+            got = torch.cat((layers[i + 1][0][f:f + 1], layers[i + 1][1][f:f + 1]), dim=1).float()
+            err = float((got - ref).abs().max()) / float(ref.abs().max())
+            worst = max(worst, err)
+            assert err <= 1e-2, (f, i, err)
+            del ref, got, x67
+    print(f"cfg2 full size: worst layer error {worst:.2e} of max|ref| (bar 1e-2)")
+
+
+@pytest.mark.parametrize("flow_kind,sigma", [("smooth", 64.0), ("iid", 64.0)])
+def test_hot_path_cfg4_4k_vs_stock_torchvision_cuda(flow_kind, sigma):
+    """BASELINE config 4 (4K frame pair, batch 1, bf16, large-displacement flow -- smooth and incoherent): the warp's tail
+    records against stock grid_sample, and the fused tcgen05 layers against stock torchvision CUDA fp32 on the same tensors."""
+    from vfi_b200 import ops
+    from vfi_b200.hotpath import synthetic_inputs, synthetic_weights
+
+    B, H, W = 1, 2160, 3840
+    frame2, flow, feat, convs = synthetic_inputs(B, H, W, dtype=torch.bfloat16, device=DEV, seed=4, flow_sigma=sigma, flow_kind=flow_kind)
+    feat = feat.contiguous(memory_format=torch.channels_last)
+    ws, bs = synthetic_weights(dtype=torch.bfloat16, device=DEV)
+    src = ops.Planes(B, H, W, DEV, zero_tail=True)
+    ops.warp(frame2, flow, out=src.tail_nchw(3), division="reciprocal")
+    warped = torch_ref.warp(frame2.float(), flow.float())
+    assert float((src.tail_nchw(3).float() - warped).abs().max()) <= 1e-2 * float(warped.abs().max())
+    del warped
+    x = (feat, src.tail_nchw(3))
+    for i, (w, b, c27) in enumerate(zip(ws, bs, convs)):
+        if i == 2 and flow_kind == "iid":
+            break                                        # two layers suffice for the second flow class (20 GB of columns each)
+        y = ops.deform_conv2d_fused(x[0], x[1], c27, w, b, math="bf16_tc")
+        ref = _stock_layer_frame(torch.cat(x, dim=1), c27, w, b)
+        got = y.to_nchw().float()
+        err = float((got - ref).abs().max()) / float(ref.abs().max())
+        assert err <= 1e-2, (i, err)
+        del ref, got
+        x = (y.main_nchw, y.tail_nchw())
+
+
+def test_interpolated_frame_psnr_delta_bf16_hot_path():
+    """North-star gate: interpolated-frame PSNR delta <= 0.01 dB.  The network of the model_psnr_256 golden (BASELINE config 1
+    size; the unmodified reference's CPU output and Middlebury frame11 as ground truth are in the fixture) runs on the GPU
+    three ways: stock ops, the fp32 drop-in, and the bf16 tensor-core drop-in; each output's PSNR against the ground-truth
+    frame is compared with the PSNR of the reference's own output."""
+    from test_refmodel import psnr, psnr_inputs, psnr_model
+    from vfi_b200.refmodel import StockInterpolator
+
+    z = load_golden("model_psnr_256")
+    model = psnr_model(z, DEV)
+    a, b, gt = (t.to(DEV) for t in psnr_inputs(z))
+    ref_out = torch.from_numpy(z["model_out"]).to(DEV)
+    ref_psnr = psnr(ref_out, gt)
+    with torch.no_grad():
+        stock = model(a, b)
+    assert maxabs(stock, ref_out) <= 2e-4                      # cuDNN vs the reference's CPU kernels
+    results = {"stock_cuda": psnr(stock, gt)}
+    for math in ("fp32", "bf16_tc"):
+        vfi_b200.install(StockInterpolator, math=math)
+        try:
+            with torch.no_grad():
+                out = model(a, b)
+        finally:
+            vfi_b200.uninstall()
+        results[math] = psnr(out, gt)
+        if math == "fp32":
+            assert maxabs(out, stock) <= 2e-5
+    print(f"PSNR vs ground truth: reference {ref_psnr:.4f} dB, " + ", ".join(f"{k} {v:.4f} dB" for k, v in results.items()))
+    for k, v in results.items():
+        assert abs(v - ref_psnr) <= 0.01, (k, v, ref_psnr)
+
+
 # ------------------------------------------------------------------------------------------------------------ path
 def test_model_hot_path_fixture_through_the_dropin():
     """Replay of the tensors recorded inside the unmodified EMA_VFI.forward (golden model_24x32): warp -> cat -> 3 x

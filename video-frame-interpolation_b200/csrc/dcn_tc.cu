@@ -42,6 +42,9 @@
 //               optionally straight from the 27-channel offset_conv output with the sigmoid folded in) into the other
 //               half of a double buffer and prefetch its footprint into L2 while the producers gather tile i; then
 //               tcgen05.ld tile i's accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is resolved at run time through cudaGetDriverEntryPoint)
+
+#include <cstddef>
 #include <cstdlib>
 #include <type_traits>
 
@@ -719,6 +722,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
 }
 
 #include "dcn_tc6.cuh"   // v6: TMEM-resident A operand, source box staged in shared memory
+#include "dcn_tc7.cuh"   // v7 (default): v6 + TMA tensor maps, tail channels gathered by the geometry warps, four producer groups
 #include "dcn_tc6_wgrad.cuh"   // weight / bias gradient on tcgen05 (pixel-reduction GEMM, accumulators persistent in TMEM)
 #include "dcn_bwd_cols.cuh"    // grad_x / grad_offset / grad_mask from the column gradient (channels-last, vector reductions)
 
@@ -832,6 +836,58 @@ int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, c
   return VFI_OK;
 }
 
+
+// cuTensorMapEncodeTiled, resolved at run time (the library has no link-time dependency on libcuda: it loads in the CPU-only
+// build container).  Returns null when the driver does not export it.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// 4-D tiled map over 16-bit elements: dims / box innermost first, strides (bytes) of dims 1..3.  False when the copy engine
+// cannot describe the tensor (alignment, stride range) -- the caller then uses another path or reports VFI_ERR_UNSUPPORTED.
+static bool make_map4(CUtensorMap* m, const void* base, const long long dim[4], const long long stride_bytes[3], const int box[4],
+                      bool swizzle128) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || !aligned(base, 16)) return false;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    if (dim[i] <= 0 || box[i] <= 0 || box[i] > 256) return false;
+    gd[i] = (cuuint64_t)dim[i];
+    bx[i] = (cuuint32_t)box[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (stride_bytes[i] <= 0 || stride_bytes[i] % 16 != 0 || stride_bytes[i] >= (1LL << 40)) return false;
+    gs[i] = (cuuint64_t)stride_bytes[i];
+  }
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// channels-last 16-bit plane [B,H,W,c] with dense rows (sh = W * sw), any pixel stride that is a multiple of 16 bytes
+static bool plane_map(CUtensorMap* m, const void* base, long long c, long long px_bytes, long long B, long long H, long long W, int box_w,
+                      int box_h, bool swizzle128) {
+  const long long dim[4] = {c, W, H, B}, st[3] = {px_bytes, px_bytes * W, px_bytes * W * H};
+  const int box[4] = {(int)c, box_w, box_h, 1};
+  return make_map4(m, base, dim, st, box, swizzle128);
+}
+// NCHW-like 16-bit tensor (unit pixel stride): box of 16 x 8 pixels x all channels
+static bool nchw_map(CUtensorMap* m, const vfi_tensor* t) {
+  if (t->sw != 1 || t->sh <= 0 || t->sc <= 0 || t->sn <= 0) return false;
+  const long long dim[4] = {t->w, t->h, t->c, t->n}, st[3] = {t->sh * 2, t->sc * 2, t->sn * 2};
+  const int box[4] = {TC_TW, TC_TH, (int)t->c, 1};
+  return make_map4(m, t->data, dim, st, box, false);
+}
+
 // Shared implementation.  x_tail == null: x_main is any [B,C,H,W] tensor (packed into planes in the workspace).
 // x_tail != null: planes in.  conv27 != null selects the fused offset/mask form.  out_tail != null: planes out.
 int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_tensor* offset, const vfi_tensor* mask,
@@ -906,7 +962,9 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   const bool geo_cl = conv27 && (conv27->dtype == VFI_BF16 || conv27->dtype == VFI_F16) && conv27->sc == 1 && conv27->sw == 27 &&
                       conv27->sh == conv27->w * 27 && conv27->sn % 8 == 0 && conv27->w % 8 == 0 && aligned(conv27->data, 16);
   const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4 && (geo_cl || (bulk_ok(offset) && bulk_ok(mask)));
-  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, use_v6 ? 6 : 4);
+  const bool use_v7 = !hq && !force_v4 && C <= TC_CMAIN + 4 && (offset->dtype == VFI_BF16 || offset->dtype == VFI_F16) &&
+                      mask->dtype == offset->dtype;
+  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, (use_v6 || use_v7) ? 6 : 4);
   if (rc) return rc;
   if (x_tail) {
     p.x_main = reinterpret_cast<const uint8_t*>(x->data);
@@ -933,6 +991,59 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   const int out_dtype = out_tail ? VFI_BF16 : out->dtype;
+  // v7 (default): v6's arithmetic with TMA tensor maps, the tail channels gathered by the geometry warps and four producer
+  // groups (dcn_tc7.cuh).  VFI_DCN_KERNEL=v6 selects the previous kernel (A/B runs).
+  static const bool force_v6 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '6'; }();
+  if (use_v7 && !force_v6) {
+    V7Args a;
+    a.p = p;
+    a.o_main_px = TC_CMAIN * 2; a.o_tail_px = TC_CTAIL * 2;
+    bool ok = plane_map(&a.tm_main, p.x_main, TC_CMAIN, p.main_stride, p.B, p.H, p.W, V6_BOX_W, V6_BOX_H, false) &&
+              plane_map(&a.tm_tail, p.x_tail, TC_CTAIL, p.tail_stride, p.B, p.H, p.W, V6_BOX_W, V6_BOX_H, false);
+    VFI_REQUIRE(ok, VFI_ERR_UNSUPPORTED, "%s(bf16_tc): the activation planes cannot be described by a TMA tensor map", who);
+    a.tm_raw0 = a.tm_main; a.tm_raw1 = a.tm_main; a.tm_out = a.tm_main;     // defined contents for the maps a mode does not use
+    static const int force_raw = [] { const char* e = getenv("VFI_DCN_RAW"); return e ? atoi(e) : -1; }();
+    if (geo_cl && force_raw != V7_RAW_LDG) a.raw_mode = V7_RAW_ROWS;
+    else if (force_raw != V7_RAW_LDG && (conv27 ? nchw_map(&a.tm_raw0, conv27) : (nchw_map(&a.tm_raw0, offset) && nchw_map(&a.tm_raw1, mask))))
+      a.raw_mode = V7_RAW_TMA;
+    else a.raw_mode = V7_RAW_LDG;
+    a.p.geo_cl = a.raw_mode == V7_RAW_ROWS ? 1 : 0;
+    static const bool no_tma_store = [] { const char* e = getenv("VFI_DCN_NO_TMA_STORE"); return e && e[0] == '1'; }();
+    a.use_tma_store = (out_tail && !no_tma_store &&
+                       plane_map(&a.tm_out, p.out, TC_CMAIN, a.o_main_px, p.B, p.H, p.W, TC_TW, TC_TH, true)) ? 1 : 0;
+    const size_t smem7 = sizeof(V7Smem) + 1024;
+    const bool dbg = p.debug != nullptr;
+#define VFI_V7_LAUNCH(FUSED, PLANES, DBG)                                                                      \
+  do {                                                                                                         \
+    auto kern = dcn_tc7_fwd_kernel<TO, TOUT, FUSED, PLANES, DBG>;                                              \
+    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));             \
+    kern<<<grid, V7_THREADS, smem7, st>>>(a);                                                                  \
+  } while (0)
+    if (out_tail) {
+      using TOUT = __nv_bfloat16;
+      if (offset->dtype == VFI_BF16) {
+        using TO = __nv_bfloat16;
+        if (p.fused27) { if (dbg) VFI_V7_LAUNCH(true, true, true); else VFI_V7_LAUNCH(true, true, false); }
+        else VFI_V7_LAUNCH(false, true, false);
+      } else {
+        using TO = __half;
+        if (p.fused27) VFI_V7_LAUNCH(true, true, false); else VFI_V7_LAUNCH(false, true, false);
+      }
+    } else {
+      VFI_DISPATCH(out_dtype, TOUT, {
+        if (offset->dtype == VFI_BF16) {
+          using TO = __nv_bfloat16;
+          if (p.fused27) VFI_V7_LAUNCH(true, false, false); else VFI_V7_LAUNCH(false, false, false);
+        } else {
+          using TO = __half;
+          if (p.fused27) VFI_V7_LAUNCH(true, false, false); else VFI_V7_LAUNCH(false, false, false);
+        }
+      });
+    }
+#undef VFI_V7_LAUNCH
+    VFI_LAUNCH_CHECK("dcn_tc7_fwd_kernel");
+    return VFI_OK;
+  }
   if (use_v6) {
     const size_t smem6 = sizeof(V6Smem) + 1024;
     const bool dbg = p.debug != nullptr;
