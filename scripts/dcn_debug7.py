@@ -23,12 +23,12 @@ def show(name, warps, labels):
     tot = x[..., 0].mean()
     idx = {0: 1, 1: 2, 2: 3, 3: 4, 4: 6, 5: 7}
     print(f"{name:10s} total {tot/1e3:8.1f} kcyc  " + "  ".join(f"{l} {x[..., idx[i]].mean()/tot*100:5.1f}%" for i, l in enumerate(labels) if l != "-"))
-HF = os.environ.get("V7_LAYOUT", "1") == "1"
-PROD, MMA, COPY, BLOAD, EPI, GEO = (16, 12, 13, 14, 8, 0) if HF else (0, 16, 17, 18, 20, 24)
-show("producers", list(range(PROD, PROD + 16)), ["geo", "box_full", "a_empty"])
+P = int(os.environ.get("V7_PARTS", "3"))
+GEO, EPI, MMA, COPY, BLOAD, PROD = 0, 4 * P, 4 * P + 4, 4 * P + 5, 4 * P + 6, 4 * P + 8
+show("producers", list(range(PROD, 32)), ["geo", "box_full", "a_empty"])
 show("mma", [MMA], ["acc_empty", "tail_full", "a_full", "issue", "commit"])
 show("copy", [COPY], ["box_empty", "raw_empty"])
 show("bload", [BLOAD], ["b_empty"])
 show("epilogue", list(range(EPI, EPI + 4)), ["-", "acc_full", "-", "epilogue"])
-show("geometry", list(range(GEO, GEO + 8)), ["geo_empty", "raw_full", "compute", "box+acc_wait", "raw_read", "tail"])
+show("geometry", list(range(GEO, GEO + 4 * P)), ["geo_empty", "raw_full", "compute", "box+acc_wait", "raw_read", "tail"])
 print("tiles per CTA", d[:, PROD, 5].mean(), " cycles per tile", d[:, PROD, 0].mean() / d[:, PROD, 5].mean())

@@ -25,24 +25,23 @@
 // TMEM columns: [0,80) / [128,208) accumulators of even / odd tiles, [80,128) and [208,256) four tail A buffers of 24 columns,
 // [256,512) the main A ring (8 stages x 32 columns).
 
-#ifndef V7_HELPERS_FIRST
-#define V7_HELPERS_FIRST 1   // 1: geometry / epilogue / MMA / copy warps take the low warp ids, the producers 16..31
-#endif
-constexpr int V7_GROUPS = 4;
+#ifndef V7_PARTS
+#define V7_PARTS 3           // geometry threads per pixel: 3 -> twelve geometry warps (three taps each) + three producer groups;
+#endif                       //                             2 -> eight geometry warps (taps 0-3 + 8 / 4-7) + four producer groups
+static_assert(V7_PARTS == 2 || V7_PARTS == 3, "V7_PARTS");
+constexpr int V7_GROUPS = V7_PARTS == 3 ? 3 : 4;
 constexpr int V7_PRODUCER_WARPS = 4 * V7_GROUPS;
-constexpr int V7_EPI_WARPS = 4, V7_GEO_WARPS = 8;
-// Every role that touches tensor memory keeps TMEM quarter = warp % 4 (all bases are multiples of four).
-#if V7_HELPERS_FIRST
-constexpr int V7_W_GEO = 0;                                                       // warps 0..7: half = warp / 4
-constexpr int V7_W_EPI = 8;                                                       // warps 8..11
-constexpr int V7_W_MMA = 12, V7_W_COPY = 13, V7_W_BLOAD = 14;                     // warp 15 idles
-constexpr int V7_W_PROD = 16;                                                     // warps 16..31
-#else
-constexpr int V7_W_PROD = 0;                                                      // warps 0..15
-constexpr int V7_W_MMA = 16, V7_W_COPY = 17, V7_W_BLOAD = 18;                     // warp 19 idles
-constexpr int V7_W_EPI = 20;                                                      // warps 20..23
-constexpr int V7_W_GEO = 24;                                                      // warps 24..31: half = (warp - 24) / 4
-#endif
+constexpr int V7_EPI_WARPS = 4, V7_GEO_WARPS = 4 * V7_PARTS;
+constexpr int V7_NT = V7_PARTS == 3 ? 3 : 4;                                      // taps a geometry thread computes in one straight-line section
+constexpr int V7_FIRST_TAPS = V7_NT;                                              // ... of which part 0's are published first (geo_first)
+constexpr int V7_NRV = V7_PARTS == 3 ? 9 : 15, V7_NENT = V7_PARTS == 3 ? 3 : 5;   // raw values / entries a geometry thread holds
+// Every role that touches tensor memory keeps TMEM quarter = warp % 4 (all bases are multiples of four).  The helper roles
+// take the low warp ids (measured 4 % faster than the other way round).
+constexpr int V7_W_GEO = 0;                                                       // warps 0 .. 4 P - 1: part = warp / 4
+constexpr int V7_W_EPI = V7_GEO_WARPS;                                            // four warps
+constexpr int V7_W_MMA = V7_W_EPI + 4, V7_W_COPY = V7_W_MMA + 1, V7_W_BLOAD = V7_W_MMA + 2;   // the fourth warp of this quad idles
+constexpr int V7_W_PROD = V7_W_MMA + 4;                                           // 4 x V7_GROUPS warps
+static_assert(V7_W_PROD + V7_PRODUCER_WARPS == 32, "32 warps");
 constexpr int V7_THREADS = 1024;
 constexpr int V7_NA = 8, V7_NB = 3;
 constexpr int V7_MAIN_BLOCKS = 9;
@@ -53,9 +52,6 @@ constexpr int V7_MAIN_BLOCKS = 9;
 __host__ __device__ constexpr uint32_t v7_tail_col(int it) { return (uint32_t)(((it >> 1) & 1) * TC_ACC_STRIDE + 80 + (it & 1) * 24); }
 constexpr int V7_BOX_TAIL_BYTES = 7552;                                            // 468 x 16 B rounded up to a multiple of 128
 constexpr uint32_t V7_BOX_TX = (uint32_t)V6_BOX_PX * (V6_MAIN_PX + V6_TAIL_PX);    // bytes one box load signals (zero fill included)
-#ifndef V7_GEO_PREFETCH
-#define V7_GEO_PREFETCH 0      // 1 (measured slower, 4.46 vs 4.29 ms): geometry warps request tile it + 1's offsets / masks before the tail gathers of tile it
-#endif
 constexpr int V7_RAW_TMA = 0, V7_RAW_ROWS = 1, V7_RAW_LDG = 2;                    // how the offsets / masks of a tile arrive
 
 struct __align__(1024) V7Smem {
@@ -112,6 +108,12 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
                : "r"(bar), "r"(parity)
                : "memory");
   return ok;
+}
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s.acc_full[i]), 1);
       mbar_init(smem_u32(&s.acc_empty[i]), V7_EPI_WARPS);
-      mbar_init(smem_u32(&s.geo_first[i]), V7_GEO_WARPS / 2);     // taps 0..3 written (the first half's warps)
+      mbar_init(smem_u32(&s.geo_first[i]), 4);                    // part 0's taps written (four warps)
       mbar_init(smem_u32(&s.geo_full[i]), V7_GEO_WARPS);
       mbar_init(smem_u32(&s.geo_empty[i]), V7_PRODUCER_WARPS);
       mbar_init(smem_u32(&s.box_full[i]), 1);
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       const uint32_t box_main = smem_u32(&s.box_main[gb][0]);
       const uint32_t bF = box_main + c_first, bS = box_main + c_second;
       bool first = true, all_taps = false;
-      for (int kb = (group - it) & 3; kb < V7_MAIN_BLOCKS; kb += V7_GROUPS) {
+      // four groups: block m = 9 it + kb goes to group m % 4 (kb = (group - it) mod 4, + 4, ...); three groups: kb = group, + 3, + 6
+      for (int kb = V7_GROUPS == 4 ? ((group - it) & 3) : group; kb < V7_MAIN_BLOCKS; kb += V7_GROUPS) {
         const int m = it * V7_MAIN_BLOCKS + kb, sa = m & (V7_NA - 1);
         const uint32_t a_taddr = tmem_base + lane_base + (uint32_t)(V6_A_COL0 + sa * 32);
         if (first) {
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
           mbar_wait_d<V6_NS_PROD, DBG>(smem_u32(&s.box_full[gb]), tphase, w1);    // this tile's source box has landed
           first = false;
         }
-        if (kb >= 4 && !all_taps) {
+        if (kb >= V7_FIRST_TAPS && !all_taps) {
           mbar_wait_d<V6_NS_PROD, DBG>(smem_u32(&s.geo_full[gb]), tphase, w0);
           all_taps = true;
         }
@@ -391,18 +394,22 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       __syncwarp();
     }
   } else if (warp >= V7_W_GEO && warp < V7_W_GEO + V7_GEO_WARPS) {
-    // =========================================================================== tap geometry + tail channels (8 warps)
-    // Thread = (tile row, half): half 0 computes taps 0..3 (published first) and tap 8, half 1 taps 4..7.  The entries stay
-    // in registers for the tail gather, whose results go straight to this tile's tail A columns in tensor memory.
-    const int half = (warp - V7_W_GEO) >> 2, quad = warp & 3;
+    // =========================================================================== tap geometry + tail channels
+    // Thread = (tile row, part).  Three parts: taps 3 part .. 3 part + 2.  Two parts: part 0 = taps 0..3 and then tap 8,
+    // part 1 = taps 4..7.  Part 0's first section is published first (geo_first: what the first K blocks of a tile need).
+    // The entries stay in registers for the tail gather, whose results go straight to this tile's tail A columns in TMEM.
+    const int part = (warp - V7_W_GEO) >> 2, quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t tail_row = p.tail_stride * (uint32_t)p.W;
     const uint16_t* const raw_flat = &s.raw[0][0];
     const int raw_mode = a.raw_mode;
-    // Offsets / masks of this thread's taps of tile `t`: half 0 = taps 0,1,2,3,8; half 1 = taps 4,5,6,7 -- (dy, dx, mask) each.
-    // Only issues the loads (15 independent LDS.U16 / LDG): with V7_GEO_PREFETCH the values of tile it + 1 are requested
-    // before the tail gathers of tile it, so the two trips through the (saturated) load/store pipe overlap.
+    const int kbase = part * V7_NT;                      // taps of the straight-line section: kbase .. kbase + V7_NT - 1
+    const bool extra = V7_PARTS == 2 && part == 0;       // ... plus tap 8 (two-part form only)
+    auto tap_of = [&](int i) -> int { return i < V7_NT ? kbase + i : 8; };
+    // Offsets / masks of this thread's taps of tile `t` -- (dy, dx, mask) each.  Only issues the loads (independent LDS.U16 /
+    // LDG), one branch on the transport for all of them: a branch per value would put every load in its own basic block,
+    // i.e. one trip through the saturated load/store queue per value (measured: 7,000 cycles per tile).
     auto fetch_raw = [&](int t, uint32_t* rv) {
       if (DBG && (p.experiment & 8) && t >= 1) return;   // diagnostics: the values of tile 0 are reused
       int b, ty0, tx0;
@@ -411,13 +418,10 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       const bool inside = y < p.H && x < p.W;
       // kernel channel c (0..17: offsets dy/dx interleaved, 18..26: mask) -> channel of the tensor the values come from
       auto chan = [&](int c) -> int { return FUSED27 ? (c < 18 ? (c < 9 ? c : c + 9) : c - 9) : c; };
-      // One branch on the transport for all fifteen values (a branch per value would put every load in its own basic block:
-      // fifteen trips through the load/store queue instead of one -- measured 7,000 cycles per tile).
       auto all = [&](auto&& rd) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int k = half == 0 ? (i < 4 ? i : 8) : 4 + i;
-          if (half == 1 && i == 4) { rv[12] = rv[13] = rv[14] = 0u; break; }
+        for (int i = 0; i < V7_NENT; ++i) {
+          const int k = tap_of(i);
           rv[3 * i] = rd(2 * k); rv[3 * i + 1] = rd(2 * k + 1); rv[3 * i + 2] = rd(18 + k);
         }
       };
@@ -431,25 +435,18 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
         all([&](int c) -> uint32_t { return (FUSED27 || c < 18) ? ldg_bits<TO>(po + chan(c) * p.f_sc) : ldg_bits<TO>(pm + (c - 18) * p.m_sc); });
       } else {
 #pragma unroll
-        for (int i = 0; i < 15; ++i) rv[i] = 0u;
+        for (int i = 0; i < V7_NRV; ++i) rv[i] = 0u;
       }
     };
     // The raw buffer is single: it is handed back once every lane holds its values in registers.
     auto release_raw = [&](uint32_t* rv) {
       if (raw_mode == V7_RAW_LDG) return;
 #pragma unroll
-      for (int i = 0; i < 15; ++i) asm volatile("" ::"r"(rv[i]) : "memory");      // the loads have returned
+      for (int i = 0; i < V7_NRV; ++i) asm volatile("" ::"r"(rv[i]) : "memory");      // the loads have returned
       __syncwarp();                                    // every lane's reads are ordered before the release below
       if (lane == 0) mbar_arrive(smem_u32(&s.raw_empty));
     };
-    uint32_t rv[15];
-#if V7_GEO_PREFETCH
-    if (my_tiles > 0) {
-      if (raw_mode != V7_RAW_LDG) mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.raw_full), 0u, w1);
-      fetch_raw(0, rv);
-      release_raw(rv);
-    }
-#endif
+    uint32_t rv[V7_NRV];
     for (int it = 0; it < my_tiles; ++it) {
       const int gb = it & 1;
       const uint32_t tphase = (uint32_t)(it >> 1) & 1u;
@@ -457,9 +454,8 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
       const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
       const bool inside = y < p.H && x < p.W;
-#if !V7_GEO_PREFETCH
-      // Optimistic and batched: the three barrier polls of this tile and the fifteen loads go through the load/store queue
-      // together; the loads are simply repeated in the rare case that the values had not landed yet.
+      // Optimistic and batched: the three barrier polls of this tile and the loads go through the load/store queue together;
+      // the loads are simply repeated in the rare case that the values had not landed yet.
       const long long tr0 = dbg ? clock64() : 0;
       const uint32_t ok_raw = raw_mode != V7_RAW_LDG ? mbar_test(smem_u32(&s.raw_full), (uint32_t)it & 1u) : 1u;
       const uint32_t ok_geo = mbar_test(smem_u32(&s.geo_empty[gb]), tphase ^ 1u);
@@ -472,18 +468,13 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       release_raw(rv);
       if (dbg) w4 += clock64() - tr0;
       if (!ok_geo) mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.geo_empty[gb]), tphase ^ 1u, w0);   // producers are done with the old entries
-#else
-      const uint32_t ok_box = 0u;
-      mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.geo_empty[gb]), tphase ^ 1u, w0);   // producers are done with the old entries
-#endif
       const long long tg0 = dbg ? clock64() : 0;
       const int by0 = ty0 - V6_BOX_TOP, bx0 = tx0 - V6_BOX_LEFT;
       const int base = b * p.H * p.W;
       const float fy0 = (float)(y - 1), fx0 = (float)(x - 1);
-      uint4 ent[5];
-      const int kbase = half == 0 ? 0 : 4;               // this thread's first four taps: kbase .. kbase + 3
-      // Straight-line code for the four taps (no branch per tap: the dependent chains -- exp, reciprocal, floor, products --
-      // of the taps interleave); samples the box does not serve are rare and patched afterwards.
+      uint4 ent[V7_NENT];
+      // Straight-line code for the section's taps (no branch per tap: the dependent chains -- exp, reciprocal, floor, products
+      // -- of the taps interleave); samples the box does not serve are rare and patched afterwards.
       auto entry = [&](int i, int k, uint32_t& slow) {
         float mk = bits_to_f32<TO>(rv[3 * i + 2]);
         // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
@@ -503,40 +494,38 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       } else if (inside) {
         uint32_t slow = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) entry(i, kbase + i, slow);
+        for (int i = 0; i < V7_NT; ++i) entry(i, kbase + i, slow);
         if (slow) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < V7_NT; ++i)
             if (slow & (1u << i)) patch(i, kbase + i);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ent[i] = make_uint4(V6_SAFE, 0u, 0u, 0u);
+        for (int i = 0; i < V7_NT; ++i) ent[i] = make_uint4(V6_SAFE, 0u, 0u, 0u);
       }
       if (!skip_geo) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s.geo[gb][kbase + i][row] = ent[i];
+        for (int i = 0; i < V7_NT; ++i) s.geo[gb][kbase + i][row] = ent[i];
       }
-      ent[4] = make_uint4(V6_SAFE, 0u, 0u, 0u);
-      if (half == 0) {                                   // taps 0..3 are all the first K blocks of the tile need
+      if (part == 0) {                                   // the first taps are all the first K blocks of the tile need
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.geo_first[gb]));
-        if (inside && !skip_geo) {
-          uint32_t slow = 0;
-          entry(4, 8, slow);
-          if (slow) patch(4, 8);
+      }
+      if (V7_NENT > V7_NT) {                             // two-part form: tap 8 goes to part 0
+        ent[V7_NENT - 1] = make_uint4(V6_SAFE, 0u, 0u, 0u);
+        if (extra) {
+          if (inside && !skip_geo) {
+            uint32_t slow = 0;
+            entry(V7_NENT - 1, 8, slow);
+            if (slow) patch(V7_NENT - 1, 8);
+          }
+          if (!skip_geo) s.geo[gb][8][row] = ent[V7_NENT - 1];
         }
-        if (!skip_geo) s.geo[gb][8][row] = ent[4];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
       if (dbg) w2 += clock64() - tg0;
-#if V7_GEO_PREFETCH
-      if (it + 1 < my_tiles) {                           // rv is dead: request the next tile's values now
-        if (raw_mode != V7_RAW_LDG) mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.raw_full), (uint32_t)(it + 1) & 1u, w1);
-        fetch_raw(it + 1, rv);
-      }
-#endif
       // ---- tail channels of this thread's taps: box (tail plane) of this tile, then this tile's tail A columns
       if (!ok_box) mbar_wait_d<V6_NS_HELP, DBG>(smem_u32(&s.box_full[gb]), tphase, w3);
       tc_fence_after();
@@ -544,40 +533,52 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
       const uint32_t box_tail = smem_u32(&s.box_tail[gb][0]);
       const uint32_t hsel = (uint32_t)(lane & 1) * 8u;
       const uint32_t taddr = tmem_base + lane_base + v7_tail_col(it);
-      uint32_t r[8];
-      uint2 v8;
+      uint32_t r[2 * V7_NENT];
+      uint32_t all_x = 0;
+#pragma unroll
+      for (int i = 0; i < V7_NENT; ++i) all_x |= ent[i].x;
       if (DBG && (p.experiment & 1)) {                 // diagnostics: no tail gathers
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = 0u;
-        v8 = make_uint2(0u, 0u);
-      } else if ((int)(ent[0].x | ent[1].x | ent[2].x | ent[3].x | ent[4].x) >= 0) {
-        // every sample of this thread is served by the box: straight-line code, all twenty loads in flight together (one
-        // trip through the load/store queue instead of five)
-        uint2 c[5][4];
+        for (int i = 0; i < 2 * V7_NENT; ++i) r[i] = 0u;
+      } else if ((int)all_x >= 0) {
+        // every sample of this thread is served by the box: straight-line code, all loads in flight together (one trip
+        // through the load/store queue instead of one per tap)
+        uint2 c[V7_NENT][4];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < V7_NENT; ++i) {
           const uint32_t ad = box_tail + (ent[i].x >> 3) + hsel;
           c[i][0] = lds8o<0>(ad); c[i][1] = lds8o<V6_TAIL_PX>(ad); c[i][2] = lds8o<V6_TAIL_ROW>(ad); c[i][3] = lds8o<V6_TAIL_ROW + V6_TAIL_PX>(ad);
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < V7_NENT; ++i) {
           const uint4 t = lerp_chunk(make_uint4(c[i][0].x, c[i][0].y, 0u, 0u), make_uint4(c[i][1].x, c[i][1].y, 0u, 0u),
                                      make_uint4(c[i][2].x, c[i][2].y, 0u, 0u), make_uint4(c[i][3].x, c[i][3].y, 0u, 0u),
                                      make_uint2(ent[i].y, ent[i].z));
-          if (i < 4) { r[2 * i] = t.x; r[2 * i + 1] = t.y; } else v8 = make_uint2(t.x, t.y);
+          r[2 * i] = t.x; r[2 * i + 1] = t.y;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < V7_NENT; ++i) {
           const uint2 v = v7_sample_tail(ent[i], box_tail, p.x_tail, p.tail_stride, tail_row, hsel);
           r[2 * i] = v.x; r[2 * i + 1] = v.y;
         }
-        v8 = v7_sample_tail(ent[4], box_tail, p.x_tail, p.tail_stride, tail_row, hsel);
       }
-      tmem_st_32x32b_x8(taddr + (half == 0 ? 0u : 8u), r);       // K elements [0,16) / [16,32): taps 0..3 / 4..7
-      if (half == 0) {
-        uint32_t r2[8] = {v8.x, v8.y, 0x3f803f80u, 0u, 0u, 0u, 0u, 0u};   // tap 8, then K elements 36, 37 = 1.0 (bias hi / lo), zeros
-        tmem_st_32x32b_x8(taddr + 16u, r2);
+      // TMEM columns of the tail A block: tap k at 2 k, 2 k + 1 (K elements 4 k .. 4 k + 3); column 18 = K elements 36, 37
+      // = 1.0 (the weight image holds bias hi / lo there); columns 19..23 zero.
+      const uint32_t ones[6] = {0x3f803f80u, 0u, 0u, 0u, 0u, 0u};
+      if (V7_PARTS == 3) {
+        tmem_st_32x32b_x4(taddr + (uint32_t)(6 * part), r);
+        tmem_st_32x32b_x2(taddr + (uint32_t)(6 * part + 4), r + 4);
+        if (part == 2) {
+          tmem_st_32x32b_x4(taddr + 18u, ones);
+          tmem_st_32x32b_x2(taddr + 22u, ones + 4);
+        }
+      } else {
+        tmem_st_32x32b_x8(taddr + (part == 0 ? 0u : 8u), r);     // taps 0..3 / 4..7
+        if (part == 0) {
+          const uint32_t r2[8] = {r[2 * (V7_NENT - 1)], r[2 * (V7_NENT - 1) + 1], 0x3f803f80u, 0u, 0u, 0u, 0u, 0u};
+          tmem_st_32x32b_x8(taddr + 16u, r2);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -587,9 +588,6 @@ __global__ void __launch_bounds__(V7_THREADS, 1) dcn_tc7_fwd_kernel(const __grid
         mbar_arrive(smem_u32(&s.box_empty[gb]));
       }
       if (dbg) w5 += clock64() - tt0;
-#if V7_GEO_PREFETCH
-      if (it + 1 < my_tiles) release_raw(rv);
-#endif
     }
   } else if (warp >= V7_W_EPI && warp < V7_W_EPI + V7_EPI_WARPS) {
     // =========================================================================== epilogue (4 warps)
