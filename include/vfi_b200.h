@@ -73,6 +73,12 @@ void vfi_reset_launch_count(void);
  * and a multiplication by the fp32 reciprocal when it runs on CUDA (aten's tensor/scalar fast path).  Default = IEEE. */
 #define VFI_WARP_DIV_IEEE 0
 #define VFI_WARP_DIV_RECIPROCAL 1
+/* vfi_warp_fwd only: `out` is the [B,3,H,W] view of a DCN tail plane (bf16 channels-last records of 8 elements = 16 bytes per
+ * pixel, 16-byte aligned) and the kernel writes WHOLE records, [c0 c1 c2 0 | c0 c1 c2 0]: elements 3..7 of every pixel are
+ * overwritten.  This is what removes the torch.cat of ema_vfi.py:134 (the warp writes where DCN layer 1 gathers from).
+ * Without the flag only the C channels described by `out` are written, whatever its strides are.  The flag with an `out`
+ * that is not such a view is VFI_ERR_INVALID. */
+#define VFI_WARP_OUT_TAIL_RECORD 2
 
 /* ---- warp: replaces EMA_VFI.warp, /root/reference/src/models/ema_vfi.py:149-171 ----------------------------- */
 /* out[b,c,y,x] = bilinear(src[b,c], x + flow[b,0,y,x], y + flow[b,1,y,x]), zeros outside, align_corners=True,

@@ -130,6 +130,51 @@ def test_dropin_patches_and_restores_both_seams():
     assert tv.deform_conv2d is orig_tv and WarpHost.warp is orig_warp and not dropin.installed()
 
 
+def test_fused_dropin_patches_and_restores_seams_3_and_4():
+    """install(fuse=True): the block class's forward and the module-level name `torch` (the cat of ema_vfi.py:134) are patched
+    on the class / module of the model handed in and restored by uninstall(); a class that only inherits `warp` gets its
+    override removed again.  With CPU tensors (no autocast) the fused routes do not apply and the stock code runs."""
+    import vfi_b200.refmodel as rm
+    from vfi_b200.refmodel import FusionPack, StockInterpolator
+
+    class Child(StockInterpolator):        # inherits warp
+        pass
+
+    orig_fwd, real_torch = FusionPack.forward, rm.torch
+    dropin.install(Child, fuse=True, patch_torchvision=False)
+    try:
+        assert FusionPack.forward is not orig_fwd and FusionPack.forward._vfi_orig is orig_fwd
+        assert rm.torch is not real_torch and rm.torch.nn is real_torch.nn and rm.torch.float32 is real_torch.float32
+        assert "warp" in Child.__dict__
+        a, b = torch.rand(1, 64, 4, 4), torch.rand(1, 3, 4, 4)
+        assert torch.equal(rm.torch.cat((a, b), dim=1), real_torch.cat((a, b), dim=1))       # ordinary cats pass through
+        pack = FusionPack(67).eval()
+        x = torch.randn(1, 67, 8, 8)
+        with torch.no_grad():
+            assert torch.equal(pack(x), orig_fwd(pack, x))                                   # CPU / fp32: not fusable -> stock forward
+    finally:
+        dropin.uninstall()
+    assert FusionPack.forward is orig_fwd and rm.torch is real_torch and "warp" not in Child.__dict__
+    assert Child.warp is StockInterpolator.warp
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
+def test_fused_dropin_finds_the_reference_block_class():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, "/root/reference")
+    try:
+        import src.models.ema_vfi as ref
+    finally:
+        sys.path.remove("/root/reference")
+    orig = ref.ModulatedDeformConvPack.forward
+    dropin.install(ref.EMA_VFI, fuse=True, patch_torchvision=False)
+    try:
+        assert ref.ModulatedDeformConvPack.forward is not orig and type(ref.torch).__name__ == "_TorchProxy"
+    finally:
+        dropin.uninstall()
+    assert ref.ModulatedDeformConvPack.forward is orig and type(ref.torch).__name__ == "module"
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
 def test_dropin_intercepts_the_unmodified_reference_model():
     """EMA_VFI.forward must hit the warp seam first (call site ema_vfi.py:130); on a CPU box the CUDA op then refuses."""

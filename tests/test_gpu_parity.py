@@ -116,11 +116,26 @@ def test_warp_into_tail_plane_records():
     ref = oracle.warp_fwd(src.float().numpy(), flow.float().numpy())
     pl = ops.Planes(2, 40, 64, DEV)
     pl.tail.fill_(7.0)                                            # garbage: the kernel must overwrite pad channels with 0
-    out = vfi_b200.warp(src.to(DEV), flow.to(DEV), out=pl.tail_nchw(3))
+    out = vfi_b200.warp(src.to(DEV), flow.to(DEV), out=pl.tail_nchw(3), tail_record=True)
     assert out.data_ptr() == pl.tail.data_ptr()
     assert relerr(pl.tail_nchw(3), ref) <= 1e-2
     assert float(pl.tail[..., 3].abs().max()) == 0.0 and torch.equal(pl.tail[..., 4:], pl.tail[..., :4])   # mirrored halves
     assert maxabs(pl.tail_nchw(3), vfi_b200.warp(src.to(DEV), flow.to(DEV))) == 0.0   # same values as the planar kernel
+
+
+def test_warp_into_a_slice_of_an_8_channel_tensor_keeps_the_other_channels():
+    """Without VFI_WARP_OUT_TAIL_RECORD the warp writes exactly the channels `out` describes, whatever its strides: a
+    [:, :3] slice of an ordinary channels-last bf16 tensor has the strides of a tail plane but is not one."""
+    g = torch.Generator().manual_seed(16)
+    src = torch.randn(1, 3, 24, 40, generator=g).to(torch.bfloat16).to(DEV)
+    flow = (3 * torch.randn(1, 2, 24, 40, generator=g)).to(torch.bfloat16).to(DEV)
+    buf = torch.full((1, 8, 24, 40), 7.0, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    out = vfi_b200.warp(src, flow, out=buf[:, :3])
+    assert out.data_ptr() == buf.data_ptr()
+    assert maxabs(buf[:, :3], vfi_b200.warp(src, flow)) == 0.0
+    assert float((buf[:, 3:] - 7.0).abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="TAIL_RECORD"):
+        vfi_b200.warp(src, flow, out=torch.empty_like(src), tail_record=True)
 
 
 def test_warp_empty_batch_and_errors():
@@ -628,7 +643,7 @@ def test_hot_path_cfg2_full_size_vs_stock_torchvision_cuda():
     out = HotPath(ws, bs, math="bf16_tc").run(frame2, flow, feat, convs)
     # the same chain with every intermediate kept
     src = ops.Planes(B, H, W, DEV, zero_tail=True)
-    ops.warp(frame2, flow, out=src.tail_nchw(3))
+    ops.warp(frame2, flow, out=src.tail_nchw(3), tail_record=True)
     layers = [(feat, src.tail_nchw(3))]
     for w, b, c27 in zip(ws, bs, convs):
         y = ops.deform_conv2d_fused(layers[-1][0], layers[-1][1], c27, w, b, math="bf16_tc")
@@ -662,7 +677,7 @@ def test_hot_path_cfg4_4k_vs_stock_torchvision_cuda(flow_kind, sigma):
     feat = feat.contiguous(memory_format=torch.channels_last)
     ws, bs = synthetic_weights(dtype=torch.bfloat16, device=DEV)
     src = ops.Planes(B, H, W, DEV, zero_tail=True)
-    ops.warp(frame2, flow, out=src.tail_nchw(3), division="reciprocal")
+    ops.warp(frame2, flow, out=src.tail_nchw(3), division="reciprocal", tail_record=True)
     warped = torch_ref.warp(frame2.float(), flow.float())
     assert float((src.tail_nchw(3).float() - warped).abs().max()) <= 1e-2 * float(warped.abs().max())
     del warped
@@ -706,6 +721,22 @@ def test_interpolated_frame_psnr_delta_bf16_hot_path():
         results[math] = psnr(out, gt)
         if math == "fp32":
             assert maxabs(out, stock) <= 2e-5
+    # the reference's own GPU inference mode (inference.py:158-159: no_grad + CUDA autocast), stock and with the fused drop-in
+    with torch.no_grad(), torch.autocast("cuda"):
+        stock_amp = model(a, b).float()
+    results["stock_cuda_autocast"] = psnr(stock_amp, gt)
+    before = dict(vfi_b200.dropin.call_counts())
+    vfi_b200.install(StockInterpolator, fuse=True)
+    try:
+        with torch.no_grad(), torch.autocast("cuda"):
+            fused = model(a, b).float()
+    finally:
+        vfi_b200.uninstall()
+    after = vfi_b200.dropin.call_counts()
+    assert (after["fused_block"] - before["fused_block"], after["fused_cat"] - before["fused_cat"],
+            after["fused_warp"] - before["fused_warp"], after["dcn"] - before["dcn"]) == (3, 1, 1, 0)
+    results["fused_autocast"] = psnr(fused, gt)
+    assert maxabs(fused, stock_amp) <= 2e-2
     print(f"PSNR vs ground truth: reference {ref_psnr:.4f} dB, " + ", ".join(f"{k} {v:.4f} dB" for k, v in results.items()))
     for k, v in results.items():
         assert abs(v - ref_psnr) <= 0.01, (k, v, ref_psnr)
@@ -718,7 +749,7 @@ def test_model_hot_path_fixture_through_the_dropin():
     import torchvision.ops
 
     z = load_golden("model_24x32")
-    vfi_b200.install(torch_ref.WarpHost)
+    vfi_b200.install(torch_ref.WarpHost, division="ieee")     # the golden vectors are the reference's CPU output
     try:
         host = torch_ref.WarpHost()
         warped = host.warp(cu(z["frame2"]), cu(z["feat"]), cu(z["flow"]))

@@ -22,6 +22,7 @@ ERR_NAMES = {1: "VFI_ERR_INVALID", 2: "VFI_ERR_UNSUPPORTED", 3: "VFI_ERR_CUDA", 
 F32, BF16, F16 = 0, 1, 2
 MATH_AUTO, MATH_FP32, MATH_BF16_TC, MATH_BF16_TC_HQ = 0, 1, 2, 3
 WARP_DIV_IEEE, WARP_DIV_RECIPROCAL = 0, 1
+WARP_OUT_TAIL_RECORD = 2
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 

@@ -803,6 +803,12 @@ static bool is_plane(const vfi_tensor* t, long long stride) {
   return t->dtype == VFI_BF16 && t->sc == 1 && t->sw == stride && t->sh == t->w * stride && t->sn == t->h * t->w * stride &&
          aligned(t->data, 16);
 }
+// ... or with any pixel stride >= min_stride that keeps pixels 16-byte aligned (rows and images dense): e.g. the main / tail
+// channel ranges of one [B,H,W,72] activation buffer.  The v7 kernel addresses planes through TMA tensor maps and takes these.
+static bool is_strided_plane(const vfi_tensor* t, long long min_stride) {
+  return t->dtype == VFI_BF16 && t->sc == 1 && t->sw >= min_stride && t->sw % 8 == 0 && t->sh == t->w * t->sw &&
+         t->sn == t->h * t->w * t->sw && aligned(t->data, 16);
+}
 
 int dcn_tc_pack_weight(const void* weight, int weight_dtype, const void* bias, int bias_dtype, long long O, long long C,
                        void* packed, float* bias_out, cudaStream_t st, int variant) {
@@ -921,10 +927,10 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   if (out_tail) {
     VFI_REQUIRE(O > TC_CMAIN && O <= TC_CMAX && out->c == TC_CMAIN && out_tail->c == O - TC_CMAIN && out_tail->data &&
                     out->n == x->n && out->h == x->h && out->w == x->w && out_tail->n == x->n && out_tail->h == x->h &&
-                    out_tail->w == x->w && is_plane(out, TC_CMAIN) && is_plane(out_tail, TC_CTAIL),
+                    out_tail->w == x->w && is_strided_plane(out, TC_CMAIN) && is_strided_plane(out_tail, TC_CTAIL),
                 VFI_ERR_UNSUPPORTED,
-                "%s: plane output needs out [B,64,H,W] and out_tail [B,O-64,H,W] as dense channels-last bf16 planes "
-                "(pixel strides 64 and 8 elements)", who);
+                "%s: plane output needs out [B,64,H,W] and out_tail [B,O-64,H,W] as channels-last bf16 planes "
+                "(pixel strides >= 64 / 8 elements and multiples of 8, dense rows)", who);
     p.out = out->data; p.out_tail = out_tail->data;
     p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0; p.out_rows = 0;
   } else {
@@ -939,11 +945,13 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   }
   if (x_tail) {
     VFI_REQUIRE(x_tail->data && x->c == TC_CMAIN && x_tail->c <= TC_CTAIL && x_tail->n == x->n && x_tail->h == x->h &&
-                    x_tail->w == x->w && is_plane(x, TC_CMAIN) && is_plane(x_tail, TC_CTAIL),
+                    x_tail->w == x->w && is_strided_plane(x, TC_CMAIN) && is_strided_plane(x_tail, TC_CTAIL),
                 VFI_ERR_UNSUPPORTED,
-                "%s: plane input needs x_main [B,64,H,W] and x_tail [B,<=8,H,W] as dense channels-last bf16 planes "
-                "(pixel strides 64 and 8 elements, pad channels of the tail zero)", who);
+                "%s: plane input needs x_main [B,64,H,W] and x_tail [B,<=8,H,W] as channels-last bf16 planes "
+                "(pixel strides >= 64 / 8 elements and multiples of 8, dense rows, pad channels of the tail zero)", who);
   }
+  const bool dense_planes = (!x_tail || (is_plane(x, TC_CMAIN) && is_plane(x_tail, TC_CTAIL))) &&
+                            (!out_tail || (is_plane(out, TC_CMAIN) && is_plane(out_tail, TC_CTAIL)));
   const size_t need = x_tail ? ws_main_off() : dcn_tc_workspace_bytes(x->n, x->h, x->w);
   VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
               "%s(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
@@ -961,7 +969,7 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   // ... or, for the fused form, a dense channels-last offset_conv output ([P][27], what a channels_last model hands over)
   const bool geo_cl = conv27 && (conv27->dtype == VFI_BF16 || conv27->dtype == VFI_F16) && conv27->sc == 1 && conv27->sw == 27 &&
                       conv27->sh == conv27->w * 27 && conv27->sn % 8 == 0 && conv27->w % 8 == 0 && aligned(conv27->data, 16);
-  const bool use_v6 = !hq && !force_v4 && C <= TC_CMAIN + 4 && (geo_cl || (bulk_ok(offset) && bulk_ok(mask)));
+  const bool use_v6 = !hq && !force_v4 && dense_planes && C <= TC_CMAIN + 4 && (geo_cl || (bulk_ok(offset) && bulk_ok(mask)));
   const bool use_v7 = !hq && !force_v4 && C <= TC_CMAIN + 4 && (offset->dtype == VFI_BF16 || offset->dtype == VFI_F16) &&
                       mask->dtype == offset->dtype;
   int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, (use_v6 || use_v7) ? 6 : 4);
@@ -975,7 +983,7 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
     p.x_main = ws + ws_main_off();
     p.x_tail = ws + ws_tail_off(P);
   }
-  p.main_stride = TC_CMAIN * 2; p.tail_stride = TC_CTAIL * 2;
+  p.main_stride = x_tail ? (uint32_t)(x->sw * 2) : TC_CMAIN * 2; p.tail_stride = x_tail ? (uint32_t)(x_tail->sw * 2) : TC_CTAIL * 2;
   p.offset = offset->data; p.mask = mask->data; p.fused27 = conv27 ? 1 : 0; p.geo_cl = (use_v6 && geo_cl) ? 1 : 0;
   p.f_sn = offset->sn; p.f_sc = offset->sc; p.f_sh = offset->sh; p.f_sw = offset->sw;
   p.m_sn = mask->sn; p.m_sc = mask->sc; p.m_sh = mask->sh; p.m_sw = mask->sw;
@@ -994,10 +1002,12 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   // v7 (default): v6's arithmetic with TMA tensor maps, the tail channels gathered by the geometry warps and four producer
   // groups (dcn_tc7.cuh).  VFI_DCN_KERNEL=v6 selects the previous kernel (A/B runs).
   static const bool force_v6 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '6'; }();
+  VFI_REQUIRE(dense_planes || (use_v7 && !force_v6), VFI_ERR_UNSUPPORTED,
+              "%s: planes with a pixel stride other than 64 / 8 elements need the default (v7) tensor-core kernel", who);
   if (use_v7 && !force_v6) {
     V7Args a;
     a.p = p;
-    a.o_main_px = TC_CMAIN * 2; a.o_tail_px = TC_CTAIL * 2;
+    a.o_main_px = out_tail ? (uint32_t)(out->sw * 2) : TC_CMAIN * 2; a.o_tail_px = out_tail ? (uint32_t)(out_tail->sw * 2) : TC_CTAIL * 2;
     bool ok = plane_map(&a.tm_main, p.x_main, TC_CMAIN, p.main_stride, p.B, p.H, p.W, V6_BOX_W, V6_BOX_H, false) &&
               plane_map(&a.tm_tail, p.x_tail, TC_CTAIL, p.tail_stride, p.B, p.H, p.W, V6_BOX_W, V6_BOX_H, false);
     VFI_REQUIRE(ok, VFI_ERR_UNSUPPORTED, "%s(bf16_tc): the activation planes cannot be described by a TMA tensor map", who);

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(WARPF_BLOCK) warp_fwd_fast_kernel(const WarpPa
     if (x >= W) continue;
     if constexpr (REC) {
       // tail-plane record: 16 bytes per pixel = [c0 c1 c2 0 | c0 c1 c2 0] (mirrored halves, see dcn_tc.cu)
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + (long long)x * 8;
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + (long long)x * p.o_sw;
       const __nv_bfloat162 c01 = __floats2bfloat162_rn(r[i][0], r[i][1]), c2z = __floats2bfloat162_rn(r[i][2], 0.0f);
       const uint32_t lo = *reinterpret_cast<const uint32_t*>(&c01), hi = *reinterpret_cast<const uint32_t*>(&c2z);
       __stcs(reinterpret_cast<uint4*>(out), make_uint4(lo, hi, lo, hi));
@@ -475,9 +475,13 @@ extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const
   VFI_REQUIRE(src->h <= 65535 && src->n <= 65535, VFI_ERR_UNSUPPORTED, "vfi_warp_fwd: H and B must be <= 65535");
   WarpParams p = make_params(src, flow, out, flags);
   cudaStream_t st = (cudaStream_t)stream;
-  // tail-plane record output: [B,H,W,8] bf16 records holding C = 3 channels + zeros
-  const bool rec = src->dtype == VFI_BF16 && src->c == 3 && out->sc == 1 && out->sw == 8 && out->sh % 8 == 0 &&
-                   out->sn % 8 == 0 && aligned(out->data, 16);
+  // tail-plane record output ([B,H,W,8] bf16 records holding C = 3 channels + zeros): only on request, because whole
+  // 16-byte records are written -- a caller's [:, :3] slice of an ordinary channels-last tensor must keep channels 3..7
+  const bool rec_shape = src->dtype == VFI_BF16 && src->c == 3 && out->sc == 1 && out->sw >= 8 && out->sw % 8 == 0 && out->sh % 8 == 0 &&
+                         out->sn % 8 == 0 && aligned(out->data, 16);
+  const bool rec = (flags & VFI_WARP_OUT_TAIL_RECORD) != 0;
+  VFI_REQUIRE(!rec || rec_shape, VFI_ERR_INVALID,
+              "vfi_warp_fwd: VFI_WARP_OUT_TAIL_RECORD needs a bf16 [B,3,H,W] view of 16-byte channels-last records");
   // fast path: three planar channels with unit pixel strides
   const bool fast = src->c == 3 && src->sw == 1 && flow->sw == 1 && src->w >= 2 && src->h >= 2 && src->sh >= 0 && src->sc >= 0 &&
                     src->sn >= 0 && (rec || out->sw == 1);

@@ -29,31 +29,39 @@ class HotPath:
         self.biases = list(biases)
         self.math = math
         self._streams = None
-        self._bufs = None
-        self._bufs_key = None
+        self._bufs = {}
 
     # ---------------------------------------------------------------------------------------------- device API
     def run(self, frame2: torch.Tensor, flow: torch.Tensor, feat: torch.Tensor,
-            convs27: Sequence[torch.Tensor]) -> torch.Tensor:
+            convs27: Sequence[torch.Tensor], out: "ops.Planes | None" = None) -> torch.Tensor:
+        """Tensor-core form (bf16 channels-last ``feat``): returns :class:`ops.Planes`.  The activation planes between the
+        layers are cached per (shape, device, CUDA stream) and reused by the next call ON THAT STREAM; the RESULT is written
+        to ``out`` when given, else to a plane set of the same cache -- in that case **it is overwritten by the next ``run``
+        with the same key** (the benchmark's steady state: no allocation in the timed region).  Pass ``out=ops.Planes(...)``
+        to keep results across calls.  Any other input takes the generic path and returns a fresh [B,67,H,W] tensor."""
         if self._fast(frame2, feat):
             # Tensor-core path with the reference's glue folded away: the warp writes its 3 channels into the 16-byte
             # tail record of each pixel, the first DCN layer gathers from (feat, tail) directly (no torch.cat), every
             # layer reads the raw 27-channel offset_conv output (no chunk/cat/sigmoid) and writes the two planes the
             # next layer gathers from.  Returns ops.Planes (``.to_nchw()`` gives the logical [B,67,H,W] tensor).
             B, C, H, W = feat.shape
-            key = (B, H, W, feat.device)
-            if self._bufs is None or self._bufs_key != key:
+            # keyed by stream as well: buffers allocated under one stream are only ever reused in that stream's order
+            key = (B, H, W, feat.device, torch.cuda.current_stream(feat.device).cuda_stream)
+            bufs = self._bufs.get(key) if isinstance(self._bufs, dict) else None
+            if bufs is None:
+                if not isinstance(self._bufs, dict) or len(self._bufs) >= 4:
+                    self._bufs = {}
                 # ping-pong activation planes, allocated once; tail pad channels of `src` are zeroed once and stay zero
-                self._bufs = (ops.Planes(B, H, W, feat.device, zero_tail=True), ops.Planes(B, H, W, feat.device),
-                              ops.Planes(B, H, W, feat.device))
-                self._bufs_key = key
-            src, ping, pong = self._bufs
-            ops.warp(frame2, flow, out=src.tail_nchw(frame2.shape[1]))
+                bufs = self._bufs[key] = (ops.Planes(B, H, W, feat.device, zero_tail=True), ops.Planes(B, H, W, feat.device),
+                                          ops.Planes(B, H, W, feat.device))
+            src, ping, pong = bufs
+            ops.warp(frame2, flow, out=src.tail_nchw(frame2.shape[1]), tail_record=True)
             math = self.math if self.math != "auto" else "bf16_tc"
             x_main, x_tail = feat, src.tail_nchw(frame2.shape[1])
             dst = ping
-            for w, b, c27 in zip(self.weights, self.biases, convs27):
-                y = ops.deform_conv2d_fused(x_main, x_tail, c27, w, b, math=math, out=dst)
+            last = len(self.weights) - 1
+            for i, (w, b, c27) in enumerate(zip(self.weights, self.biases, convs27)):
+                y = ops.deform_conv2d_fused(x_main, x_tail, c27, w, b, math=math, out=out if (i == last and out is not None) else dst)
                 x_main, x_tail = y.main_nchw, y.tail_nchw()
                 dst = pong if dst is ping else ping
             return y
@@ -85,7 +93,8 @@ class HotPath:
         for s in self._streams:
             s.wait_stream(cur)
         B = frame2.shape[0]
-        keep = []
+        # device memory stays O(chunk): every per-chunk tensor is handed to the caching allocator as soon as Python drops it,
+        # record_stream() keeps the memory from being reused before the streams that touch it have passed
         for i in range(0, B, chunk):
             sl = slice(i, min(i + chunk, B))
             with torch.cuda.stream(s_in):
@@ -105,7 +114,6 @@ class HotPath:
                 s_out.wait_event(done)
                 out[sl].copy_(y, non_blocking=True)
                 y.record_stream(s_out)
-            keep.append((d, y))
         s_out.synchronize()
         return out
 

@@ -8,7 +8,9 @@ Every op raises when its inputs are not on a B200: there is no CPU or PyTorch fa
 """
 from __future__ import annotations
 
+import collections
 import ctypes
+import warnings
 from typing import Optional
 
 import torch
@@ -16,7 +18,32 @@ import torch
 from . import _lib
 from ._lib import check, desc, dtype_code, ref, require_cuda, stream_handle
 
-__all__ = ["warp", "warp_blend", "deform_conv2d", "deform_conv2d_fused", "Planes", "dcn_workspace_bytes", "launch_count", "reset_launch_count"]
+__all__ = ["warp", "warp_blend", "deform_conv2d", "deform_conv2d_fused", "Planes", "dcn_workspace_bytes", "launch_count", "reset_launch_count",
+           "fallback_counts", "reset_fallback_counts"]
+
+
+# Slower-but-correct routes the operators may take silently are counted here and announced once each (warnings.warn), so
+# that a shape or layout change that costs performance is visible: `fallback_counts()` after a run, or -W error in tests.
+_FALLBACKS: "collections.Counter[str]" = collections.Counter()
+_WARNED = set()
+
+
+def _note(kind: str, detail: str) -> None:
+    _FALLBACKS[kind] += 1
+    if kind not in _WARNED:
+        _WARNED.add(kind)
+        warnings.warn(f"vfi_b200: {kind}: {detail} (counted in vfi_b200.ops.fallback_counts(); reported once)", RuntimeWarning,
+                      stacklevel=3)
+
+
+def fallback_counts() -> dict:
+    """How often each slower route was taken since import / the last :func:`reset_fallback_counts`."""
+    return dict(_FALLBACKS)
+
+
+def reset_fallback_counts() -> None:
+    _FALLBACKS.clear()
+    _WARNED.clear()
 
 
 def launch_count() -> int:
@@ -68,7 +95,8 @@ class _WarpFn(torch.autograd.Function):
 _DIVISION = {"ieee": _lib.WARP_DIV_IEEE, "reciprocal": _lib.WARP_DIV_RECIPROCAL}
 
 
-def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee", out: Optional[torch.Tensor] = None,
+         tail_record: bool = False) -> torch.Tensor:
     """Backward-warp ``src`` [B,C,H,W] by ``flow`` [B,2,H,W] (pixels; channel 0 = x, 1 = y).
 
     Same result as the reference's grid build + normalise + ``F.grid_sample(bilinear, zeros,
@@ -77,10 +105,12 @@ def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee", out: Opt
     ``division`` selects which bit-level meaning of the reference's ``2.0 * v / (size-1)`` is replayed: ``"ieee"``
     (what the reference computes on CPU -- BASELINE config 1 and the golden vectors) or ``"reciprocal"`` (what aten
     computes for ``tensor / python_scalar`` on CUDA: a multiplication by the fp32 reciprocal).
-    ``out`` (optional, any strides) receives the result in place -- e.g. channels 64..66 of the fused feature buffer,
-    which removes the ``torch.cat`` of ema_vfi.py:134.
+    ``out`` (optional, any strides) receives the result in place: exactly the C channels it describes are written.
+    ``tail_record=True`` (VFI_WARP_OUT_TAIL_RECORD): ``out`` is the [B,3,H,W] view of a DCN tail plane
+    (:meth:`Planes.tail_nchw`) and the kernel writes whole 16-byte records ``[c0 c1 c2 0 | c0 c1 c2 0]`` -- elements 3..7
+    of every pixel are overwritten.  This is what removes the ``torch.cat`` of ema_vfi.py:134.
     """
-    return _WarpFn.apply(src, flow, _DIVISION[division], out)
+    return _WarpFn.apply(src, flow, _DIVISION[division] | (_lib.WARP_OUT_TAIL_RECORD if tail_record else 0), out)
 
 
 def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch.Tensor:
@@ -115,6 +145,25 @@ class Planes:
         self.main = torch.empty((B, H, W, MAIN_C), dtype=torch.bfloat16, device=device)
         alloc = torch.zeros if zero_tail else torch.empty
         self.tail = alloc((B, H, W, TAIL_C), dtype=torch.bfloat16, device=device)
+
+    @classmethod
+    def from_buffer72(cls, buf: torch.Tensor, channels: int = 67) -> "Planes":
+        """View one dense channels-last activation buffer ``[B,H,W,72]`` (bf16) as planes: main = channels 0..63, tail record
+        = channels 64..71 of every pixel (pixel stride 144 bytes for both).  The logical [B,channels,H,W] tensor is then the
+        plain strided view ``buf.permute(0, 3, 1, 2)[:, :channels]`` -- what the fused drop-in hands between the reference's
+        blocks and on to its stock convolutions, with no layout pass in between."""
+        if buf.dim() != 4 or buf.shape[-1] != MAIN_C + TAIL_C or buf.dtype != torch.bfloat16 or not buf.is_contiguous():
+            raise ValueError("from_buffer72 expects a contiguous bf16 [B,H,W,72] tensor")
+        self = cls.__new__(cls)
+        self.channels = channels
+        self.main = buf[..., :MAIN_C]
+        self.tail = buf[..., MAIN_C:]
+        self.buffer = buf
+        return self
+
+    def nchw_view(self) -> torch.Tensor:
+        """Zero-copy logical tensor of planes made by :meth:`from_buffer72`."""
+        return self.buffer.permute(0, 3, 1, 2)[:, : self.channels]
 
     def set_tail(self, t: torch.Tensor) -> None:
         """Fill the tail plane from a [B,c,H,W] tensor (c <= 8): channels, zero padding and, for c <= 4, the mirrored half."""
@@ -265,12 +314,17 @@ class _DcnFn(torch.autograd.Function):
             # The staged-box kernels (forward v6, weight gradient) read 16-bit offsets / masks.  fp16 keeps a sampling position
             # to 2^-11 of the offset (0.004 px at 8 px) -- far inside what rounding the activations to bf16 costs -- and is what
             # the reference's own autocast path hands over; the HQ mode keeps fp32 offsets and the v4 kernel.
+            _note("offset_fp16_rounding", "fp32 offsets / mask rounded to fp16 for the tensor-core kernels (math='bf16_tc' on fp32 "
+                  "offset tensors; 2^-11 relative on the sampling position)")
             offset = offset.clamp(-30000.0, 30000.0).half()
             mask = mask.half()
         if tc and offset.dtype != torch.float32:
             # the staged-box kernels (forward v6, weight gradient) stream offset / mask rows with bulk copies: unit pixel
             # stride.  A channels_last offset_conv output (layers 2 and 3 under channels_last training) costs one 54 B/px copy
             # here instead of the slower generic kernels.
+            if offset.stride(3) != 1 or mask.stride(3) != 1:
+                _note("offset_layout_copy", "offset / mask without unit pixel stride (channels_last) copied to NCHW for the "
+                      "tensor-core kernels: one 54 B/px pass")
             if offset.stride(3) != 1:
                 offset = offset.contiguous()
             if mask.stride(3) != 1:
@@ -328,6 +382,9 @@ class _DcnFn(torch.autograd.Function):
                 ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, _lib.MATH_BF16_TC)))
                 # the kernel's grad_out^T loaders take any strides, but a channels_last grad_out costs them 128 two-byte
                 # loads per thread and tile (measured 2.1 vs 0.7 ms per layer at config 3): one 134 B/px copy is cheaper
+                if grad_out.stride(3) != 1:
+                    _note("grad_out_layout_copy", "channels_last grad_out copied to NCHW for the tcgen05 weight-gradient kernel: "
+                          "one 134 B/px pass")
                 g_w = grad_out if grad_out.stride(3) == 1 else grad_out.contiguous()
                 rc = lib.vfi_dcn_bwd_weight_tc(ref(desc(g_w)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O,
                                                gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
@@ -336,6 +393,9 @@ class _DcnFn(torch.autograd.Function):
                     done = True
                 elif rc != 2:
                     check(rc, "vfi_dcn_bwd_weight_tc")
+                else:
+                    _note("wgrad_cuda_core_fallback", "the tcgen05 weight-gradient kernel does not take this call ("
+                          + _lib.last_error() + "); using the fp32 CUDA-core kernel (~13x slower at config 3)")
             if (need_w or need_b) and not done:
                 check(lib.vfi_dcn_bwd_weight(ref(desc(grad_out)), ref(desc(x)), ref(desc(offset)), ref(desc(mask)), O,
                                              gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
