@@ -38,6 +38,9 @@ WORKLOADS = {
     "cfg5": (8, 1080, 1920, 8.0, 1.5, "cfg5: stream of 256 independent 1080p frame pairs in batches of 8, sharded over the ranks, bf16"),
 }
 # SURVEY 8d (iii), worst-case locality: per-pixel independent displacements (not timed in round 1)
+# BASELINE config 3: training step (forward + backward + gradient all-reduce), handled by run_cfg3 below
+WORKLOADS["cfg3"] = (16, 256, 256, 2.0, 1.5, "cfg3: training step at crop 256x256, global batch 16: warp + concat + 3 x (offset_conv, DCNv2) "
+                     "forward + backward, gradient all-reduce over the ranks")
 WORKLOADS["cfg4_iid"] = (1, 2160, 3840, 64.0, 1.5, "cfg4, incoherent variant: 4K frame pair, batch 1, bf16, iid N(0, 64^2) px flow")
 FLOW_KIND = {"cfg4_iid": "iid"}          # everything else: the smooth field of hotpath.synthetic_inputs
 STREAM_PAIRS = 256
@@ -45,10 +48,46 @@ FLOP_PER_PX = 2 * 603 * 67          # one DCNv2 layer, algorithmic (SURVEY.md se
 WARP_BYTES_PER_PX_BF16 = (3 + 2 + 3) * 2
 
 
+def csrc_digest() -> str:
+    """sha256 over the kernel sources: what a committed ncu capture must have been taken from to describe this build."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "video-frame-interpolation_b200" / "csrc").glob("*.cu*")) + sorted((ROOT / "video-frame-interpolation_b200" / "csrc").glob("*.h")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic():
-    """DRAM bytes per launch of the hot kernels from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    """DRAM bytes per launch of the hot kernels from the committed `ncu --set full` captures (profiles/traffic.json, written by
+    scripts/update_traffic.py).  An entry counts only while the kernel sources are the ones it was captured from; otherwise the
+    bench line says null + why (the number is a property of a build, not of the benchmark run)."""
     f = ROOT / "profiles" / "traffic.json"
-    return json.loads(f.read_text()) if f.exists() else {}
+    d = json.loads(f.read_text()) if f.exists() else {}
+    now, out = csrc_digest(), {}
+    for k, v in d.items():
+        if isinstance(v, dict) and v.get("csrc_digest") == now:
+            out[k] = v["dram_bytes_per_launch"]
+            out[k + "_source"] = f"{v.get('report')} @ {v.get('commit')} (csrc {now})"
+        elif isinstance(v, dict):
+            out[k + "_source"] = f"stale: captured from csrc {v.get('csrc_digest')} @ {v.get('commit')}, tree is {now}"
+    return out
+
+
+def measured_gather_floor():
+    """scripts/microbench/gather_floor.cu on this pool (profiles/r02_*gather_floor*.jsonl): the producers' work of the DCN forward
+    alone -- entry reads, 36 x LDS.128 per pixel, blend, tcgen05.st, box copies -- in clocks per output pixel."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r02_*gather_floor*.jsonl")):
+        for ln in f.read_text().splitlines():
+            try:
+                r = json.loads(ln)
+            except ValueError:
+                continue
+            if r.get("mode") == "gather+entry+lerp+tmem_st+box_copy" and (best is None or r["clk_per_px"] < best["clk_per_px"]):
+                best = dict(r, file=f.name)
+    return best
 
 
 def peaks():
@@ -165,6 +204,119 @@ def run_reference_arm(args, desc, H, W):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------- cfg5: frames in, frames out
+def e2e_stream(args, topo, dev, H, W):
+    """BASELINE config 5 end to end: STREAM_PAIRS independent 1080p frame pairs as uint8 frames in pinned host memory -> interpolated
+    uint8 frames back on the host, through vfi_b200.stream.PairStreamer and the network (vfi_b200.refmodel.StockInterpolator: the
+    reference's layers as stock PyTorch, hot path through install(fuse=True)), the pairs sharded contiguously over the ranks in
+    batches of 8.  uint8 frames are the only PCIe traffic (6.2 MB per frame each way)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import vfi_b200
+    from vfi_b200 import stream
+    from vfi_b200.refmodel import StockInterpolator
+
+    torch.manual_seed(2026)
+    model = StockInterpolator().eval()
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        for blk in model.attention_blocks:       # SURVEY F4: offset_conv is zero-initialised; randomise it so the gather is exercised
+            blk.offset_conv.weight.normal_(0, 0.02, generator=g)
+            blk.offset_conv.bias.normal_(0, 0.5, generator=g)
+        model.motion_estimation[-1].weight.mul_(40.0)
+    model = model.to(dev)
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    n = STREAM_PAIRS + 1
+    frames = [np.roll(base, 3 * i, axis=1) for i in range(n)]
+    vfi_b200.install(StockInterpolator, fuse=True)
+    try:
+        ps = stream.PairStreamer(model, dev, batch_pairs=8, topology=topo, autocast_dtype=torch.float16)
+        list(ps.run(frames[:17]))                            # warm-up
+        torch.cuda.synchronize(dev)
+        if topo.world > 1:
+            dist.barrier()
+        h0, d0 = ps.stats["h2d_bytes"], ps.stats["d2h_bytes"]
+        t0 = time.perf_counter()
+        written = sum(1 for _ in ps.run(frames))
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        calls = vfi_b200.dropin.call_counts()
+    finally:
+        vfi_b200.uninstall()
+    h2d, d2h = ps.stats["h2d_bytes"] - h0, ps.stats["d2h_bytes"] - d0
+    if topo.world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    steps = max(1, -(-(STREAM_PAIRS // topo.world) // 8))
+    return {"value": STREAM_PAIRS / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d // steps), "d2h_bytes_per_step": int(d2h // steps),
+            "steps": steps, "ms_per_step": 1e3 * dt / steps, "pairs": STREAM_PAIRS, "written_this_rank": written,
+            "api": "vfi_b200.stream.PairStreamer over vfi_b200.refmodel.StockInterpolator with install(fuse=True): uint8 frames in pinned "
+                   "host memory in, interpolated uint8 frames out (inference.py:160-199), no_grad + fp16 autocast",
+            "seam_calls": calls}
+
+
+# --------------------------------------------------------------------------------------------------- cfg3: training step
+def run_cfg3(args, desc):
+    """Strong scaling (the global batch of 16 is fixed): samples/s over all ranks, CUDA events, max over ranks; the exposed part of
+    the gradient all-reduce is measured on rank 0 with events around the wait that follows backward."""
+    import torch
+    import torch.distributed as dist
+
+    import vfi_b200
+    from vfi_b200 import shard
+    from vfi_b200.trainstep import TrainStep
+
+    topo = shard.init_distributed()
+    dev = torch.device("cuda", topo.local_rank)
+    torch.cuda.set_device(dev)
+    math = "bf16_tc" if args.math == "auto" else args.math
+    ts = TrainStep(topo, dev, math=math, overlap=not args.no_overlap)
+    for _ in range(args.warmup):
+        ts.step()
+    if topo.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index or 0).start() if topo.is_root else None
+    vfi_b200.reset_launch_count()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ts.step()
+    e1.record()
+    if topo.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    launches = vfi_b200.launch_count()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms = e0.elapsed_time(e1) / args.steps
+    if topo.world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    for _ in range(5):                                   # separate, synchronising pass: how long the step waits for the exchange
+        ts.step(measure=True)
+    exposed_us = 1e3 * statistics.fmean(ts.exposed_ms) if ts.exposed_ms else 0.0
+    ok = bool(torch.isfinite(ts.flow.grad).all()) and bool(torch.isfinite(ts.bucket.flat).all())
+    if topo.is_root:
+        line = {"metric": "cfg3 training step samples/sec", "value": ts.global_batch / (ms * 1e-3), "unit": "samples/s", "n_gpus": topo.world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16" if math == "bf16_tc" else "f32", "data": "synthetic",
+                "config": {"workload": desc, "global_batch": ts.global_batch, "batch_per_gpu": ts.B, "height": ts.H, "width": ts.W, "math": math,
+                           "exchange": ("3 group all-reduces launched from autograd hooks (block 3 first), overlapped with backward"
+                                        if ts.overlap else "one flat-bucket all-reduce after backward"),
+                           "bucket_bytes": ts.bucket.numel * 4},
+                "gpu_launches": int(launches), "allreduce_exposed_us": exposed_us, "gradients_finite": ok, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if topo.world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -180,6 +332,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-overlap", action="store_true", help="cfg3: one all-reduce after backward instead of the overlapped group exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.dcn_kernel:
@@ -188,6 +341,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, desc, H, W)
+        return
+    if args.workload == "cfg3":
+        run_cfg3(args, desc)
         return
 
     import torch
@@ -203,6 +359,7 @@ def main():
     world = topo.world
     dev = torch.device("cuda", topo.local_rank)
     torch.cuda.set_device(dev)
+    affinity = shard.bind_to_gpu(topo.local_rank)          # before any pinned allocation: host buffers land on this GPU's node
     dtype = torch.bfloat16
     P = B * H * W
 
@@ -331,36 +488,39 @@ def main():
     except Exception as exc:   # never let the extension break the headline line
         print(f"bench: warp_blend timing skipped: {exc}", file=sys.stderr)
 
-    # ---------------------------------------------------------------- e2e: pinned host buffers through run_host
+    # ---------------------------------------------------------------- e2e: pinned host buffers through the public API
     e2e = None
-    if not args.no_e2e:
-        hf2, hflow, hfeat, hconvs = synthetic_inputs(B, H, W, dtype=dtype, seed=99 + topo.rank, flow_sigma=flow_sigma,
-                                                     offset_sigma=off_sigma, pinned_host=True,
-                                                     flow_kind=FLOW_KIND.get(args.workload, "smooth"))
-        if args.conv27_layout == "channels_last":
-            hconvs = [c.contiguous(memory_format=torch.channels_last).pin_memory() for c in hconvs]
-        hout = torch.empty((B, 67, H, W), dtype=dtype).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in (hf2, hflow, hfeat, *hconvs))
-        d2h = hout.numel() * hout.element_size()
+    if not args.no_e2e and args.workload == "cfg5":
+        e2e = e2e_stream(args, topo, dev, H, W)
+    elif not args.no_e2e:
+        from vfi_b200.hotpath import HostBatch
+
+        src = synthetic_inputs(B, H, W, dtype=dtype, device="cpu", seed=99 + topo.rank, flow_sigma=flow_sigma, offset_sigma=off_sigma,
+                               flow_kind=FLOW_KIND.get(args.workload, "smooth"))
+        hb = HostBatch(B, H, W, dtype=dtype, conv27_channels_last=args.conv27_layout == "channels_last").copy_from(*src)
+        del src
+        h2d, d2h = hb.h2d_bytes, hb.d2h_bytes
         n_e2e = args.e2e_steps or min(args.steps, 5)
-        if args.workload == "cfg5":
-            # every rank streams its contiguous share of the pairs (vfi_b200.shard.shard_pairs), one run_host call per batch
-            n_e2e = max(1, -(-len(shard.shard_pairs(STREAM_PAIRS, topo.rank, world, "contiguous")) // B))
-        path.run_host(hf2, hflow, hfeat, hconvs, hout)          # warm-up (stream creation, allocator)
+        path.run_host_batch(hb)                                 # warm-up (stream creation, allocator)
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            path.run_host(hf2, hflow, hfeat, hconvs, hout)      # returns after the D2H copy has completed
+            path.run_host_batch(hb)                             # returns after the D2H copy has completed
         torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
+        dt_rank = time.perf_counter() - t0
+        dt = dt_rank
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * B * n_e2e / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
-               "api": "vfi_b200.HotPath.run_host (pinned host tensors in/out, 3-stream frame pipeline)"}
-        del hf2, hflow, hfeat, hconvs, hout
+               "h2d_gbs_this_rank": h2d * n_e2e / dt_rank / 1e9, "d2h_gbs_this_rank": d2h * n_e2e / dt_rank / 1e9,
+               "copies_per_step": {"h2d": B, "d2h": B}, "cpu_affinity": affinity,
+               "api": "vfi_b200.HotPath.run_host_batch (frame-major pinned HostBatch: one H2D and one D2H copy per frame, 3-stream pipeline)",
+               "bound": "PCIe: the step moves feat (265 MB / frame) and three conv27 from the host -- tensors that are born on the device "
+                        "in the real pipeline (see --workload cfg5 for the frame-in / frame-out number)"}
+        del hb
 
     if not topo.is_root:
         if world > 1:
@@ -382,19 +542,23 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "DCNv2 forward (one launch per layer, 3 per step)",
                      "achieved": dcn_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                     "frac": dcn_tflops / pk["tensor_sustained"], "traffic": tr.get("dcn_tc_fwd_kernel"), "peak_source": pk["source"] + " sustained bf16",
+                     "frac": dcn_tflops / pk["tensor_sustained"], "traffic": tr.get("dcn_fwd"), "traffic_source": tr.get("dcn_fwd_source"), "peak_source": pk["source"] + " sustained bf16",
                      "frac_of_burst_peak": dcn_tflops / pk["tensor_burst"], "ms_per_launch": dcn_ms,
                      "algorithmic_flop_per_launch": P * FLOP_PER_PX,
                      # what actually bounds the operator on this SM: building one A row reads
                      # 9 taps x 4 corners x 128 B of activations through the 128 B/clk/SM load/store data path
                      "lsu_bound": (lambda f_hz: {"bytes_per_px": 36 * 128, "floor_ms": 1e3 * P * 36 / 148 / f_hz,
                                                  "frac": (1e3 * P * 36 / 148 / f_hz) / dcn_ms,
-                                                 "note": "36 x 128 B gather per output pixel / (128 B/clk/SM x 148 SMs) at the sampled SM clock"})(
+                                                 "note": "36 x 128 B gather per output pixel / (128 B/clk/SM x 148 SMs) at the sampled SM clock",
+                                                 "measured": (lambda m: None if m is None else {
+                                                     "clk_per_px": m["clk_per_px"], "ms": 1e3 * P * m["clk_per_px"] / 148 / f_hz,
+                                                     "frac": (1e3 * P * m["clk_per_px"] / 148 / f_hz) / dcn_ms, "producer_warps": m["producer_warps"],
+                                                     "source": "scripts/microbench/gather_floor.cu, " + m["file"]})(measured_gather_floor())})(
                          1e6 * float((clocks or {}).get("sm_mhz") or 1965.0))},
         "roofline_warp": {"bound": "hbm", "kernel": "warp_fwd (planar NCHW bf16 in/out, timed alone, 20 launches)",
                           "achieved": P * WARP_BYTES_PER_PX_BF16 / (planar_ms["bf16"] * 1e-3) / 1e9, "peak": pk["hbm"],
                           "unit": "GB/s", "frac": P * WARP_BYTES_PER_PX_BF16 / (planar_ms["bf16"] * 1e-3) / 1e9 / pk["hbm"],
-                          "traffic": tr.get("warp_fwd_kernel_bf16_planar"), "ms_per_launch": planar_ms["bf16"],
+                          "traffic": tr.get("warp_fwd_planar_bf16"), "traffic_source": tr.get("warp_fwd_planar_bf16_source"), "ms_per_launch": planar_ms["bf16"],
                           "algorithmic_bytes_per_launch": P * WARP_BYTES_PER_PX_BF16, "peak_source": pk["source"],
                           "f32": {"ms_per_launch": planar_ms["f32"],
                                   "achieved": 2 * P * WARP_BYTES_PER_PX_BF16 / (planar_ms["f32"] * 1e-3) / 1e9,

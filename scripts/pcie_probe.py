@@ -1,10 +1,22 @@
 """Pinned-memory copy bandwidth of this box: H2D alone, D2H alone, both at once (the ceiling of bench.py's e2e leg)."""
 import json
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
-    dev = torch.device("cuda:0")
+    # under torchrun every rank probes its own GPU AT THE SAME TIME (a barrier lines the ranks up): what the host fabric gives
+    # when all the GPUs of the box copy at once is the ceiling of the multi-GPU e2e leg
+    from vfi_b200 import shard
+
+    topo = shard.init_distributed()
+    dev = torch.device("cuda", topo.local_rank)
+    torch.cuda.set_device(dev)
+    aff = shard.bind_to_gpu(topo.local_rank)
     n = 1 << 30
     h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -14,6 +26,8 @@ def main():
     res = {}
 
     def run(h2d, d2h, reps=4, piece=n):
+        if topo.world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -36,7 +50,18 @@ def main():
     res["both_each_GBps"] = run(True, True)
     res["h2d_alone_8MB_pieces_GBps"] = run(True, False, piece=8 << 20)
     res["both_each_8MB_pieces_GBps"] = run(True, True, piece=8 << 20)
-    print(json.dumps(res))
+    res.update(rank=topo.rank, world=topo.world, cpu_affinity=aff)
+    if topo.world > 1:
+        allr = [None] * topo.world
+        torch.distributed.all_gather_object(allr, res)
+        if topo.is_root:
+            for r in allr:
+                print(json.dumps(r))
+            print(json.dumps({"world": topo.world, "sum_h2d_alone_GBps": sum(r["h2d_alone_GBps"] for r in allr),
+                              "sum_both_each_GBps": sum(r["both_each_GBps"] for r in allr)}))
+        torch.distributed.destroy_process_group()
+    else:
+        print(json.dumps(res))
 
 
 if __name__ == "__main__":

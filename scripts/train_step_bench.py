@@ -18,25 +18,7 @@ import vfi_b200
 from vfi_b200 import shard
 
 
-class Block(torch.nn.Module):
-    """offset_conv + modulated DCN as in ema_vfi.py:41-60 (stock conv for the offsets, the op under test for the DCN)."""
-
-    def __init__(self, dcn):
-        super().__init__()
-        self.offset_conv = torch.nn.Conv2d(67, 27, 3, padding=1)
-        self.weight = torch.nn.Parameter(torch.empty(67, 67, 3, 3).uniform_(-1, 1) / 603 ** 0.5)
-        self.bias = torch.nn.Parameter(torch.empty(67).uniform_(-1, 1) / 603 ** 0.5)
-        torch.nn.init.normal_(self.offset_conv.weight, std=0.02)
-        torch.nn.init.normal_(self.offset_conv.bias, std=0.5)
-        self.dcn = dcn
-
-    def forward(self, x):
-        # fp32 master parameters; in the bf16 mode they are cast per step and autograd returns fp32 gradients to them
-        dt = x.dtype
-        c27 = torch.nn.functional.conv2d(x, self.offset_conv.weight.to(dt), self.offset_conv.bias.to(dt), padding=1)
-        o1, m, o2 = c27.chunk(3, dim=1)
-        return self.dcn(x, torch.cat((o1, o2), 1), self.weight.to(dt), self.bias.to(dt), stride=1, padding=1, dilation=1,
-                        mask=torch.sigmoid(m))
+from vfi_b200.trainstep import FusionBlockParams as Block, stock_warp  # noqa: E402
 
 
 def main():

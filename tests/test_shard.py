@@ -78,3 +78,72 @@ def test_world_size_2_gradient_exchange_and_gather_over_gloo():
         assert p.exitcode == 0
     assert ok and same_ptr and keys == list(range(6))
     assert numel == 3 * 4 * 9 + 4 + 4 * 2 * 9 + 2
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    shard.init_distributed("gloo")
+    torch.manual_seed(0)                      # identical replicas
+    blocks = torch.nn.ModuleList([torch.nn.Conv2d(3, 3, 3, padding=1) for _ in range(3)])
+    groups = [list(b.parameters()) for b in reversed(blocks)]          # the last block's gradients are final first
+    bucket = shard.GradBucket(blocks.parameters(), groups=groups)
+    bucket.zero()
+    bucket.attach()
+    bucket.enable_overlap()
+    data = torch.arange(8 * 3 * 6 * 6, dtype=torch.float32).reshape(8, 3, 6, 6) / 300.0
+    mine = shard.shard_pairs(8, rank, world, "contiguous")
+    results = []
+    for step in range(2):                     # twice: the counters must reset
+        bucket.zero()
+        bucket.begin_step()
+        x = data[mine]
+        for b in blocks:
+            x = b(x)
+        x.square().sum().backward()
+        exposed = bucket.finish_overlap()
+        results.append((bucket.flat.clone(), list(bucket.launched), exposed))
+    # reference: every rank's local gradient, averaged
+    ref_blocks = torch.nn.ModuleList([torch.nn.Conv2d(3, 3, 3, padding=1) for _ in range(3)])
+    ref_blocks.load_state_dict(blocks.state_dict())
+    x = data[mine]
+    for b in ref_blocks:
+        x = b(x)
+    x.square().sum().backward()
+    local = torch.cat([p.grad.flatten() for g in reversed(ref_blocks) for p in g.parameters()])
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    expect = sum(gathered) / world
+    ok = all(torch.allclose(r[0], expect, rtol=1e-5, atol=1e-6) for r in results)
+    same_ptr = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    if rank == 0:
+        out.put((ok, same_ptr, [r[1] for r in results], bucket.segments))
+    bucket.disable_overlap()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_overlapped_group_exchange_over_gloo():
+    """The all-reduce of a group is launched from the autograd hook of its last gradient -- block 3 first, block 1 last -- and
+    the bucket holds the mean of the ranks' gradients afterwards, step after step."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, same_ptr, launched, segments = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and same_ptr
+    assert launched == [[0, 1, 2], [0, 1, 2]]           # group 0 = the last block
+    assert segments == [(0, 84), (84, 168), (168, 252)]
+
+
+def test_grad_bucket_groups_must_partition_the_parameters():
+    m = torch.nn.ModuleList([torch.nn.Linear(2, 2), torch.nn.Linear(2, 2)])
+    with pytest.raises(ValueError, match="partition"):
+        shard.GradBucket(m.parameters(), groups=[list(m[0].parameters())])
+    b = shard.GradBucket(m.parameters())
+    with pytest.raises(ValueError, match="groups"):
+        b.enable_overlap()

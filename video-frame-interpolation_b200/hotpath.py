@@ -118,6 +118,83 @@ class HotPath:
         return out
 
 
+    def run_host_batch(self, hb: "HostBatch", chunk: int = 1) -> torch.Tensor:
+        """``run_host`` on a frame-major :class:`HostBatch`: one H2D copy (the chunk's whole input record) and one D2H copy per
+        chunk, pipelined over three streams.  Returns ``hb.out`` after the last copy has completed."""
+        dev = self.weights[0].device
+        if self._streams is None:
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        s_in, s_run, s_out = self._streams
+        cur = torch.cuda.current_stream(dev)
+        for s in self._streams:
+            s.wait_stream(cur)
+        for i in range(0, hb.B, chunk):
+            sl = slice(i, min(i + chunk, hb.B))
+            with torch.cuda.stream(s_in):
+                d_arena = hb.arena[sl].to(dev, non_blocking=True)           # one cudaMemcpyAsync
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ready)
+                f2, fl, ft, cv = hb.views(d_arena)
+                ys = []
+                for j in range(d_arena.shape[0]):                            # a frame's planes are dense: one frame per launch set
+                    yj = self.run(f2[j:j + 1], fl[j:j + 1], ft[j:j + 1], [c[j:j + 1] for c in cv])
+                    ys.append(yj.to_nchw() if isinstance(yj, ops.Planes) else yj)
+                y = ys[0] if len(ys) == 1 else torch.cat(ys, 0)
+                d_arena.record_stream(s_run)
+                done = torch.cuda.Event()
+                done.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                hb.out[sl].copy_(y, non_blocking=True)                       # one cudaMemcpyAsync
+                y.record_stream(s_out)
+        s_out.synchronize()
+        return hb.out
+
+
+class HostBatch:
+    """Pinned host staging of one batch, FRAME-MAJOR: frame i's inputs -- frame2 [3,H,W], flow [2,H,W], feat [64,H,W]
+    (channels-last inside the record), three conv27 [27,H,W] -- are one contiguous record, so a chunk of frames crosses PCIe
+    as ONE cudaMemcpyAsync in each direction (``HotPath.run_host_batch``) instead of one per tensor.  The fields are ordinary
+    strided views of the arena: fill them in place (``copy_from``) or hand them to whatever produces the tensors."""
+
+    def __init__(self, B: int, H: int, W: int, *, dtype=torch.bfloat16, out_channels: int = 67, conv27_channels_last: bool = False):
+        hw = H * W
+        sizes = [3 * hw, 2 * hw, 64 * hw, 27 * hw, 27 * hw, 27 * hw]
+        self.offsets = [0]
+        for n in sizes:
+            self.offsets.append(self.offsets[-1] + n)
+        self.B, self.H, self.W, self.dtype, self.conv_cl = B, H, W, dtype, conv27_channels_last
+        self.arena = torch.empty((B, self.offsets[-1]), dtype=dtype).pin_memory()
+        self.out = torch.empty((B, out_channels, H, W), dtype=dtype).pin_memory()
+        self.frame2, self.flow, self.feat, self.convs = self.views(self.arena)
+
+    def views(self, arena: torch.Tensor):
+        """The six tensors of an arena laid out like this one (host arena or its device copy)."""
+        o, n, H, W = self.offsets, arena.shape[0], self.H, self.W
+        frame2 = arena[:, o[0]:o[1]].view(n, 3, H, W)
+        flow = arena[:, o[1]:o[2]].view(n, 2, H, W)
+        feat = arena[:, o[2]:o[3]].view(n, H, W, 64).permute(0, 3, 1, 2)
+        convs = [arena[:, o[3 + i]:o[4 + i]].view(n, H, W, 27).permute(0, 3, 1, 2) if self.conv_cl else arena[:, o[3 + i]:o[4 + i]].view(n, 27, H, W)
+                 for i in range(3)]
+        return frame2, flow, feat, convs
+
+    def copy_from(self, frame2, flow, feat, convs) -> "HostBatch":
+        self.frame2.copy_(frame2); self.flow.copy_(flow); self.feat.copy_(feat)
+        for d, c in zip(self.convs, convs):
+            d.copy_(c)
+        return self
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.arena.numel() * self.arena.element_size()
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.out.numel() * self.out.element_size()
+
+
 def synthetic_inputs(B: int, H: int, W: int, *, dtype=torch.bfloat16, device="cuda", seed: int = 1234,
                      flow_sigma: float = 8.0, offset_sigma: float = 1.5, pinned_host: bool = False,
                      flow_kind: str = "smooth"):
