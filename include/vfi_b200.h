@@ -179,6 +179,14 @@ int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tensor* x, const
  * of gcol's dtype in the workspace (vfi_dcn_bwd_data_cols_workspace_bytes; bf16 gcol rounds x to bf16, f32 gcol keeps fp32
  * arithmetic throughout: tolerance of vfi_dcn_bwd_data); offset / mask: any dtype and strides.  Any of the three outputs may
  * be NULL.  Semantics (liveness, corner validity, ungated offset gradient) are vfi_dcn_bwd_data's. */
+/* The column gradient itself on the tensor cores (bf16 operands, fp32 accumulation in tensor memory, bf16 result): replaces the
+ * grad_columns GEMM torchvision::_deform_conv2d_backward makes with its BLAS.  grad_out: [B,O,H,W], any dtype and strides, read
+ * where it lies (O <= 68); weight: [O,C,3,3] contiguous (C <= 72); gcol: [B*H*W][648] bf16, 16-byte aligned, gcol_ld = 648,
+ * column k * 72 + c (columns c >= C of every tap are written as zeros).  Workspace: vfi_dcn_gcol_workspace_bytes(), 256-byte
+ * aligned. */
+size_t vfi_dcn_gcol_workspace_bytes(void);
+int vfi_dcn_gcol(const vfi_tensor* grad_out, const void* weight, int32_t weight_dtype, int64_t C, void* gcol, int64_t gcol_ld,
+                 void* workspace, size_t workspace_bytes, vfi_stream_t stream);
 size_t vfi_dcn_bwd_data_cols_workspace_bytes(int64_t B, int64_t H, int64_t W, int32_t gcol_dtype);
 int vfi_dcn_bwd_data_cols(const void* gcol, int32_t gcol_dtype, int64_t gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
                           const vfi_tensor* mask, float* grad_x_rows, int64_t grad_x_ld, const vfi_tensor* grad_offset,

@@ -551,6 +551,34 @@ def test_dcn_data_grads_from_column_gradient(B, H, W, sigma):
     assert relerr(x.grad, x2.grad) <= 2e-2 and relerr(off.grad, off2.grad) <= 2e-2 and relerr(m.grad, m2.grad) <= 2e-2
 
 
+@pytest.mark.parametrize("B,H,W,cl,gdt", [(2, 24, 40, False, torch.bfloat16), (1, 9, 13, False, torch.float32), (3, 16, 24, True, torch.bfloat16),
+                                          (1, 128, 130, True, torch.float32)])
+def test_dcn_column_gradient_gemm_on_tcgen05(B, H, W, cl, gdt):
+    """vfi_dcn_gcol: gcol[p, k * 72 + c] = sum_o grad_out[p, o] * W[o, c, k] on the tensor cores (grad_out read where it lies, A
+    operand in tensor memory, weights resident in shared memory, TMA stores) against the same product in fp32 on the
+    bf16-rounded operands.  P = 117 and 16,640 exercise the partial last tile; channels_last / fp32 grad_out the loaders."""
+    import ctypes
+
+    from vfi_b200 import _lib, ops
+
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + H)
+    go = torch.randn(B, 67, H, W, device=DEV, generator=g).to(gdt)
+    if cl:
+        go = go.contiguous(memory_format=torch.channels_last)
+    w = ((torch.rand(67, 67, 3, 3, device=DEV, generator=g) * 2 - 1) / 603 ** 0.5).to(torch.bfloat16)
+    P = B * H * W
+    gcol = torch.full((P, 648), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lib = _lib.load()
+    ws = torch.empty(int(lib.vfi_dcn_gcol_workspace_bytes()), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.vfi_dcn_gcol(_lib.ref(_lib.desc(go)), w.data_ptr(), _lib.dtype_code(w.dtype), 67, gcol.data_ptr(), 648, ws.data_ptr(),
+                                ws.numel(), _lib.stream_handle(torch.device(DEV))), "vfi_dcn_gcol")
+    rows = go.to(torch.bfloat16).float().permute(0, 2, 3, 1).reshape(P, 67)
+    ref = rows @ ops.cols_weight_matrix(w, torch.float32)[:67]
+    assert torch.isfinite(gcol.float()).all()
+    assert relerr(gcol, ref) <= 5e-3                      # bf16 rounding of the result
+    assert float(gcol.view(P, 9, 72)[:, :, 67:].abs().max()) == 0.0      # pad columns are zeros
+
+
 def test_dcn_training_gradients_config3_full_size_vs_stock_torchvision_cuda():
     """BASELINE config 3 at full size (16 x 67 x 256 x 256, forward + backward of one DCNv2 layer): all five gradients of
     (a) the fp32 path and (b) the bf16 tensor-core training path (tcgen05 forward and weight gradient, column-gradient

@@ -53,6 +53,8 @@ SIGNATURES = {
     "vfi_dcn_fwd_fused": (c_int, [_T, _T, _T, c_void_p, c_int32, c_void_p, c_int32, _T, _T, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "vfi_dcn_bwd_data": (c_int, [_T, _T, _T, _T, c_void_p, c_int32, c_int64, _T, _T, _T, c_void_p, c_size_t, c_void_p]),
     "vfi_dcn_bwd_weight": (c_int, [_T, _T, _T, _T, c_int64, c_void_p, c_void_p, c_void_p]),
+    "vfi_dcn_gcol_workspace_bytes": (c_size_t, []),
+    "vfi_dcn_gcol": (c_int, [_T, c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "vfi_dcn_bwd_data_cols_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32]),
     "vfi_dcn_bwd_data_cols": (c_int, [c_void_p, c_int32, c_int64, _T, _T, _T, c_void_p, c_int64, _T, _T, c_void_p, c_size_t,
                               c_void_p]),

@@ -37,6 +37,9 @@ int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, co
                          const vfi_tensor* mask, float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset,
                          const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
+size_t dcn_tc_gcol_workspace_bytes();
+int dcn_tc_gcol(const vfi_tensor* grad_out, const void* weight, int weight_dtype, long long C, void* gcol, long long gcol_ld,
+                void* workspace, size_t workspace_bytes, cudaStream_t st);
 unsigned long long* dcn_tc_debug_buffer();
 int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, cudaStream_t st);
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight,
@@ -133,6 +136,13 @@ extern "C" int vfi_dcn_bwd_data_cols(const void* gcol, int32_t gcol_dtype, int64
                                      size_t workspace_bytes, vfi_stream_t stream) {
   return dcn_tc_bwd_data_cols(gcol, gcol_dtype, gcol_ld, x, offset, mask, grad_x_rows, grad_x_ld, grad_offset, grad_mask,
                               workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t vfi_dcn_gcol_workspace_bytes(void) { return dcn_tc_gcol_workspace_bytes(); }
+
+extern "C" int vfi_dcn_gcol(const vfi_tensor* grad_out, const void* weight, int32_t weight_dtype, int64_t C, void* gcol,
+                            int64_t gcol_ld, void* workspace, size_t workspace_bytes, vfi_stream_t stream) {
+  return dcn_tc_gcol(grad_out, weight, weight_dtype, C, gcol, gcol_ld, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int vfi_debug_abort_info(uint64_t* info36) { return dcn_tc_abort_info(reinterpret_cast<unsigned long long*>(info36)); }

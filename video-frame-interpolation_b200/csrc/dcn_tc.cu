@@ -725,6 +725,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParam
 #include "dcn_tc7.cuh"   // v7 (default): v6 + TMA tensor maps, tail channels gathered by the geometry warps, four producer groups
 #include "dcn_tc6_wgrad.cuh"   // weight / bias gradient on tcgen05 (pixel-reduction GEMM, accumulators persistent in TMEM)
 #include "dcn_bwd_cols.cuh"    // grad_x / grad_offset / grad_mask from the column gradient (channels-last, vector reductions)
+#include "dcn_gcol.cuh"        // the column gradient itself: gcol = grad_out x W on tcgen05 (A in TMEM, weights resident in smem)
 
 // ------------------------------------------------------------------------------------------------ UMMA self test
 // D[128, 80] = A[128, K] * Bm[80, K]^T with A, Bm row-major bf16 in global memory, K a multiple of 64.  Uses exactly
@@ -1219,6 +1220,54 @@ size_t dcn_tc_bwd_data_cols_workspace_bytes(long long B, long long H, long long 
   const long long P = B * H * W;
   const size_t es = gcol_dtype == VFI_F32 ? 4 : 2;
   return cols_tail_off(P, es) + (((size_t)P * TC_CTAIL * es + 255) / 256) * 256 + 256;
+}
+
+// Column gradient gcol[P][648] (bf16, column k * 72 + c) = grad_out[P][O] x W[O][C][k] on the tensor cores (dcn_gcol.cuh).
+// Workspace: the 12-atom weight image.
+size_t dcn_tc_gcol_workspace_bytes() { return (size_t)GC_ATOMS * TC_B_BYTES + 256; }
+
+int dcn_tc_gcol(const vfi_tensor* grad_out, const void* weight, int weight_dtype, long long C, void* gcol, long long gcol_ld,
+                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const char* who = "vfi_dcn_gcol";
+  VFI_REQUIRE(grad_out && weight && gcol, VFI_ERR_INVALID, "%s: null pointer", who);
+  const long long O = grad_out->c;
+  VFI_REQUIRE(O > 0 && O <= 68 && C > 0 && C <= TC_CMAX, VFI_ERR_UNSUPPORTED, "%s: supports O <= 68, C <= %d (got O=%lld, C=%lld)", who,
+              TC_CMAX, O, C);
+  VFI_REQUIRE(gcol_ld == GC_TAPS * GC_LD && aligned(gcol, 16), VFI_ERR_INVALID, "%s: gcol must be a 16-byte aligned [P][%d] bf16 matrix",
+              who, GC_TAPS * GC_LD);
+  const long long P = (long long)grad_out->n * grad_out->h * grad_out->w;
+  if (P == 0) return VFI_OK;
+  VFI_REQUIRE(grad_out->data, VFI_ERR_INVALID, "%s: null data pointer", who);
+  VFI_REQUIRE(P < 2147483647LL - TC_M, VFI_ERR_UNSUPPORTED, "%s: more than 2^31 pixels per call", who);
+  VFI_REQUIRE(workspace && workspace_bytes >= dcn_tc_gcol_workspace_bytes() && aligned(workspace, 256), VFI_ERR_WORKSPACE,
+              "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, dcn_tc_gcol_workspace_bytes(), workspace_bytes);
+  uint8_t* wimg = reinterpret_cast<uint8_t*>(workspace);
+  const int n = GC_ATOMS * TC_N * 64;
+  VFI_DISPATCH(weight_dtype, TW, {
+    pack_gcol_weight_kernel<TW><<<ceil_div(n, 256), 256, 0, st>>>(reinterpret_cast<const TW*>(weight), (int)O, (int)C, wimg);
+  });
+  VFI_LAUNCH_CHECK("pack_gcol_weight_kernel");
+  GcArgs q;
+  q.gout = grad_out->data; q.g_sn = grad_out->sn; q.g_sc = grad_out->sc; q.g_sh = grad_out->sh; q.g_sw = grad_out->sw;
+  q.wimg = wimg;
+  q.B = (int)grad_out->n; q.H = (int)grad_out->h; q.W = (int)grad_out->w; q.O = (int)O;
+  q.P = P;
+  q.num_tiles = ceil_div(P, TC_M);
+  const long long dim[4] = {gcol_ld, P, 1, 1}, stb[3] = {gcol_ld * 2, gcol_ld * 2 * P, gcol_ld * 2 * P};
+  const int box[4] = {GC_LD, TC_M, 1, 1};
+  VFI_REQUIRE(make_map4(&q.tm_gcol, gcol, dim, stb, box, false), VFI_ERR_UNSUPPORTED, "%s: gcol cannot be described by a TMA tensor map", who);
+  int dev = 0, sms = 148;
+  VFI_CUDA(cudaGetDevice(&dev));
+  VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = q.num_tiles < sms ? q.num_tiles : sms;
+  const size_t smem = sizeof(GcSmem) + 1024;
+  VFI_DISPATCH(grad_out->dtype, TG, {
+    auto kern = dcn_gcol_gemm_kernel<TG>;
+    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, GC_THREADS, smem, st>>>(q);
+  });
+  VFI_LAUNCH_CHECK("dcn_gcol_gemm_kernel");
+  return VFI_OK;
 }
 
 int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,

@@ -265,12 +265,12 @@ def _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need
     TAP = MAIN_C + TAIL_C
     cdt = torch.float32 if f32_math else torch.bfloat16
     f32 = dict(dtype=torch.float32, device=dev)
-    wt = cols_weight_matrix(weight, cdt)
+    wt = cols_weight_matrix(weight, cdt) if (f32_math or O > 68) else None
     hw = H * W
     gx_rows = torch.zeros((B * hw, _GX_LD), **f32) if need_x else None
     goff = torch.empty(offset.shape, **f32) if need_off else None
     gmask = torch.empty(mask.shape, **f32) if need_mask else None
-    step = max(1, _COLS_CHUNK_BYTES // max(1, hw * _COLS_LD * wt.element_size()))
+    step = max(1, _COLS_CHUNK_BYTES // max(1, hw * _COLS_LD * (4 if f32_math else 2)))
     tf32 = torch.backends.cuda.matmul.allow_tf32
     try:
         if f32_math:
@@ -281,9 +281,17 @@ def _dcn_bwd_data_cols(grad_out, x, offset, mask, weight, need_x, need_off, need
                 n = (b1 - b0) * hw
                 if n == 0:
                     continue
-                g72 = torch.zeros((n, TAP), dtype=cdt, device=dev)
-                g72[:, :O] = grad_out[b0:b1].permute(0, 2, 3, 1).reshape(n, O)
-                gcol = torch.matmul(g72, wt)
+                if not f32_math and O <= 68:
+                    # tensor-core training path: the column gradient on tcgen05, grad_out read where it lies (vfi_dcn_gcol)
+                    gcol = torch.empty((n, _COLS_LD), dtype=cdt, device=dev)
+                    wsg = _workspace(dev, int(lib.vfi_dcn_gcol_workspace_bytes()))
+                    check(lib.vfi_dcn_gcol(ref(desc(grad_out[b0:b1])), weight.data_ptr(), dtype_code(weight.dtype), C, gcol.data_ptr(),
+                                           _COLS_LD, wsg.data_ptr(), wsg.numel(), stream_handle(dev)), "vfi_dcn_gcol")
+                else:
+                    # fp32 parity path: true fp32 GEMM arithmetic through the BLAS (TF32 off)
+                    g72 = torch.zeros((n, TAP), dtype=cdt, device=dev)
+                    g72[:, :O] = grad_out[b0:b1].permute(0, 2, 3, 1).reshape(n, O)
+                    gcol = torch.matmul(g72, wt)
                 ws = _workspace(dev, int(lib.vfi_dcn_bwd_data_cols_workspace_bytes(b1 - b0, H, W, dtype_code(cdt))))
                 check(lib.vfi_dcn_bwd_data_cols(gcol.data_ptr(), dtype_code(cdt), _COLS_LD, ref(desc(x[b0:b1])),
                                                 ref(desc(offset[b0:b1])), ref(desc(mask[b0:b1])),
