@@ -56,7 +56,7 @@ typedef enum vfi_dcn_math {
   VFI_DCN_MATH_FP32 = 1,  /* fp32 gather + FFMA contraction: the parity mode (max-abs 1e-5 vs torchvision fp32)     */
   VFI_DCN_MATH_BF16_TC = 2,/* bf16 operands, fp32 accumulate in TMEM via tcgen05.mma (C <= 72, O <= 80); the bilinear  */
                           /* blend of the four corners runs in packed bf16 FMAs (HFMA2.BF16)                          */
-  VFI_DCN_MATH_BF16_TC_HQ = 3 /* same, but the four-corner blend is done in fp32 and rounded to bf16 once            */
+  VFI_DCN_MATH_BF16_TC_HQ = 3 /* REMOVED in round 2 (fp32 four-corner blend on the v4 kernel): VFI_ERR_UNSUPPORTED      */
 } vfi_dcn_math;
 
 /* ---- library ----------------------------------------------------------------------------------------------- */
@@ -119,9 +119,9 @@ int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int
                         vfi_stream_t stream);
 
 /* Host-only query (no GPU needed): K element kk of block kb of the weight image multiplies weight[:, channel, tap] (channel
- * -1: zero padding or, for variant 6, the two bias slots 36/37 of block 9).  variant 4 = the v4 kernel's image (the one
- * vfi_dcn_pack_weight writes), 6 = the image the v6 kernel builds in its workspace, whose main blocks follow the thread <->
- * column mapping of tcgen05.st.16x256b. */
+ * -1: zero padding or the two bias slots 36/37 of block 9).  variant must be 6: the image the v6 / v7 kernels build in their
+ * workspace (and vfi_dcn_pack_weight writes), whose main blocks follow the thread <-> column mapping of tcgen05.st.16x256b.
+ * (variant 4, the round-1 v4 kernel's image, was removed with that kernel: VFI_ERR_INVALID.) */
 int vfi_dcn_k_order(int32_t variant, int32_t kb, int32_t kk, int32_t* tap, int32_t* channel);
 
 /* Converts an activation tensor of any supported layout/dtype (C <= 72) into planes: main_plane B*H*W*64 bf16,

@@ -210,14 +210,16 @@ def test_launcher_shims():
 
 def test_weight_image_k_order_is_a_bijection():
     """Host logic of the tensor-core path (no GPU): every (tap, channel) of the 3x3x67 contraction appears exactly once in
-    the K order of each kernel variant's weight image, and v6's main blocks follow the tcgen05.st.16x256b thread mapping
+    the K order of the v6 / v7 weight image, and its main blocks follow the tcgen05.st.16x256b thread mapping
     (thread u of a pixel holds the 16-byte chunks u and u + 4)."""
     import ctypes
 
     from vfi_b200 import _lib
 
     lib = _lib.load()
-    for variant, blocks in ((4, 11), (6, 10)):
+    tap, c = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.vfi_dcn_k_order(4, 0, 0, ctypes.byref(tap), ctypes.byref(c)) != 0   # the round-1 v4 kernel and its K order are gone
+    for variant, blocks in ((6, 10),):
         seen = {}
         for kb in range(blocks):
             for kk in range(64):
@@ -226,7 +228,7 @@ def test_weight_image_k_order_is_a_bijection():
                 if c.value >= 0:
                     assert (tap.value, c.value) not in seen, (variant, kb, kk)
                     seen[(tap.value, c.value)] = (kb, kk)
-        channels = 72 if variant == 4 else 68
+        channels = 68
         assert set(seen) == {(t, c) for t in range(9) for c in range(channels)}
     # v6 main block: K elements 16 i + 4 u + j  <->  channel 32 (i // 2) + 8 u + 4 (i % 2) + j
     for kk in range(64):

@@ -1,47 +1,31 @@
 // dcn_tc.cu -- DCNv2 on the tensor cores of sm_100a (bf16 operands, fp32 accumulate): the translation unit of the throughput path.
 //
-// What lives here:   host side of every tensor-core entry point (dispatch, argument checks, workspace layout), the weight and
-//                    input packers, the v4 forward kernel described below, and the tcgen05 self test;
-// dcn_tc6.cuh        the DEFAULT forward kernel (v6): A operand written to tensor memory by the gather warps, source box
-//                    staged in shared memory -- its header describes the design; v4 is kept for the HQ blend, C > 68 and
-//                    offset tensors v6 cannot stream;
+// What lives here:   host side of every tensor-core entry point (dispatch, argument checks, workspace layout, TMA tensor maps),
+//                    the weight and input packers, the PTX wrappers the kernels share, and the tcgen05 self test;
+// dcn_tc7.cuh        the forward kernel (v7): A operand written to tensor memory by the gather warps, source box / offsets /
+//                    output through TMA tensor maps, tail channels gathered by the geometry warps -- its header has the design;
+// dcn_tc6.cuh        v6, the round-1 kernel: kept as the bit-exactness reference of v7 (VFI_DCN_KERNEL=v6, one instantiation)
+//                    and for the box / geometry roles the weight-gradient kernel shares;
 // dcn_tc6_wgrad.cuh  weight / bias gradient (pixel-reduction GEMM, accumulators persistent in tensor memory);
+// dcn_gcol.cuh       column gradient gcol = grad_out x W (A in tensor memory, weights resident in shared memory, TMA stores);
 // dcn_bwd_cols.cuh   input / offset / mask gradients from the column gradient (no tensor-core work; shares the packers).
 //
-// ---- v4 forward kernel (this file) ----
 // Replaces torchvision::deform_conv2d (call site /root/reference/src/models/ema_vfi.py:60) on the throughput path.
-// torchvision materialises columns[603, P] in HBM (40 GB fp32 at 1080p batch 8) and calls a BLAS GEMM; here the
-// modulated bilinear im2col is the A-operand PRODUCER of the GEMM and never leaves the SM:
+// torchvision materialises columns[603, P] in HBM (40 GB fp32 at 1080p batch 8) and calls a BLAS GEMM; here the modulated
+// bilinear im2col is the A-operand PRODUCER of the GEMM and never leaves the SM:
 //
-//     D[128 px, 80 o] (TMEM, fp32)  +=  A[128 px, 64 k] (smem, written by the gather warps)  x  B[80 o, 64 k]^T (smem, bulk copy)
+//     D[128 px, 80 o] (TMEM, fp32)  +=  A[128 px, 64 k] (TMEM, written by the gather warps)  x  B[80 o, 64 k]^T (smem, bulk copy)
 //
-// Activation layout ("planes"): channels-last bf16 in two dense buffers,
-//     main [B, H, W, 64]  (128 B per pixel = exactly one aligned L1 line per bilinear corner) and
-//     tail [B, H, W,  8]  ( 16 B per pixel: channels 64.. and zeros; when there are at most four tail channels the
-//                           upper 8 bytes MIRROR the lower 8, so that a gather may read either half -- v6 picks it by lane
-//                           parity and so spreads its 8-byte reads over all 32 banks).
-// This is how feat (64 ch) and the warped frame (3 ch) exist before the reference's torch.cat (ema_vfi.py:134), and it is
-// what the kernel writes for the next layer.  Any other input layout is converted by pack_input_kernel (workspace).
+// Activation layout ("planes"): channels-last bf16, main = 64 channels (128 B per pixel = exactly one aligned line per
+// bilinear corner) and tail = a 16-byte record per pixel (channels 64.. and zeros; with at most four tail channels the upper
+// 8 bytes MIRROR the lower 8, so that a gather may read either half and spread its 8-byte reads over all 32 banks).  The two
+// may be separate dense buffers ([B,H,W,64] + [B,H,W,8]) or the channel ranges 0..63 / 64..71 of ONE [B,H,W,72] buffer (v7
+// addresses them through tensor maps).  This is how feat (64 ch) and the warped frame (3 ch) exist before the reference's
+// torch.cat (ema_vfi.py:134), and it is what the kernel writes for the next layer.  Any other input layout is converted by
+// pack_input_kernel (workspace).
 //
-//   K ordering  : 11 blocks of 64: block t < 9 = the 64 main channels of tap t (t = 3i + j); block 9 = the 8-channel
-//                 tails of taps 0..7; block 10 = the tail of tap 8 + zero padding (one UMMA_K = 16 step).  656 in all.
-//   A stage     : 128 rows x 128 B, canonical K-major SWIZZLE_128B (16-byte chunk j of row r sits at chunk j ^ (r & 7))
-//   B stage     : 80 rows x 128 B of the pre-swizzled weight image, one cp.async.bulk (UBLKCP) per K block
-//   accumulator : 2 x (128 lanes x 80 columns) in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
-//   tile        : 8 rows x 16 columns of output pixels (keeps the gather footprint, ~75 KB at sigma = 1.5 px, inside L1)
-//
-// Warp roles (928 threads, one persistent CTA per SM, tiles dealt round-robin):
-//   warps 0-23  producers in three groups of 8; group g produces the K blocks n with n % 3 == g into pipeline stage g, so
-//               three blocks are being gathered at once and one group's load latency hides behind the others' lerp/store
-//               work.  Main blocks: each lane owns one 16-byte chunk of four rows; the 8 lanes of a row read one aligned
-//               128 B line per corner.  Tail blocks: each lane owns one row, warps split the taps.  4 corner loads of
-//               16 B (read-only path), packed HFMA2.BF16 lerp (fp32 in HQ mode), one 16-byte store into the swizzled A
-//               stage; fence.proxy.async; one mbarrier arrive per warp.
-//   warp 24     one elected lane issues tcgen05.mma (M128 N80 K16) and tcgen05.commit -> frees the stage / publishes D.
-//   warps 25-28 geometry + epilogue: compute tile i+1's 9 x 128 tap geometries (corner pixel index + mask-folded weights;
-//               optionally straight from the 27-channel offset_conv output with the sigmoid folded in) into the other
-//               half of a double buffer and prefetch its footprint into L2 while the producers gather tile i; then
-//               tcgen05.ld tile i's accumulator 16 columns at a time (lane = pixel), + bias, convert, store.
+// (The round-1 v4 kernel -- L1 gathers into a shared-memory A ring, fp32 "HQ" blend, C up to 72 -- was removed in round 2: the
+// reference geometry is C = 67 (ema_vfi.py:96-99) and v7 takes every 16-bit offset layout, so nothing reached it any more.)
 #include <cuda.h>   // CUtensorMap (types only: the encoder is resolved at run time through cudaGetDriverEntryPoint)
 
 #include <cstddef>
@@ -61,13 +45,6 @@ constexpr int TC_TH = 8, TC_TW = 16;                 // output tile (rows x cols
 constexpr int TC_KBLOCKS = 11;                       // 128-byte swizzle atoms along K (9 main + 2 tail)
 constexpr int TC_A_BYTES = TC_M * 128;               // 16384
 constexpr int TC_B_BYTES = TC_N * 128;               // 10240
-constexpr int TC_STAGES = 3;
-constexpr int TC_GROUPS = 3;                         // producer groups; group g fills stage g (K blocks n with n % 3 == g)
-constexpr int TC_GROUP_WARPS = 8;
-constexpr int TC_PRODUCER_WARPS = TC_GROUPS * TC_GROUP_WARPS;   // 24
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + 4 + 1) * 32;   // + MMA issuer, 4 geometry/epilogue, 1 loader warp = 960
-static_assert(TC_GROUPS == TC_STAGES, "each producer group owns one pipeline stage");
-constexpr int TC_TMEM_COLS = 256;                    // two accumulators at column 0 and 128
 constexpr int TC_ACC_STRIDE = 128;
 
 bool dcn_tc_available() { return true; }
@@ -213,14 +190,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ operand packers
-// K index (kb, kk) -> (tap, channel) of the weight it multiplies; channel -1 = zero padding.
-__host__ __device__ inline void tc_k_to_tap_channel(int kb, int kk, int& tap, int& c) {
-  if (kb < 9) { tap = kb; c = kk; }
-  else if (kb == 9) { tap = kk >> 3; c = TC_CMAIN + (kk & 7); }
-  else if (kk < 8) { tap = 8; c = TC_CMAIN + kk; }
-  else { tap = 0; c = -1; }
-}
-
+// K index (kb, kk) -> (tap, channel) of the weight it multiplies; channel -1 = zero padding / bias slot.
 __host__ __device__ inline void v6_k_to_tap_channel(int kb, int kk, int& tap, int& c);   // dcn_tc6.cuh
 
 __device__ __forceinline__ float load_bias(const void* bias, int bias_dtype, int i) {
@@ -229,7 +199,7 @@ __device__ __forceinline__ float load_bias(const void* bias, int bias_dtype, int
   return __half2float(reinterpret_cast<const __half*>(bias)[i]);
 }
 
-// variant 4: the K order of the v4 kernel (11 blocks); variant 6: that of v6 (10 blocks, block 10 left zero)
+// the K order of the v6 / v7 kernels (10 blocks; block 10 of the 11-block image is left zero)
 template <typename TW>
 __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, int bias_dtype, int O, int C,
                                    uint8_t* __restrict__ packed, float* __restrict__ bias_out, int variant) {
@@ -237,11 +207,10 @@ __global__ void pack_weight_kernel(const TW* __restrict__ w, const void* bias, i
   if (idx < TC_KBLOCKS * TC_N * 64) {
     int kb = idx / (TC_N * 64), o = (idx / 64) % TC_N, kk = idx % 64;
     int tap, c;
-    if (variant == 6) v6_k_to_tap_channel(kb, kk, tap, c);
-    else tc_k_to_tap_channel(kb, kk, tap, c);
+    v6_k_to_tap_channel(kb, kk, tap, c);
     float v = 0.0f;
     if (o < O && c >= 0 && c < C) v = to_f32<TW>(w[((size_t)o * C + c) * 9 + tap]);
-    if (variant == 6 && kb == 9 && (kk == 36 || kk == 37) && o < O && bias) {
+    if (kb == 9 && (kk == 36 || kk == 37) && o < O && bias) {
       // v6 adds the bias on the tensor core: A holds 1.0 at K elements 36 and 37 of the tail block, the weight image the
       // bias split into two bf16 terms (hi + lo carries 16 significant bits)
       const float bv = load_bias(bias, bias_dtype, o);
@@ -331,35 +300,6 @@ struct TcParams {
   unsigned long long* debug;                       // optional [grid][32 warps][8] cycle counters (VFI_DCN_DEBUG), else null
 };
 
-// Tap geometry, one entry per (tap, tile row), double buffered across tiles: the four epilogue warps compute tile
-// i+1's entries while the producers gather tile i.  Row 9 of every buffer is all zeros: the zero-padding chunk of the
-// last K block is produced by the ordinary code path with "tap 9".
-//   pixf : bits 0..29 flattened pixel index (b*H*W + y*W + x) of corner 00 clamped into the image; bit 30: corner 01 is
-//          one pixel to the right (else same pixel); bit 31: corners 10/11 are one row below (else same row)
-//   w    : bilinear weight x modulation mask of corners 00, 01, 10, 11 (0 for corners outside the image, dead samples and
-//          padding rows): two bf16x2 words on the fast path, four fp32 words on the HQ path
-template <bool HQ> struct TcGeoW { using type = uint2; };
-template <> struct TcGeoW<true> { using type = uint4; };
-
-// Operand rings are decoupled: A (written by the gather warps over ~1k cycles) has one more slot than there are producer
-// groups, so a group never waits for the tensor core to finish ITS previous block (measured: 26 % of producer time with
-// one slot per group); B (a 10 KB bulk copy per K block, the same 11 blocks for every tile) has its own 3-slot ring fed by
-// a dedicated lane.
-template <bool HQ> struct TcRing { static constexpr int A = 4, B = 3; };
-template <> struct TcRing<true> { static constexpr int A = 3, B = 3; };   // the fp32 geometry weights need the room
-
-template <bool HQ>
-struct __align__(1024) TcSmem {
-  uint8_t a[TcRing<HQ>::A][TC_A_BYTES];
-  uint8_t b[TcRing<HQ>::B][TC_B_BYTES];
-  uint32_t geo_pix[2][10][TC_M];
-  typename TcGeoW<HQ>::type geo_w[2][10][TC_M];
-  float bias[TC_N];
-  unsigned long long a_full[TcRing<HQ>::A], a_empty[TcRing<HQ>::A], b_full[TcRing<HQ>::B], b_empty[TcRing<HQ>::B];
-  unsigned long long acc_full[2], acc_empty[2], geo_full[2], geo_empty[2];
-  uint32_t tmem_base;
-};
-
 __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
   lo = __uint_as_float(v << 16);
   hi = __uint_as_float(v & 0xffff0000u);
@@ -381,45 +321,10 @@ __device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, cons
   };
   return make_uint4(f(a.x, b.x, c.x, d.x), f(a.y, b.y, c.y, d.y), f(a.z, b.z, c.z, d.z), f(a.w, b.w, c.w, d.w));
 }
-__device__ __forceinline__ uint4 lerp_chunk(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const uint4& w) {
-  const float w0 = __uint_as_float(w.x), w1 = __uint_as_float(w.y), w2 = __uint_as_float(w.z), w3 = __uint_as_float(w.w);
-  auto f = [&](uint32_t va, uint32_t vb, uint32_t vc, uint32_t vd) {
-    float al, ah, bl, bh, cl, ch, dl, dh;
-    unpack2(va, al, ah); unpack2(vb, bl, bh); unpack2(vc, cl, ch); unpack2(vd, dl, dh);
-    float lo = fmaf(w3, dl, fmaf(w2, cl, fmaf(w1, bl, w0 * al)));
-    float hi = fmaf(w3, dh, fmaf(w2, ch, fmaf(w1, bh, w0 * ah)));
-    __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&r);
-  };
-  return make_uint4(f(a.x, b.x, c.x, d.x), f(a.y, b.y, c.y, d.y), f(a.z, b.z, c.z, d.z), f(a.w, b.w, c.w, d.w));
-}
 
 __device__ __forceinline__ void store_geo_w(uint2& dst, float w0, float w1, float w2, float w3) {
   __nv_bfloat162 a = __floats2bfloat162_rn(w0, w1), b = __floats2bfloat162_rn(w2, w3);
   dst = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-}
-__device__ __forceinline__ void store_geo_w(uint4& dst, float w0, float w1, float w2, float w3) {
-  dst = make_uint4(__float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), __float_as_uint(w3));
-}
-
-// Sampling geometry of tap k at output pixel (y, x) from its offsets (dy, dx) and modulation mk.
-template <typename GW>
-__device__ __forceinline__ void tc_geo_entry(int H, int W, int base, int y, int x, int k, float dy, float dx, float mk,
-                                             uint32_t& pixf, GW& wq) {
-  float py = (float)(y - 1 + k / 3) + dy;
-  float px = (float)(x - 1 + k % 3) + dx;
-  const bool live = (py > -1.0f) && (py < (float)H) && (px > -1.0f) && (px < (float)W);
-  if (!live) { py = -2.0f; px = -2.0f; mk = 0.0f; }
-  const float fy = floorf(py), fx = floorf(px);
-  const int y0 = (int)fy, x0 = (int)fx;
-  const float lh = py - fy, lw = px - fx, hh = 1.0f - lh, hw = 1.0f - lw;
-  const bool r0 = (unsigned)y0 < (unsigned)H, r1 = (unsigned)(y0 + 1) < (unsigned)H;
-  const bool c0 = (unsigned)x0 < (unsigned)W, c1 = (unsigned)(x0 + 1) < (unsigned)W;
-  const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
-  const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
-  pixf = (uint32_t)(base + cy0 * W + cx0) | ((uint32_t)(cx1 - cx0) << 30) | ((uint32_t)(cy1 - cy0) << 31);
-  store_geo_w(wq, (r0 && c0) ? hh * hw * mk : 0.0f, (r0 && c1) ? hh * lw * mk : 0.0f, (r1 && c0) ? lh * hw * mk : 0.0f,
-              (r1 && c1) ? lh * lw * mk : 0.0f);
 }
 
 // tile index -> (batch, top row, left column)
@@ -429,296 +334,6 @@ __device__ __forceinline__ void tile_origin(const TcParams& p, int tile, int& b,
   int t = tile % per_img;
   y0 = (t / p.tiles_x) * TC_TH;
   x0 = (t % p.tiles_x) * TC_TW;
-}
-
-// The four corner chunks of one (row, tap) item.  `base` already includes the lane's chunk offset.
-__device__ __forceinline__ void gather4(const uint8_t* base, uint32_t stride, uint32_t row_stride, uint32_t pixf, uint4* v) {
-  const uint8_t* a00 = base + (unsigned long long)(pixf & 0x3fffffffu) * stride;      // IMAD.WIDE.U32
-  const uint32_t dx = (pixf & 0x40000000u) ? stride : 0u;
-  const uint32_t dy = (pixf & 0x80000000u) ? row_stride : 0u;
-  const uint8_t* a10 = a00 + dy;
-  v[0] = __ldg(reinterpret_cast<const uint4*>(a00));
-  v[1] = __ldg(reinterpret_cast<const uint4*>(a00 + dx));
-  v[2] = __ldg(reinterpret_cast<const uint4*>(a10));
-  v[3] = __ldg(reinterpret_cast<const uint4*>(a10 + dx));
-}
-template <typename TO, typename TOUT, bool HQ>
-__global__ void __launch_bounds__(TC_THREADS, 1) dcn_tc_fwd_kernel(const TcParams p) {
-  using GW = typename TcGeoW<HQ>::type;
-  constexpr int NA = TcRing<HQ>::A, NB = TcRing<HQ>::B;
-  constexpr int W_MMA = TC_PRODUCER_WARPS, W_LOAD = TC_PRODUCER_WARPS + 5;   // warps 25..28: geometry + epilogue
-  extern __shared__ uint8_t smem_raw[];
-  TcSmem<HQ>& s = *reinterpret_cast<TcSmem<HQ>*>(smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    for (int i = 0; i < NA; ++i) {
-      mbar_init(smem_u32(&s.a_full[i]), TC_GROUP_WARPS);        // the 8 warps of the producing group
-      mbar_init(smem_u32(&s.a_empty[i]), 1);                    // one tcgen05.commit
-    }
-    for (int i = 0; i < NB; ++i) {
-      mbar_init(smem_u32(&s.b_full[i]), 1);                     // the loader's expect_tx arrival (+ the bytes)
-      mbar_init(smem_u32(&s.b_empty[i]), 1);                    // one tcgen05.commit
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&s.acc_full[i]), 1);                   // one tcgen05.commit
-      mbar_init(smem_u32(&s.acc_empty[i]), 4);                  // four epilogue warps
-      mbar_init(smem_u32(&s.geo_full[i]), 4);                   // four geometry (= epilogue) warps
-      mbar_init(smem_u32(&s.geo_empty[i]), TC_PRODUCER_WARPS);  // every producer warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == W_MMA) tmem_alloc(smem_u32(&s.tmem_base), TC_TMEM_COLS);
-  if (tid < TC_N) s.bias[tid] = p.bias[tid];
-  if (tid < 2 * TC_M) { s.geo_pix[tid >> 7][9][tid & 127] = 0u; s.geo_w[tid >> 7][9][tid & 127] = GW{}; }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = s.tmem_base;
-  // Tiles are dealt round-robin: at any moment the 148 CTAs work on 148 neighbouring tiles, so the halo lines two tiles
-  // share are fetched from DRAM once and found in L2 by the neighbour.  (A contiguous run per CTA was measured: no L1
-  // gain, +70% DRAM reads because a tile row's halo is evicted from L2 before the CTA comes back one tile row later.)
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // =========================================================================== A-operand producers
-    // Three groups of 8 warps rotate over the CTA's global K-block sequence n = tile_iter * 11 + kb: group g produces the
-    // blocks with n % 3 == g into stage g (phase = (n / 3) & 1), so up to three K blocks are being gathered at once and
-    // one group's load latency hides behind the others' lerp/store work.
-    const int group = warp >> 3, wig = warp & 7;
-    // main blocks: lane = (row-in-quad rsub, chunk j); pass q covers rows 32*q + 4*wig + rsub
-    const int rsub = lane >> 3, j = lane & 7;
-    const int r_main = 4 * wig + rsub;
-    const uint32_t a_off_main = (uint32_t)r_main * 128 + ((uint32_t)(j ^ (r_main & 7)) << 4);   // + 4096 * pass
-    const uint8_t* src_main = p.x_main + j * 16;
-    const uint32_t main_row = p.main_stride * (uint32_t)p.W, tail_row = p.tail_stride * (uint32_t)p.W;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int gb = it & 1;
-      mbar_wait(smem_u32(&s.geo_full[gb]), (uint32_t)(it >> 1) & 1u);      // this tile's geometry has been written
-      const int n0 = it * TC_KBLOCKS;
-      int kb = group - n0 % TC_GROUPS;
-      if (kb < 0) kb += TC_GROUPS;
-      for (; kb < TC_KBLOCKS; kb += TC_GROUPS) {        // blocks of this tile with (n0 + kb) % 3 == group
-        const int n = n0 + kb, sa = n % NA;
-        uint8_t* a_stage = &s.a[sa][0];
-        const uint32_t full_bar = smem_u32(&s.a_full[sa]);
-        mbar_wait(smem_u32(&s.a_empty[sa]), ((uint32_t)(n / NA) & 1u) ^ 1u);
-        if (kb < 9) {
-          // ---- the 64 main channels of tap kb: one aligned 128 B line per (row, corner), 8 lanes each
-          const uint32_t* gp = &s.geo_pix[gb][kb][r_main];
-          const GW* gw = &s.geo_w[gb][kb][r_main];
-#pragma unroll
-          for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) gather4(src_main, p.main_stride, main_row, gp[(batch * 2 + q) * 32], v[q]);
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              *reinterpret_cast<uint4*>(a_stage + a_off_main + (batch * 2 + q) * 4096) =
-                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], gw[(batch * 2 + q) * 32]);
-          }
-        } else if (kb == 9) {
-          // ---- tails of taps 0..7: warp wig owns tap wig (chunk wig), lanes run over rows so neighbouring pixels' 16 B
-          //      tail records coalesce
-          const int tap = wig;
-#pragma unroll
-          for (int batch = 0; batch < 2; ++batch) {
-            uint4 v[2][4];
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][tap][(batch * 2 + q) * 32 + lane], v[q]);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int r = (batch * 2 + q) * 32 + lane;
-              *reinterpret_cast<uint4*>(a_stage + r * 128 + ((tap ^ (r & 7)) << 4)) =
-                  lerp_chunk(v[q][0], v[q][1], v[q][2], v[q][3], s.geo_w[gb][tap][r]);
-            }
-          }
-        } else if (wig < 4) {
-          // ---- tail of tap 8 (chunk 0) and the zero chunk 1 of the last UMMA_K step: four warps, one row per lane
-          const int r = wig * 32 + lane;
-          uint4 v[4];
-          gather4(p.x_tail, p.tail_stride, tail_row, s.geo_pix[gb][8][r], v);
-          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((0 ^ (r & 7)) << 4)) = lerp_chunk(v[0], v[1], v[2], v[3], s.geo_w[gb][8][r]);
-          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((1 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-        }
-        fence_proxy_async();                            // generic-proxy smem writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s.geo_empty[gb]));   // this warp no longer reads geometry buffer gb
-    }
-  } else if (warp == W_MMA) {
-    // =========================================================================== MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
-      uint32_t acc = 0, acc_phase[2] = {0, 0};
-      int n = 0;                                         // global K-block counter of this CTA
-      for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(smem_u32(&s.acc_empty[acc]), acc_phase[acc] ^ 1);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
-        for (int kb = 0; kb < TC_KBLOCKS; ++kb, ++n) {
-          const int sa = n % NA, sb = n % NB;
-          mbar_wait(smem_u32(&s.b_full[sb]), (uint32_t)(n / NB) & 1u);
-          mbar_wait(smem_u32(&s.a_full[sa]), (uint32_t)(n / NA) & 1u);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(&s.a[sa][0]));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.b[sb][0]));
-          const int nk = (kb == TC_KBLOCKS - 1) ? 1 : 4;
-          for (int k = 0; k < nk; ++k)                   // +32 B along K inside the 128 B swizzle atom = +2 encoded
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(smem_u32(&s.a_empty[sa]));         // both slots reusable once these MMAs have read them
-          umma_commit(smem_u32(&s.b_empty[sb]));
-        }
-        umma_commit(smem_u32(&s.acc_full[acc]));         // accumulator complete
-        acc_phase[acc] ^= 1;
-        acc ^= 1;
-      }
-    }
-    __syncwarp();
-  } else if (warp == W_LOAD) {
-    // =========================================================================== weight-block loader (one lane)
-    if (lane == 0) {
-      const int total = my_tiles * TC_KBLOCKS;
-      int kb = 0;
-      for (int n = 0; n < total; ++n) {
-        const int sb = n % NB;
-        mbar_wait(smem_u32(&s.b_empty[sb]), ((uint32_t)(n / NB) & 1u) ^ 1u);
-        const uint32_t bar = smem_u32(&s.b_full[sb]);
-        mbar_arrive_expect_tx(bar, TC_B_BYTES);
-        bulk_g2s(smem_u32(&s.b[sb][0]), p.wpacked + (size_t)kb * TC_B_BYTES, TC_B_BYTES, bar);
-        if (++kb == TC_KBLOCKS) kb = 0;
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================================================================== geometry + epilogue (4 warps)
-    const int quad = warp & 3;                           // TMEM lanes [32*quad, 32*quad + 32) belong to this warp
-    const int row = quad * 32 + lane;                    // tile row = TMEM lane = geometry row of this thread
-    uint32_t acc = 0, acc_phase[2] = {0, 0};
-
-    // geometry of tile index `it` (this CTA's numbering) into buffer it & 1: this thread's row, all 9 taps
-    auto make_geometry = [&](int it) {
-      const int gb = it & 1;
-      mbar_wait(smem_u32(&s.geo_empty[gb]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // producers are done with the old contents
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
-      {
-        // pull the tile's nominal gather footprint (tile + 2 px halo: 12 x 20 pixels) towards L2 while the producers are
-        // still busy with the previous tile, so that their compulsory L1 misses find the lines in L2, not in DRAM
-        const int fy = ty0 - 2 + row / 20, fx = tx0 - 2 + row % 20;
-        const int fy2 = ty0 - 2 + (row + 128) / 20, fx2 = tx0 - 2 + (row + 128) % 20;
-        if (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x_main + (size_t)((b * p.H + fy) * p.W + fx) * p.main_stride));
-        if (row + 128 < 240 && fy2 >= 0 && fy2 < p.H && fx2 >= 0 && fx2 < p.W)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x_main + (size_t)((b * p.H + fy2) * p.W + fx2) * p.main_stride));
-      }
-      if (y < p.H && x < p.W) {
-        // all 27 offset / mask values of this pixel are requested before the first one is used (one DRAM round trip)
-        const int f_sc = (int)p.f_sc, m_sc = (int)p.m_sc;
-        const TO* off = reinterpret_cast<const TO*>(p.offset) + b * p.f_sn + y * p.f_sh + x * p.f_sw;
-        const TO* msk = reinterpret_cast<const TO*>(p.mask) + b * p.m_sn + y * p.m_sh + x * p.m_sw;
-        const int base = b * p.H * p.W;
-        TO rdy[9], rdx[9], rmk[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const int j0 = 2 * k, j1 = 2 * k + 1;
-          if (p.fused27) {
-            // ema_vfi.py:57-59 folded in: thirds 0 and 2 of the 27 channels are the offsets (tap k uses channels 2k and
-            // 2k+1 of their concatenation), the middle third is the pre-sigmoid mask
-            rdy[k] = __ldg(off + (j0 < 9 ? j0 : j0 + 9) * f_sc);
-            rdx[k] = __ldg(off + (j1 < 9 ? j1 : j1 + 9) * f_sc);
-            rmk[k] = __ldg(msk + (9 + k) * m_sc);
-          } else {
-            rdy[k] = __ldg(off + j0 * f_sc);
-            rdx[k] = __ldg(off + j1 * f_sc);
-            rmk[k] = __ldg(msk + k * m_sc);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float mk = to_f32<TO>(rmk[k]);
-          // the sigmoid result is rounded to the tensor dtype, as torch.sigmoid on that tensor would
-          if (p.fused27) mk = to_f32<TO>(from_f32<TO>(1.0f / (1.0f + __expf(-mk))));
-          uint32_t pixf;
-          GW wq;
-          tc_geo_entry<GW>(p.H, p.W, base, y, x, k, to_f32<TO>(rdy[k]), to_f32<TO>(rdx[k]), mk, pixf, wq);
-          s.geo_pix[gb][k][row] = pixf;
-          s.geo_w[gb][k][row] = wq;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { s.geo_pix[gb][k][row] = 0u; s.geo_w[gb][k][row] = GW{}; }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s.geo_full[gb]));
-    };
-
-    if (my_tiles > 0) make_geometry(0);
-    for (int it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles) make_geometry(it + 1);      // overlaps the producers' work on tile `it`
-      int b, ty0, tx0;
-      tile_origin(p, tile0 + it * tile_step, b, ty0, tx0);
-      mbar_wait(smem_u32(&s.acc_full[acc]), acc_phase[acc]);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_ACC_STRIDE;
-      const int y = ty0 + row / TC_TW, x = tx0 + row % TC_TW;
-      const bool inside = y < p.H && x < p.W;
-      const size_t pixel = (size_t)(b * p.H + y) * p.W + x;
-      __nv_bfloat16* om = reinterpret_cast<__nv_bfloat16*>(p.out) + pixel * TC_CMAIN;
-      __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(p.out_tail) + pixel * TC_CTAIL;
-      TOUT* os = reinterpret_cast<TOUT*>(p.out) + b * p.o_sn + y * p.o_sh + x * p.o_sw;
-#pragma unroll
-      for (int c16 = 0; c16 < TC_N / 16; ++c16) {
-        uint32_t d[16];
-        tmem_ld16(taddr + c16 * 16, d);
-        tmem_ld_wait();
-        if (c16 == TC_N / 16 - 1) {                      // last TMEM read of this accumulator: hand it back early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[acc]));
-        }
-        if (inside) {
-          if (p.out_tail) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = c16 * 16 + h * 8;
-              if (c0 >= TC_CMAX) break;                  // columns 72..79 are padding of the UMMA N dimension
-              uint32_t w4[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 hv = __floats2bfloat162_rn(__uint_as_float(d[h * 8 + 2 * i]) + s.bias[c0 + 2 * i],
-                                                          __uint_as_float(d[h * 8 + 2 * i + 1]) + s.bias[c0 + 2 * i + 1]);
-                w4[i] = *reinterpret_cast<uint32_t*>(&hv);
-              }
-              __nv_bfloat16* dst = c0 < TC_CMAIN ? om + c0 : ot;
-              if (c0 == TC_CMAIN && p.O <= TC_CMAIN + 4) { w4[2] = w4[0]; w4[3] = w4[1]; }   // tail of <= 4 channels: mirrored
-              *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c16 * 16 + i;
-              if (c < p.O) os[c * p.o_sc] = from_f32<TOUT>(__uint_as_float(d[i]) + s.bias[c]);
-            }
-          }
-        }
-      }
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
-  }
 }
 
 #include "dcn_tc6.cuh"   // v6: TMEM-resident A operand, source box staged in shared memory
@@ -958,11 +573,8 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
               "%s(bf16_tc): workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float* bias_ws = reinterpret_cast<float*>(ws + ws_bias_off());
-  // Kernel variant.  v6 (default): A operand in tensor memory, source box staged in shared memory (dcn_tc6.cuh); it takes
-  // the packed-bf16 blend and at most four tail channels (C <= 68).  v4 (VFI_DCN_KERNEL=v4, the HQ blend, C > 68): gathers
-  // through L1 into a shared-memory A ring.
-  static const bool force_v4 = [] { const char* e = getenv("VFI_DCN_KERNEL"); return e && e[0] == 'v' && e[1] == '4'; }();
-  // v6 brings the offsets / masks in with 16-byte bulk copies: 16-bit dtype, unit pixel stride, 16-byte aligned rows
+  // Kernel: v7 (dcn_tc7.cuh) -- packed-bf16 blend, at most four tail channels (C <= 68), 16-bit offsets / masks in any layout.
+  // The reference kernel v6 brings the offsets / masks in with 16-byte bulk copies: unit pixel stride, 16-byte aligned rows
   auto bulk_ok = [](const vfi_tensor* t) {
     return (t->dtype == VFI_BF16 || t->dtype == VFI_F16) && t->sw == 1 && t->w % 8 == 0 && t->sh % 8 == 0 && t->sc % 8 == 0 &&
            t->sn % 8 == 0 && aligned(t->data, 16) && t->sh >= 0 && t->sc >= 0 && t->sn >= 0;
@@ -970,10 +582,10 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
   // ... or, for the fused form, a dense channels-last offset_conv output ([P][27], what a channels_last model hands over)
   const bool geo_cl = conv27 && (conv27->dtype == VFI_BF16 || conv27->dtype == VFI_F16) && conv27->sc == 1 && conv27->sw == 27 &&
                       conv27->sh == conv27->w * 27 && conv27->sn % 8 == 0 && conv27->w % 8 == 0 && aligned(conv27->data, 16);
-  const bool use_v6 = !hq && !force_v4 && dense_planes && C <= TC_CMAIN + 4 && (geo_cl || (bulk_ok(offset) && bulk_ok(mask)));
-  const bool use_v7 = !hq && !force_v4 && C <= TC_CMAIN + 4 && (offset->dtype == VFI_BF16 || offset->dtype == VFI_F16) &&
+  const bool use_v6 = !hq && dense_planes && C <= TC_CMAIN + 4 && (geo_cl || (bulk_ok(offset) && bulk_ok(mask)));
+  const bool use_v7 = !hq && C <= TC_CMAIN + 4 && (offset->dtype == VFI_BF16 || offset->dtype == VFI_F16) &&
                       mask->dtype == offset->dtype;
-  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, (use_v6 || use_v7) ? 6 : 4);
+  int rc = dcn_tc_pack_weight(weight, weight_dtype, bias, bias_dtype, O, C, ws, bias_ws, st, 6);
   if (rc) return rc;
   if (x_tail) {
     p.x_main = reinterpret_cast<const uint8_t*>(x->data);
@@ -1030,24 +642,28 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
     VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));             \
     kern<<<grid, V7_THREADS, smem7, st>>>(a);                                                                  \
   } while (0)
+    // Two forms are instantiated -- the ones the two entry points produce: the fused form (27-channel offset_conv input) with
+    // planes out (vfi_dcn_fwd_fused through ops.deform_conv2d_fused / HotPath / the fused drop-in), and the torchvision form
+    // (offset + mask) with a strided tensor out (vfi_dcn_fwd, the generic drop-in).
+    VFI_REQUIRE((p.fused27 != 0) == (out_tail != nullptr), VFI_ERR_UNSUPPORTED,
+                "%s(bf16_tc): the fused (conv27) form writes planes (out_tail), the offset + mask form a [B,O,H,W] tensor", who);
     if (out_tail) {
       using TOUT = __nv_bfloat16;
       if (offset->dtype == VFI_BF16) {
         using TO = __nv_bfloat16;
-        if (p.fused27) { if (dbg) VFI_V7_LAUNCH(true, true, true); else VFI_V7_LAUNCH(true, true, false); }
-        else VFI_V7_LAUNCH(false, true, false);
+        if (dbg) VFI_V7_LAUNCH(true, true, true); else VFI_V7_LAUNCH(true, true, false);
       } else {
         using TO = __half;
-        if (p.fused27) VFI_V7_LAUNCH(true, true, false); else VFI_V7_LAUNCH(false, true, false);
+        VFI_V7_LAUNCH(true, true, false);
       }
     } else {
       VFI_DISPATCH(out_dtype, TOUT, {
         if (offset->dtype == VFI_BF16) {
           using TO = __nv_bfloat16;
-          if (p.fused27) VFI_V7_LAUNCH(true, false, false); else VFI_V7_LAUNCH(false, false, false);
+          VFI_V7_LAUNCH(false, false, false);
         } else {
           using TO = __half;
-          if (p.fused27) VFI_V7_LAUNCH(true, false, false); else VFI_V7_LAUNCH(false, false, false);
+          VFI_V7_LAUNCH(false, false, false);
         }
       });
     }
@@ -1055,57 +671,20 @@ int dcn_tc_run(const vfi_tensor* x_main, const vfi_tensor* x_tail, const vfi_ten
     VFI_LAUNCH_CHECK("dcn_tc7_fwd_kernel");
     return VFI_OK;
   }
-  if (use_v6) {
+  // v6, the round-1 kernel, is kept as the bit-exactness reference of v7: one instantiation (bf16 offsets, planes in and out,
+  // 27-channel offset_conv input), reached only through VFI_DCN_KERNEL=v6.
+  if (force_v6 && use_v6 && out_tail && p.fused27 && offset->dtype == VFI_BF16) {
     const size_t smem6 = sizeof(V6Smem) + 1024;
-    const bool dbg = p.debug != nullptr;
-#define VFI_V6_LAUNCH(FUSED, PLANES, DBG)                                                                      \
-  do {                                                                                                         \
-    auto kern = dcn_tc6_fwd_kernel<TO, TOUT, FUSED, PLANES, DBG>;                                              \
-    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));             \
-    kern<<<grid, V6_THREADS, smem6, st>>>(p);                                                                  \
-  } while (0)
-    if (out_tail) {
-      // planes out (always bf16): the hot-path form; the only one with a debug-counter instantiation
-      using TOUT = __nv_bfloat16;
-      if (offset->dtype == VFI_BF16) {
-        using TO = __nv_bfloat16;
-        if (p.fused27) { if (dbg) VFI_V6_LAUNCH(true, true, true); else VFI_V6_LAUNCH(true, true, false); }
-        else VFI_V6_LAUNCH(false, true, false);
-      } else {
-        using TO = __half;
-        if (p.fused27) VFI_V6_LAUNCH(true, true, false); else VFI_V6_LAUNCH(false, true, false);
-      }
-    } else {
-      VFI_DISPATCH(out_dtype, TOUT, {
-        if (offset->dtype == VFI_BF16) {
-          using TO = __nv_bfloat16;
-          if (p.fused27) VFI_V6_LAUNCH(true, false, false); else VFI_V6_LAUNCH(false, false, false);
-        } else {
-          using TO = __half;
-          if (p.fused27) VFI_V6_LAUNCH(true, false, false); else VFI_V6_LAUNCH(false, false, false);
-        }
-      });
-    }
-#undef VFI_V6_LAUNCH
+    auto kern = dcn_tc6_fwd_kernel<__nv_bfloat16, __nv_bfloat16, true, true, false>;
+    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+    kern<<<grid, V6_THREADS, smem6, st>>>(p);
     VFI_LAUNCH_CHECK("dcn_tc6_fwd_kernel");
     return VFI_OK;
   }
-  const size_t smem = (hq ? sizeof(TcSmem<true>) : sizeof(TcSmem<false>)) + 1024;
-  VFI_DISPATCH(offset->dtype, TO, {
-    VFI_DISPATCH(out_dtype, TOUT, {
-      if (hq) {
-        auto kern = dcn_tc_fwd_kernel<TO, TOUT, true>;
-        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TC_THREADS, smem, st>>>(p);
-      } else {
-        auto kern = dcn_tc_fwd_kernel<TO, TOUT, false>;
-        VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TC_THREADS, smem, st>>>(p);
-      }
-    });
-  });
-  VFI_LAUNCH_CHECK("dcn_tc_fwd_kernel");
-  return VFI_OK;
+  VFI_REQUIRE(false, VFI_ERR_UNSUPPORTED,
+              "%s(bf16_tc): needs 16-bit offset / mask tensors of one dtype and C <= %d (got C=%lld, offset dtype %d%s); the fp32-blend "
+              "'bf16_tc_hq' mode and the v4 kernel were removed in round 2", who, TC_CMAIN + 4, C, (int)offset->dtype,
+              force_v6 ? "; VFI_DCN_KERNEL=v6 only takes the fused bf16 planes form" : "");
 }
 
 int dcn_tc_fwd(const vfi_tensor* x, const vfi_tensor* offset, const vfi_tensor* mask, const void* weight, int weight_dtype,
@@ -1135,10 +714,9 @@ int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t s
 
 // Host-only: which (tap, channel) the weight image multiplies at K element kk of block kb (channel -1 = zero / bias slot).
 int dcn_tc_k_order(int variant, int kb, int kk, int* tap, int* channel) {
-  VFI_REQUIRE(tap && channel && kb >= 0 && kb < TC_KBLOCKS && kk >= 0 && kk < 64 && (variant == 4 || variant == 6), VFI_ERR_INVALID,
-              "vfi_dcn_k_order: variant 4|6, kb in [0,11), kk in [0,64)");
-  if (variant == 6) v6_k_to_tap_channel(kb, kk, *tap, *channel);
-  else tc_k_to_tap_channel(kb, kk, *tap, *channel);
+  VFI_REQUIRE(tap && channel && kb >= 0 && kb < TC_KBLOCKS && kk >= 0 && kk < 64 && variant == 6, VFI_ERR_INVALID,
+              "vfi_dcn_k_order: variant 6 (the K order of the v6 / v7 kernels), kb in [0,11), kk in [0,64)");
+  v6_k_to_tap_channel(kb, kk, *tap, *channel);
   return VFI_OK;
 }
 

@@ -129,7 +129,7 @@ def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch
 
 
 # ------------------------------------------------------------------------------------------------------ DCN
-_MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC, "bf16_tc_hq": _lib.MATH_BF16_TC_HQ}
+_MATH = {"auto": _lib.MATH_AUTO, "fp32": _lib.MATH_FP32, "bf16_tc": _lib.MATH_BF16_TC}
 MAIN_C, TAIL_C = 64, 8   # channels per pixel in the two activation planes of the tensor-core path
 
 
@@ -317,11 +317,11 @@ class _DcnFn(torch.autograd.Function):
         weight_c = weight.contiguous()
         bias_c = None if bias is None else bias.contiguous()
         lib = _lib.load()
-        tc = math in (_lib.MATH_BF16_TC, _lib.MATH_BF16_TC_HQ) or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
-        if tc and math != _lib.MATH_BF16_TC_HQ and offset.dtype == torch.float32:
+        tc = math == _lib.MATH_BF16_TC or (math == _lib.MATH_AUTO and x.dtype != torch.float32)
+        if tc and offset.dtype == torch.float32:
             # The staged-box kernels (forward v6, weight gradient) read 16-bit offsets / masks.  fp16 keeps a sampling position
             # to 2^-11 of the offset (0.004 px at 8 px) -- far inside what rounding the activations to bf16 costs -- and is what
-            # the reference's own autocast path hands over; the HQ mode keeps fp32 offsets and the v4 kernel.
+            # the reference's own autocast path hands over.
             _note("offset_fp16_rounding", "fp32 offsets / mask rounded to fp16 for the tensor-core kernels (math='bf16_tc' on fp32 "
                   "offset tensors; 2^-11 relative on the sampling position)")
             offset = offset.clamp(-30000.0, 30000.0).half()
@@ -421,7 +421,7 @@ def deform_conv2d_fused(x_main: torch.Tensor, x_tail: Optional[torch.Tensor], co
     the torch.cat of ema_vfi.py:134, or the :class:`Planes` a previous layer produced.  ``x_tail=None``: ``x_main`` is
     any [B,C,H,W] tensor.  Returns :class:`Planes` (what the next layer reads without a layout pass)."""
     dev = require_cuda(x_main, x_tail, conv27, weight, bias)
-    if math not in ("auto", "bf16_tc", "bf16_tc_hq"):
+    if math not in ("auto", "bf16_tc"):
         raise NotImplementedError("deform_conv2d_fused implements the tensor-core math modes only")
     B, _, H, W = x_main.shape
     O = weight.shape[0]
