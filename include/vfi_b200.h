@@ -79,6 +79,13 @@ void vfi_reset_launch_count(void);
  * Without the flag only the C channels described by `out` are written, whatever its strides are.  The flag with an `out`
  * that is not such a view is VFI_ERR_INVALID. */
 #define VFI_WARP_OUT_TAIL_RECORD 2
+/* vfi_warp_fwd only.  By default three planar channels with unit pixel strides take the STAGED kernel: per 32 x 32 tile the
+ * source window is copied into shared memory by the copy engine (TMA, zero fill outside the frame) and gathered from there;
+ * tiles whose corners span more than the window (large incoherent flow) gather through L1 inside the same launch.  Results do
+ * not depend on the route.  VFI_WARP_NO_STAGING forces the L1 kernel of round 1 for the whole frame (A/B runs, parity tests);
+ * VFI_WARP_COUNT_TILES makes the launch count its staged / L1 tiles (read with vfi_warp_tile_counts; costs one atomic per tile). */
+#define VFI_WARP_NO_STAGING 4
+#define VFI_WARP_COUNT_TILES 8
 
 /* ---- warp: replaces EMA_VFI.warp, /root/reference/src/models/ema_vfi.py:149-171 ----------------------------- */
 /* out[b,c,y,x] = bilinear(src[b,c], x + flow[b,0,y,x], y + flow[b,1,y,x]), zeros outside, align_corners=True,
@@ -86,6 +93,10 @@ void vfi_reset_launch_count(void);
  * src/out: [B,C,H,W] same dtype (f32|bf16|f16); flow: [B,2,H,W] f32 or the dtype of src. */
 int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const vfi_tensor* out, int32_t flags,
                  vfi_stream_t stream);
+
+/* Diagnostic: tiles the staged warp kernel served from its shared-memory window / through L1 since the last reset, over all
+ * launches that carried VFI_WARP_COUNT_TILES on the current device.  Synchronises the device. */
+int vfi_warp_tile_counts(uint64_t* staged, uint64_t* direct, int32_t reset);
 
 /* Autograd of the above (aten::grid_sampler_2d_backward chained through ema_vfi.py:165-166).
  * grad_flow [B,2,H,W] f32 is always written.  grad_src may be NULL (the model path: frame2 needs no grad); when

@@ -158,6 +158,61 @@ def test_warp_low_precision(dtype):
     assert relerr(out32, ref) <= 1e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("division", ["ieee", "reciprocal"])
+def test_warp_staged_kernel_is_bit_identical_to_the_l1_kernel(dtype, division):
+    """The TMA-staged warp (source window in shared memory, zero fill by the copy engine) against round 1's L1-gather
+    kernel on every flow class the staging decision distinguishes: near-identity (40 x 40 window), sheared / translated
+    (64-wide window, anchored at the tile's north-west corner wherever it lies, also outside the frame), incoherent large
+    displacement (tiles fall back to L1 inside the same launch), NaN / inf flow, frames whose size is not a multiple of the
+    tile.  Results must not depend on the route: exact equality, and the tile counters prove both routes ran."""
+    from vfi_b200 import ops
+
+    g = torch.Generator().manual_seed(77)
+    for (B, H, W), kind in [((2, 72, 136), "tiny"), ((1, 100, 232), "shear"), ((2, 64, 96), "translate"), ((1, 96, 160), "iid"),
+                            ((1, 40, 72), "nan"), ((3, 33, 40), "edge")]:
+        src = torch.randn(B, 3, H, W, generator=g).to(dtype).to(DEV)
+        yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+        if kind == "tiny":
+            flow = 0.03 * torch.randn(B, 2, H, W, generator=g)
+        elif kind == "shear":
+            flow = torch.stack([0.3 * yy - 0.2 * xx + 5, 0.25 * xx - 9], 0)[None].repeat(B, 1, 1, 1) + 0.2 * torch.randn(B, 2, H, W, generator=g)
+        elif kind == "translate":
+            flow = torch.tensor([-70.3, 41.6]).view(1, 2, 1, 1) + 0.5 * torch.randn(B, 2, H, W, generator=g)   # window partly / wholly outside
+        elif kind == "iid":
+            flow = 40.0 * torch.randn(B, 2, H, W, generator=g)
+        elif kind == "nan":
+            flow = 2.0 * torch.randn(B, 2, H, W, generator=g)
+            flow[0, 0, 3, 5] = float("nan"); flow[0, 1, 20, 40] = float("inf"); flow[0, 0, 39, 71] = -float("inf")
+        else:
+            flow = 1.5 * torch.randn(B, 2, H, W, generator=g)
+        flow = flow.to(DEV)
+        ops.warp_tile_counts(reset=True)
+        a = vfi_b200.warp(src, flow, division=division, count_tiles=True)
+        staged, direct = ops.warp_tile_counts(reset=True)
+        b = vfi_b200.warp(src, flow, division=division, staging=False)
+        tiles = B * ((H + 31) // 32) * ((W + 31) // 32)
+        assert staged + direct == tiles, (kind, staged, direct, tiles)
+        if kind in ("tiny", "shear", "translate", "edge"):
+            assert direct == 0, (kind, staged, direct)
+        if kind == "iid":
+            assert direct == tiles
+        assert torch.equal(torch.nan_to_num(a.float(), nan=123.0), torch.nan_to_num(b.float(), nan=123.0)), kind
+    # tail-record output and a source the copy engine cannot map (row pitch not a multiple of 16 bytes): L1 kernels, same values
+    src = torch.randn(2, 3, 48, 64, generator=g).to(torch.bfloat16).to(DEV)
+    flow = (0.5 * torch.randn(2, 2, 48, 64, generator=g)).to(DEV)
+    pa, pb = ops.Planes(2, 48, 64, DEV), ops.Planes(2, 48, 64, DEV)
+    vfi_b200.warp(src, flow, out=pa.tail_nchw(3), tail_record=True, division=division)
+    vfi_b200.warp(src, flow, out=pb.tail_nchw(3), tail_record=True, division=division, staging=False)
+    assert torch.equal(pa.tail, pb.tail)
+    wide = torch.randn(1, 3, 40, 75, generator=g).to(dtype).to(DEV)
+    sl, fl = wide[..., 1:73], (2.0 * torch.randn(1, 2, 40, 72, generator=g)).to(DEV)
+    ops.warp_tile_counts(reset=True)
+    a = vfi_b200.warp(sl, fl, division=division, count_tiles=True)
+    assert ops.warp_tile_counts() == (0, 0)                       # not staged at all: the whole launch is the L1 kernel
+    assert torch.equal(a, vfi_b200.warp(sl.contiguous(), fl, division=division))
+
+
 def test_warp_blend_matches_composition():
     g = torch.Generator().manual_seed(14)
     a, b = torch.randn(2, 2, 3, 50, 70, generator=g)

@@ -7,7 +7,7 @@ There is no fallback: if the shared object is missing, or the device is not sm_1
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 import torch
@@ -22,7 +22,7 @@ ERR_NAMES = {1: "VFI_ERR_INVALID", 2: "VFI_ERR_UNSUPPORTED", 3: "VFI_ERR_CUDA", 
 F32, BF16, F16 = 0, 1, 2
 MATH_AUTO, MATH_FP32, MATH_BF16_TC, MATH_BF16_TC_HQ = 0, 1, 2, 3
 WARP_DIV_IEEE, WARP_DIV_RECIPROCAL = 0, 1
-WARP_OUT_TAIL_RECORD = 2
+WARP_OUT_TAIL_RECORD, WARP_NO_STAGING, WARP_COUNT_TILES = 2, 4, 8
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 
@@ -42,6 +42,7 @@ SIGNATURES = {
     "vfi_launch_count": (c_int64, []),
     "vfi_reset_launch_count": (None, []),
     "vfi_warp_fwd": (c_int, [_T, _T, _T, c_int32, c_void_p]),
+    "vfi_warp_tile_counts": (c_int, [POINTER(c_uint64), POINTER(c_uint64), c_int32]),
     "vfi_warp_bwd": (c_int, [_T, _T, _T, _T, _T, c_int32, c_void_p]),
     "vfi_warp_blend_fwd": (c_int, [_T, _T, _T, _T, _T, _T, c_int32, c_void_p]),
     "vfi_dcn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int32]),

@@ -1,5 +1,6 @@
 // common.cuh -- shared host/device helpers for libvfi_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>        // CUtensorMap (types only: the encoder is resolved at run time, see tensor_map_encoder)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -85,5 +86,22 @@ template <typename T> __device__ __forceinline__ float ldg_f32(const T* p) { ret
   }
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------- TMA tensor maps (host)
+// cuTensorMapEncodeTiled, resolved at run time (the library has no link-time dependency on libcuda: it loads in the CPU-only
+// build container).  Returns null when the driver does not export it.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
 
 }  // namespace vfi

@@ -459,21 +459,6 @@ int dcn_tc_pack_input(const vfi_tensor* x, void* main_plane, void* tail_plane, c
 }
 
 
-// cuTensorMapEncodeTiled, resolved at run time (the library has no link-time dependency on libcuda: it loads in the CPU-only
-// build container).  Returns null when the driver does not export it.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
 // 4-D tiled map over 16-bit elements: dims / box innermost first, strides (bytes) of dims 1..3.  False when the copy engine
 // cannot describe the tensor (alignment, stride range) -- the caller then uses another path or reports VFI_ERR_UNSUPPORTED.
 static bool make_map4(CUtensorMap* m, const void* base, const long long dim[4], const long long stride_bytes[3], const int box[4],

@@ -7,6 +7,7 @@
 //
 // HBM-bound by design: algorithmic traffic is (C_in + 2 + C_out) elements per pixel (32 B/px fp32, 16 B/px bf16, C = 3);
 // the corner gathers go through the read-only path and hit L1/L2 for everything but the compulsory first touch.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -236,6 +237,166 @@ __global__ void __launch_bounds__(WARPF_BLOCK) warp_fwd_fast_kernel(const WarpPa
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, staged path
+// The form the north star names: the source window of a tile is brought into shared memory by the copy engine (TMA), and the
+// twelve corner gathers of a pixel become shared-memory loads.
+//
+// A CTA owns a 32 x 32 tile of output pixels (8 warps, warp = tile row mod 8, lane = column, four rows per thread).
+//   1. every thread reads its flow values, replays the reference's coordinate arithmetic (bit for bit the fast kernel's) and
+//      keeps the integer north-west corners; a warp reduction (redux.sync) + one shared-memory exchange gives the bounding box
+//      of the tile's corners;
+//   2. if that box fits the staging window -- 48 x 40 source pixels for near-identity flow (what the reference's model
+//      produces), else 64 x WS_BH -- thread 0 issues ONE cp.async.bulk.tensor (three planes) anchored at the box's north-west
+//      pixel (rounded down to an 8-pixel boundary in x); the copy engine zero-fills whatever lies outside the frame, so the zeros padding of F.grid_sample needs no
+//      clamping, no re-slotting of weights and no predicated loads;
+//   3. the gathers read the window (2-byte LDS by 32 consecutive pixels: one 64-byte wavefront per request for small flows),
+//      same products in the same order (nw, ne, sw, se) as every other warp kernel here.
+// Tiles whose corners do not fit (large incoherent flow) take the fast kernel's L1 path inside the same launch, so the result
+// never depends on which path a tile took.  What this buys: ~95 instead of ~190 issue slots per pixel (the fast kernel's bound,
+// DESIGN.md section 4.2) and no data-dependent L1 wavefronts.
+constexpr int WS_TILE = 32, WS_THREADS = 256, WS_ROWS = WS_TILE / 8;      // rows per thread
+constexpr int WS_BW = 64, WS_SMALL_W = 48, WS_SMALL_H = 40;                // staging windows (source pixels): big is 64 x WsBox::H
+template <typename TS> struct WsBox { static constexpr int H = sizeof(TS) == 4 ? 48 : 64; };
+
+struct WarpStagedArgs {
+  WarpParams p;
+  unsigned long long* tile_counts;                                         // optional [2]: tiles staged / tiles on the L1 path
+  int dbg;                                                                 // VFI_WARP_DEBUG (diagnostics): 1 = never stage, 2 = big window only
+  alignas(128) CUtensorMap tm_big;                                         // src {W, H, 3, B}, box {64, WS_BH, 3, 1}
+  alignas(128) CUtensorMap tm_small;                                       // same tensor, box {48, 40, 3, 1}
+};
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename TS, typename TF, bool REC, bool RECIP>
+__global__ void __launch_bounds__(WS_THREADS) warp_fwd_staged_kernel(const __grid_constant__ WarpStagedArgs a) {
+  constexpr int BH = WsBox<TS>::H;
+  const WarpParams& p = a.p;
+  __shared__ __align__(128) TS box[3 * BH * WS_BW];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int red[8][4];
+  __shared__ int plan[4];                                                  // anchor x, anchor y, window width (0 = L1 path), window height
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int b = blockIdx.z, x = blockIdx.x * WS_TILE + lane, ybase = blockIdx.y * WS_TILE + wrp;
+  const int H = p.H, W = p.W;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ws_smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- 1. flow -> source coordinates
+  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn;
+  float fx[WS_ROWS], fy[WS_ROWS];
+  bool ok[WS_ROWS];
+#pragma unroll
+  for (int i = 0; i < WS_ROWS; ++i) {
+    const int y = ybase + 8 * i;
+    ok[i] = x < W && y < H;
+    const TF* q = fl + (long long)min(y, H - 1) * p.f_sh + min(x, W - 1);
+    fx[i] = to_f32<TF>(__ldcs(q));
+    fy[i] = to_f32<TF>(__ldcs(q + p.f_sc));
+  }
+  float ix[WS_ROWS], iy[WS_ROWS];
+  int x0[WS_ROWS], y0[WS_ROWS];
+  int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < WS_ROWS; ++i) {
+    ix[i] = warp_coord_t<RECIP>(min(x, W - 1), fx[i], p.ax);
+    iy[i] = warp_coord_t<RECIP>(min(ybase + 8 * i, H - 1), fy[i], p.ay);
+    x0[i] = __float2int_rd(ix[i]);
+    y0[i] = __float2int_rd(iy[i]);
+    if (ok[i]) { mnx = min(mnx, x0[i]); mxx = max(mxx, x0[i]); mny = min(mny, y0[i]); mxy = max(mxy, y0[i]); }
+  }
+  mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+  mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+  if (lane == 0) { red[wrp][0] = mnx; red[wrp][1] = mxx; red[wrp][2] = mny; red[wrp][3] = mxy; }
+  __syncthreads();
+  // ---- 2. plan + copy (thread 0)
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { mnx = min(mnx, red[w][0]); mxx = max(mxx, red[w][1]); mny = min(mny, red[w][2]); mxy = max(mxy, red[w][3]); }
+    // The copy engine wants the first byte of a box row 16-byte aligned: the window is anchored at the 8-pixel boundary at or
+    // left of the box (a misaligned innermost coordinate faults as "illegal instruction").
+    mnx = (mnx >> 3) << 3;
+    const int ex = mxx - mnx + 2, ey = mxy - mny + 2;                      // source pixels from the anchor to the last corner
+    int bw = 0, bh = 0;
+    if (ex <= WS_SMALL_W && ey <= WS_SMALL_H && !(a.dbg & 2)) { bw = WS_SMALL_W; bh = WS_SMALL_H; }
+    else if (ex <= WS_BW && ey <= BH) { bw = WS_BW; bh = BH; }
+    if (a.dbg & 1) bw = bh = 0;
+    plan[0] = mnx; plan[1] = mny; plan[2] = bw; plan[3] = bh;
+    if (bw) {
+      const uint32_t bar_a = ws_smem_u32(&bar);
+      const uint32_t bytes = (a.dbg & 8) ? 0u : (uint32_t)(3 * bw * bh * sizeof(TS));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+      if (!(a.dbg & 8)) {
+        if (bw == WS_SMALL_W) {
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                  ws_smem_u32(box)),
+              "l"(reinterpret_cast<uint64_t>(&a.tm_small)), "r"(mnx), "r"(mny), "r"(0), "r"(b), "r"(bar_a)
+              : "memory");
+        } else {
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                  ws_smem_u32(box)),
+              "l"(reinterpret_cast<uint64_t>(&a.tm_big)), "r"(mnx), "r"(mny), "r"(0), "r"(b), "r"(bar_a)
+              : "memory");
+        }
+      }
+    }
+    if (a.tile_counts) atomicAdd(a.tile_counts + (bw ? 0 : 1), 1ull);
+  }
+  __syncthreads();
+  const int ax0 = plan[0], ay0 = plan[1], bw = plan[2], bh = plan[3];
+  float r[WS_ROWS][3];
+  if (bw) {
+    // ---- 3a. gathers from the staged window
+    {
+      const uint32_t bar_a = ws_smem_u32(&bar);
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+    }
+    const int plane = bw * bh;
+#pragma unroll
+    for (int i = 0; i < WS_ROWS; ++i) {
+      const float x0f = (float)x0[i], y0f = (float)y0[i];
+      const float wx1 = ix[i] - x0f, wx0 = (x0f + 1.0f) - ix[i], wy1 = iy[i] - y0f, wy0 = (y0f + 1.0f) - iy[i];
+      const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+      const int o = ok[i] ? (y0[i] - ay0) * bw + (x0[i] - ax0) : 0;       // pixels past the frame edge are not stored: any address
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const TS* q = box + c * plane + o;
+        const float v00 = to_f32<TS>(q[0]), v01 = to_f32<TS>(q[1]), v10 = to_f32<TS>(q[bw]), v11 = to_f32<TS>(q[bw + 1]);
+        r[i][c] = fmaf(v11, w11, fmaf(v10, w10, fmaf(v01, w01, v00 * w00)));
+      }
+    }
+  } else {
+    // ---- 3b. the fast kernel's L1 path (tile's corners do not fit a window)
+    const TS* s0 = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
+#pragma unroll
+    for (int i = 0; i < WS_ROWS; ++i)
+      sample3<TS, RECIP>(s0, s0 + p.s_sc, s0 + 2 * p.s_sc, (int)p.s_sh, H, W, min(x, W - 1), min(ybase + 8 * i, H - 1), fx[i], fy[i], p.ax,
+                         p.ay, r[i]);
+  }
+  // ---- 4. store
+#pragma unroll
+  for (int i = 0; i < WS_ROWS; ++i) {
+    if (!ok[i]) continue;
+    const int y = ybase + 8 * i;
+    if constexpr (REC) {
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + (long long)x * p.o_sw;
+      const __nv_bfloat162 c01 = __floats2bfloat162_rn(r[i][0], r[i][1]), c2z = __floats2bfloat162_rn(r[i][2], 0.0f);
+      const uint32_t lo = *reinterpret_cast<const uint32_t*>(&c01), hi = *reinterpret_cast<const uint32_t*>(&c2z);
+      __stcs(reinterpret_cast<uint4*>(out), make_uint4(lo, hi, lo, hi));
+    } else {
+      TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) __stcs(out + c * p.o_sc, from_f32<TS>(r[i][c]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ blend (W3)
 struct BlendParams {
   WarpParams a;          // src_a / flow_a / out
@@ -429,8 +590,55 @@ WarpParams make_params(const vfi_tensor* src, const vfi_tensor* flow, const vfi_
   return p;
 }
 
+// Tensor map over the three source planes of every frame: dims {W, H, 3, B} (innermost first), box {bw, bh, 3, 1}, zero fill
+// outside the tensor.  False when the copy engine cannot describe the tensor (alignment / stride rules of cuTensorMapEncodeTiled).
+template <typename TS>
+bool warp_src_map(CUtensorMap* m, const WarpParams& p, int bw, int bh) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  const long long es = (long long)sizeof(TS);
+  if (!enc || !aligned(p.src, 16) || p.s_sw != 1) return false;
+  const long long sb[3] = {p.s_sh * es, p.s_sc * es, (p.B > 1 ? p.s_sn : p.s_sc * 3) * es};
+  for (int i = 0; i < 3; ++i)
+    if (sb[i] <= 0 || sb[i] % 16 != 0 || sb[i] >= (1LL << 40)) return false;
+  const cuuint64_t gd[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, 3, (cuuint64_t)p.B};
+  const cuuint64_t gs[3] = {(cuuint64_t)sb[0], (cuuint64_t)sb[1], (cuuint64_t)sb[2]};
+  const cuuint32_t bx[4] = {(cuuint32_t)bw, (cuuint32_t)bh, 3, 1}, el[4] = {1, 1, 1, 1};
+  return enc(m, sizeof(TS) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(p.src), gd, gs, bx,
+             el, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ unsigned long long g_warp_tile_counts[2];                       // VFI_WARP_COUNT_TILES: tiles staged / on the L1 path
+
 template <typename TS, typename TF>
-int launch_fwd(const WarpParams& p, bool rec, bool fast, cudaStream_t st) {
+int launch_fwd(const WarpParams& p, bool rec, bool fast, int flags, cudaStream_t st) {
+  if (fast && !(flags & VFI_WARP_NO_STAGING) && p.W >= WS_TILE && p.H >= 8) {
+    // staged path (TMA window + shared-memory gathers); falls through to the L1 kernels when the source cannot be mapped
+    WarpStagedArgs a;
+    a.p = p;
+    a.tile_counts = nullptr;
+    const char* dbg_env = getenv("VFI_WARP_DEBUG");
+    a.dbg = dbg_env ? atoi(dbg_env) : 0;
+    if (warp_src_map<TS>(&a.tm_big, p, WS_BW, WsBox<TS>::H) && warp_src_map<TS>(&a.tm_small, p, WS_SMALL_W, WS_SMALL_H)) {
+      if (flags & VFI_WARP_COUNT_TILES) VFI_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.tile_counts), g_warp_tile_counts));
+      dim3 grid(ceil_div(p.W, WS_TILE), ceil_div(p.H, WS_TILE), p.B);
+      const bool recip = p.ax.recip != 0;
+      bool launched = false;
+      if constexpr (std::is_same<TS, __nv_bfloat16>::value) {
+        if (rec) {
+          if (recip) warp_fwd_staged_kernel<TS, TF, true, true><<<grid, WS_THREADS, 0, st>>>(a);
+          else warp_fwd_staged_kernel<TS, TF, true, false><<<grid, WS_THREADS, 0, st>>>(a);
+          launched = true;
+        }
+      }
+      if (!launched) {
+        if (recip) warp_fwd_staged_kernel<TS, TF, false, true><<<grid, WS_THREADS, 0, st>>>(a);
+        else warp_fwd_staged_kernel<TS, TF, false, false><<<grid, WS_THREADS, 0, st>>>(a);
+      }
+      VFI_LAUNCH_CHECK("warp_fwd_staged_kernel");
+      return VFI_OK;
+    }
+  }
   if (fast) {
     dim3 grid(ceil_div(p.W, WARPF_BLOCK * WARPF_PPT), p.H, p.B);
     const bool recip = p.ax.recip != 0;
@@ -486,10 +694,22 @@ extern "C" int vfi_warp_fwd(const vfi_tensor* src, const vfi_tensor* flow, const
   const bool fast = src->c == 3 && src->sw == 1 && flow->sw == 1 && src->w >= 2 && src->h >= 2 && src->sh >= 0 && src->sc >= 0 &&
                     src->sn >= 0 && (rec || out->sw == 1);
   VFI_DISPATCH(src->dtype, TS, {
-    if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, rec, fast, st); }
-    else { rc = launch_fwd<TS, TS>(p, rec, fast, st); }
+    if (flow->dtype == VFI_F32) { rc = launch_fwd<TS, float>(p, rec, fast, flags, st); }
+    else { rc = launch_fwd<TS, TS>(p, rec, fast, flags, st); }
   });
   return rc;
+}
+
+extern "C" int vfi_warp_tile_counts(uint64_t* staged, uint64_t* direct, int32_t reset) {
+  unsigned long long h[2] = {0, 0};
+  VFI_CUDA(cudaMemcpyFromSymbol(h, g_warp_tile_counts, sizeof(h)));
+  if (staged) *staged = h[0];
+  if (direct) *direct = h[1];
+  if (reset) {
+    const unsigned long long z[2] = {0, 0};
+    VFI_CUDA(cudaMemcpyToSymbol(g_warp_tile_counts, z, sizeof(z)));
+  }
+  return VFI_OK;
 }
 
 extern "C" int vfi_warp_blend_fwd(const vfi_tensor* src_a, const vfi_tensor* flow_a, const vfi_tensor* src_b,

@@ -96,7 +96,7 @@ _DIVISION = {"ieee": _lib.WARP_DIV_IEEE, "reciprocal": _lib.WARP_DIV_RECIPROCAL}
 
 
 def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee", out: Optional[torch.Tensor] = None,
-         tail_record: bool = False) -> torch.Tensor:
+         tail_record: bool = False, staging: bool = True, count_tiles: bool = False) -> torch.Tensor:
     """Backward-warp ``src`` [B,C,H,W] by ``flow`` [B,2,H,W] (pixels; channel 0 = x, 1 = y).
 
     Same result as the reference's grid build + normalise + ``F.grid_sample(bilinear, zeros,
@@ -109,8 +109,22 @@ def warp(src: torch.Tensor, flow: torch.Tensor, division: str = "ieee", out: Opt
     ``tail_record=True`` (VFI_WARP_OUT_TAIL_RECORD): ``out`` is the [B,3,H,W] view of a DCN tail plane
     (:meth:`Planes.tail_nchw`) and the kernel writes whole 16-byte records ``[c0 c1 c2 0 | c0 c1 c2 0]`` -- elements 3..7
     of every pixel are overwritten.  This is what removes the ``torch.cat`` of ema_vfi.py:134.
+    ``staging=False`` (VFI_WARP_NO_STAGING) forces round 1's L1-gather kernel instead of the TMA-staged one (same results;
+    A/B runs and parity tests); ``count_tiles=True`` makes the launch count its staged / L1 tiles (:func:`warp_tile_counts`).
     """
-    return _WarpFn.apply(src, flow, _DIVISION[division] | (_lib.WARP_OUT_TAIL_RECORD if tail_record else 0), out)
+    flags = _DIVISION[division] | (_lib.WARP_OUT_TAIL_RECORD if tail_record else 0)
+    flags |= (0 if staging else _lib.WARP_NO_STAGING) | (_lib.WARP_COUNT_TILES if count_tiles else 0)
+    return _WarpFn.apply(src, flow, flags, out)
+
+
+def warp_tile_counts(reset: bool = True):
+    """(tiles served from the staged shared-memory window, tiles gathered through L1) over the ``count_tiles=True`` launches on
+    the current device since the last reset.  Synchronises."""
+    import ctypes
+
+    a, b = ctypes.c_uint64(), ctypes.c_uint64()
+    check(_lib.load().vfi_warp_tile_counts(ctypes.byref(a), ctypes.byref(b), 1 if reset else 0), "vfi_warp_tile_counts")
+    return int(a.value), int(b.value)
 
 
 def warp_blend(src_a, flow_a, src_b, flow_b, m, division: str = "ieee") -> torch.Tensor:
