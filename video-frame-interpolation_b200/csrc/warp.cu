@@ -8,7 +8,10 @@
 // HBM-bound by design: algorithmic traffic is (C_in + 2 + C_out) elements per pixel (32 B/px fp32, 16 B/px bf16, C = 3);
 // the corner gathers go through the read-only path and hit L1/L2 for everything but the compulsory first touch.
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 
 #include "common.cuh"
 #include "warp_math.h"
@@ -164,12 +167,10 @@ template <bool RECIP> __device__ __forceinline__ float warp_coord_t(int pix, flo
   return fminf(fmaxf(i, -4.0f), ax.hi);
 }
 
-// Three planar channels of one output pixel (x, y) displaced by (fx, fy): the sampler of the fast kernels.
-template <typename TS, bool RECIP>
-__device__ __forceinline__ void sample3(const TS* s0, const TS* s1, const TS* s2, int pitch, int H, int W, int x, int y, float fx,
-                                        float fy, const WarpAxis& ax, const WarpAxis& ay, float (&r)[3]) {
-  const float ix = warp_coord_t<RECIP>(x, fx, ax);
-  const float iy = warp_coord_t<RECIP>(y, fy, ay);
+// Three planar channels sampled at source position (ix, iy): the sampler of the fast kernels.
+template <typename TS>
+__device__ __forceinline__ void sample3_at(const TS* s0, const TS* s1, const TS* s2, int pitch, int H, int W, float ix, float iy,
+                                           float (&r)[3]) {
   const int x0 = __float2int_rd(ix), y0 = __float2int_rd(iy);
   const float x0f = (float)x0, y0f = (float)y0;
   // The 2 x 2 patch is addressed from its clamped north-west pixel (xc, yc) in [0, W-2] x [0, H-2]: the other three
@@ -191,6 +192,12 @@ __device__ __forceinline__ void sample3(const TS* s0, const TS* s1, const TS* s2
     return fmaf(e, w11, fmaf(d, w10, fmaf(bb, w01, a * w00)));
   };
   r[0] = lerp(s0); r[1] = lerp(s1); r[2] = lerp(s2);
+}
+// ... of one output pixel (x, y) displaced by (fx, fy)
+template <typename TS, bool RECIP>
+__device__ __forceinline__ void sample3(const TS* s0, const TS* s1, const TS* s2, int pitch, int H, int W, int x, int y, float fx,
+                                        float fy, const WarpAxis& ax, const WarpAxis& ay, float (&r)[3]) {
+  sample3_at<TS>(s0, s1, s2, pitch, H, W, warp_coord_t<RECIP>(x, fx, ax), warp_coord_t<RECIP>(y, fy, ay), r);
 }
 
 constexpr int WARPF_PPT = VFI_WARPF_PPT;                      // pixels per thread, one block apart (x, x + 128)
@@ -241,158 +248,258 @@ __global__ void __launch_bounds__(WARPF_BLOCK) warp_fwd_fast_kernel(const WarpPa
 // The form the north star names: the source window of a tile is brought into shared memory by the copy engine (TMA), and the
 // twelve corner gathers of a pixel become shared-memory loads.
 //
-// A CTA owns a 32 x 32 tile of output pixels (8 warps, warp = tile row mod 8, lane = column, four rows per thread).
-//   1. every thread reads its flow values, replays the reference's coordinate arithmetic (bit for bit the fast kernel's) and
-//      keeps the integer north-west corners; a warp reduction (redux.sync) + one shared-memory exchange gives the bounding box
-//      of the tile's corners;
-//   2. if that box fits the staging window -- 48 x 40 source pixels for near-identity flow (what the reference's model
-//      produces), else 64 x WS_BH -- thread 0 issues ONE cp.async.bulk.tensor (three planes) anchored at the box's north-west
-//      pixel (rounded down to an 8-pixel boundary in x); the copy engine zero-fills whatever lies outside the frame, so the zeros padding of F.grid_sample needs no
-//      clamping, no re-slotting of weights and no predicated loads;
-//   3. the gathers read the window (2-byte LDS by 32 consecutive pixels: one 64-byte wavefront per request for small flows),
-//      same products in the same order (nw, ne, sw, se) as every other warp kernel here.
-// Tiles whose corners do not fit (large incoherent flow) take the fast kernel's L1 path inside the same launch, so the result
-// never depends on which path a tile took.  What this buys: ~95 instead of ~190 issue slots per pixel (the fast kernel's bound,
-// DESIGN.md section 4.2) and no data-dependent L1 wavefronts.
-constexpr int WS_TILE = 32, WS_THREADS = 256, WS_ROWS = WS_TILE / 8;      // rows per thread
+// Persistent CTAs (as many as fit the SMs) walk over 32 x 32 tiles of output pixels (8 warps; a half-warp is one tile row, a
+// thread owns two pairs of adjacent pixels) in a two-stage software pipeline -- per iteration, for tiles t (being produced), t + G (next)
+// and t + 2 G (G = grid size):
+//   A. flow of tile t + G (loaded during the previous iteration) -> source coordinates, replaying the reference's arithmetic bit
+//      for bit as the fast kernel does; a warp reduction (redux.sync) + one shared-memory exchange gives the bounding box of the
+//      tile's corners.  If it fits a staging window -- 48 x 40 source pixels for near-identity flow (what the reference's model
+//      produces), else 64 x WsBox::H -- thread 0 issues ONE cp.async.bulk.tensor (three planes) into the other window buffer,
+//      anchored at the box's north-west pixel (x rounded down to a 16-byte boundary: the copy engine faults on a misaligned
+//      innermost coordinate).  The copy engine zero-fills whatever lies outside the frame, so the zeros padding of
+//      F.grid_sample needs no clamping, no re-slotting of weights and no predicated loads.
+//   B. the flow loads of tile t + 2 G are issued (they have a whole iteration to arrive).
+//   C. tile t: wait for its window (issued one iteration ago), gather from shared memory (2-byte LDS by 32 consecutive pixels:
+//      one 64-byte wavefront per request for small flows), same products in the same order (nw, ne, sw, se) as every other warp
+//      kernel here, store.
+// One __syncthreads per tile.  Tiles whose corners do not fit a window (large incoherent flow) take the fast kernel's L1 path
+// inside the same launch, so the result never depends on the route (up to the sign of a zero: a zero-weight corner with a
+// negative value gives -0 on the L1 path, the zero-filled window always +0, which is also what aten returns).
+// What this buys over the L1 kernel: ~100 instead of ~190 issue slots per pixel (that kernel's bound),
+// no data-dependent L1 wavefronts, and every DRAM / L2 latency of a tile hidden behind the previous tile's arithmetic.
+#ifndef VFI_WS_MIN_CTAS
+#define VFI_WS_MIN_CTAS 3
+#endif
+constexpr int WS_TILE = 32, WS_THREADS = 256, WS_MIN_CTAS = VFI_WS_MIN_CTAS;  // resident CTAs per SM the register budget allows
 constexpr int WS_BW = 64, WS_SMALL_W = 48, WS_SMALL_H = 40;                // staging windows (source pixels): big is 64 x WsBox::H
-template <typename TS> struct WsBox { static constexpr int H = sizeof(TS) == 4 ? 48 : 64; };
+// fp32 frames get a 64 x 32 big window (the bytes of the 16-bit one): three resident CTAs then leave the L1 the fall-back tiles
+// gather through as large as in the 16-bit case (with 64 x 48 it shrank to ~30 KB and incoherent flow ran 3.5x slower).
+template <typename TS> struct WsBox { static constexpr int H = sizeof(TS) == 4 ? 32 : 64; };
+
+template <typename TS>
+struct __align__(128) WsSmem {
+  TS box[2][3 * WsBox<TS>::H * WS_BW];                                     // TMA destinations (128-byte aligned)
+  unsigned long long bar[2];
+  int red[2][8][4];
+  int plan[2][4];                                                          // anchor x, anchor y, window width (0 = L1 path), window height
+};
 
 struct WarpStagedArgs {
   WarpParams p;
   unsigned long long* tile_counts;                                         // optional [2]: tiles staged / tiles on the L1 path
+  int tiles_x, tiles_y, num_tiles;
   int dbg;                                                                 // VFI_WARP_DEBUG (diagnostics): 1 = never stage, 2 = big window only
-  alignas(128) CUtensorMap tm_big;                                         // src {W, H, 3, B}, box {64, WS_BH, 3, 1}
+  alignas(128) CUtensorMap tm_big;                                         // src {W, H, 3, B}, box {64, WsBox::H, 3, 1}
   alignas(128) CUtensorMap tm_small;                                       // same tensor, box {48, 40, 3, 1}
 };
 
 __device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_tma_load(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(0), "r"(c3), "r"(bar)
+               : "memory");
+}
+
+// Two adjacent elements as one load / store (flow pairs, output pairs).
+template <typename T> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<__nv_bfloat16> { using type = uint32_t; };
+template <> struct Pair<__half> { using type = uint32_t; };
+__device__ __forceinline__ void unpack_pair(float2 v, const float*, float& a, float& b) { a = v.x; b = v.y; }
+__device__ __forceinline__ void unpack_pair(uint32_t v, const __nv_bfloat16*, float& a, float& b) {
+  a = __uint_as_float(v << 16); b = __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack_pair(uint32_t v, const __half*, float& a, float& b) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+  a = f.x; b = f.y;
+}
+__device__ __forceinline__ float2 pack_pair(float a, float b, const float*) { return make_float2(a, b); }
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, const __nv_bfloat16*) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, const __half*) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Where a thread's pixels of one tile are: batch entry, row of its first pixel pair, column of the pair (always even).
+struct WsOrigin { int b, y, x, tx, ty; };
 
 template <typename TS, typename TF, bool REC, bool RECIP>
-__global__ void __launch_bounds__(WS_THREADS) warp_fwd_staged_kernel(const __grid_constant__ WarpStagedArgs a) {
+__global__ void __launch_bounds__(WS_THREADS, WS_MIN_CTAS) warp_fwd_staged_kernel(const __grid_constant__ WarpStagedArgs a) {
   constexpr int BH = WsBox<TS>::H;
+  using FP = typename Pair<TF>::type;
+  using SP = typename Pair<TS>::type;
   const WarpParams& p = a.p;
-  __shared__ __align__(128) TS box[3 * BH * WS_BW];
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ int red[8][4];
-  __shared__ int plan[4];                                                  // anchor x, anchor y, window width (0 = L1 path), window height
+  extern __shared__ uint8_t ws_raw[];
+  WsSmem<TS>& s = *reinterpret_cast<WsSmem<TS>*>(ws_raw + ((128 - (ws_smem_u32(ws_raw) & 127)) & 127));
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int b = blockIdx.z, x = blockIdx.x * WS_TILE + lane, ybase = blockIdx.y * WS_TILE + wrp;
-  const int H = p.H, W = p.W;
+  const int H = p.H, W = p.W, G = (int)gridDim.x, N = a.num_tiles;
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ws_smem_u32(&bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ws_smem_u32(&s.bar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ws_smem_u32(&s.bar[1])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- 1. flow -> source coordinates
-  const TF* fl = reinterpret_cast<const TF*>(p.flow) + b * p.f_sn;
-  float fx[WS_ROWS], fy[WS_ROWS];
-  bool ok[WS_ROWS];
+  // Thread -> pixels of a tile: a half-warp is one row of 32 pixels (lane & 15 = pixel pair), a warp two neighbouring rows, and
+  // a thread owns the pairs at rows 4 w + h and 4 w + 2 + h (w = warp, h = lane / 16): flow loads and planar stores move two
+  // pixels each.  Tiles advance by G = gridDim.x with carries instead of divisions.
+  const int per_img = a.tiles_x * a.tiles_y;
+  const int gb = G / per_img, gy = (G - gb * per_img) / a.tiles_x, gx = G - gb * per_img - gy * a.tiles_x;
+  const int yin = 4 * wrp + (lane >> 4), xin = 2 * (lane & 15);
+  auto first = [&](int t) {
+    WsOrigin o;
+    o.b = t / per_img;
+    const int r = t - o.b * per_img;
+    o.ty = r / a.tiles_x; o.tx = r - o.ty * a.tiles_x;
+    o.y = o.ty * WS_TILE + yin; o.x = o.tx * WS_TILE + xin;
+    return o;
+  };
+  auto advance = [&](WsOrigin o) {
+    o.tx += gx;
+    if (o.tx >= a.tiles_x) { o.tx -= a.tiles_x; ++o.ty; }
+    o.ty += gy;
+    if (o.ty >= a.tiles_y) { o.ty -= a.tiles_y; ++o.b; }
+    o.b += gb;
+    o.y = o.ty * WS_TILE + yin; o.x = o.tx * WS_TILE + xin;
+    return o;
+  };
+  // (B) flow of a tile: the loads only -- the values stay raw so that nothing waits for them before the next iteration
+  auto load_flow = [&](const WsOrigin& o, FP (&fx)[2], FP (&fy)[2]) {
+    const TF* fl = reinterpret_cast<const TF*>(p.flow) + o.b * p.f_sn + min(o.x, W - 2);
 #pragma unroll
-  for (int i = 0; i < WS_ROWS; ++i) {
-    const int y = ybase + 8 * i;
-    ok[i] = x < W && y < H;
-    const TF* q = fl + (long long)min(y, H - 1) * p.f_sh + min(x, W - 1);
-    fx[i] = to_f32<TF>(__ldcs(q));
-    fy[i] = to_f32<TF>(__ldcs(q + p.f_sc));
-  }
-  float ix[WS_ROWS], iy[WS_ROWS];
-  int x0[WS_ROWS], y0[WS_ROWS];
-  int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+    for (int j = 0; j < 2; ++j) {
+      const TF* q = fl + (long long)min(o.y + 2 * j, H - 1) * p.f_sh;
+      fx[j] = __ldcs(reinterpret_cast<const FP*>(q));
+      fy[j] = __ldcs(reinterpret_cast<const FP*>(q + p.f_sc));
+    }
+  };
+  // (A) coordinates of a tile (pixel 2 j + e: row pair j, column x + e), its bounding box, the plan and the copy into window
+  // `slot`.  Contains the tile's __syncthreads.
+  auto plan_tile = [&](const WsOrigin& o, int slot, const FP (&fx)[2], const FP (&fy)[2], float (&ix)[4], float (&iy)[4]) {
+    int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+    const int xc = min(o.x, W - 2);
 #pragma unroll
-  for (int i = 0; i < WS_ROWS; ++i) {
-    ix[i] = warp_coord_t<RECIP>(min(x, W - 1), fx[i], p.ax);
-    iy[i] = warp_coord_t<RECIP>(min(ybase + 8 * i, H - 1), fy[i], p.ay);
-    x0[i] = __float2int_rd(ix[i]);
-    y0[i] = __float2int_rd(iy[i]);
-    if (ok[i]) { mnx = min(mnx, x0[i]); mxx = max(mxx, x0[i]); mny = min(mny, y0[i]); mxy = max(mxy, y0[i]); }
-  }
-  mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
-  mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
-  if (lane == 0) { red[wrp][0] = mnx; red[wrp][1] = mxx; red[wrp][2] = mny; red[wrp][3] = mxy; }
-  __syncthreads();
-  // ---- 2. plan + copy (thread 0)
-  if (tid == 0) {
+    for (int j = 0; j < 2; ++j) {
+      const int y = o.y + 2 * j;
+      float f0, f1, g0, g1;
+      unpack_pair(fx[j], static_cast<const TF*>(nullptr), f0, f1);
+      unpack_pair(fy[j], static_cast<const TF*>(nullptr), g0, g1);
+      ix[2 * j] = warp_coord_t<RECIP>(xc, f0, p.ax);
+      ix[2 * j + 1] = warp_coord_t<RECIP>(xc + 1, f1, p.ax);
+      iy[2 * j] = warp_coord_t<RECIP>(min(y, H - 1), g0, p.ay);
+      iy[2 * j + 1] = warp_coord_t<RECIP>(min(y, H - 1), g1, p.ay);
+      if (o.x < W && y < H) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { mnx = min(mnx, red[w][0]); mxx = max(mxx, red[w][1]); mny = min(mny, red[w][2]); mxy = max(mxy, red[w][3]); }
-    // The copy engine wants the first byte of a box row 16-byte aligned: the window is anchored at the 8-pixel boundary at or
-    // left of the box (a misaligned innermost coordinate faults as "illegal instruction").
-    mnx = (mnx >> 3) << 3;
-    const int ex = mxx - mnx + 2, ey = mxy - mny + 2;                      // source pixels from the anchor to the last corner
-    int bw = 0, bh = 0;
-    if (ex <= WS_SMALL_W && ey <= WS_SMALL_H && !(a.dbg & 2)) { bw = WS_SMALL_W; bh = WS_SMALL_H; }
-    else if (ex <= WS_BW && ey <= BH) { bw = WS_BW; bh = BH; }
-    if (a.dbg & 1) bw = bh = 0;
-    plan[0] = mnx; plan[1] = mny; plan[2] = bw; plan[3] = bh;
-    if (bw) {
-      const uint32_t bar_a = ws_smem_u32(&bar);
-      const uint32_t bytes = (a.dbg & 8) ? 0u : (uint32_t)(3 * bw * bh * sizeof(TS));
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-      if (!(a.dbg & 8)) {
-        if (bw == WS_SMALL_W) {
-          asm volatile(
-              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-                  ws_smem_u32(box)),
-              "l"(reinterpret_cast<uint64_t>(&a.tm_small)), "r"(mnx), "r"(mny), "r"(0), "r"(b), "r"(bar_a)
-              : "memory");
-        } else {
-          asm volatile(
-              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-                  ws_smem_u32(box)),
-              "l"(reinterpret_cast<uint64_t>(&a.tm_big)), "r"(mnx), "r"(mny), "r"(0), "r"(b), "r"(bar_a)
-              : "memory");
+        for (int e = 0; e < 2; ++e) {
+          const int xi = __float2int_rd(ix[2 * j + e]), yi = __float2int_rd(iy[2 * j + e]);
+          mnx = min(mnx, xi); mxx = max(mxx, xi); mny = min(mny, yi); mxy = max(mxy, yi);
         }
       }
     }
-    if (a.tile_counts) atomicAdd(a.tile_counts + (bw ? 0 : 1), 1ull);
-  }
-  __syncthreads();
-  const int ax0 = plan[0], ay0 = plan[1], bw = plan[2], bh = plan[3];
-  float r[WS_ROWS][3];
-  if (bw) {
-    // ---- 3a. gathers from the staged window
-    {
-      const uint32_t bar_a = ws_smem_u32(&bar);
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) *reinterpret_cast<int4*>(&s.red[slot][wrp][0]) = make_int4(mnx, mxx, mny, mxy);
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int4 v = *reinterpret_cast<const int4*>(&s.red[slot][w][0]);
+        mnx = min(mnx, v.x); mxx = max(mxx, v.y); mny = min(mny, v.z); mxy = max(mxy, v.w);
+      }
+      mnx = (mnx >> 3) << 3;                                               // 16-byte aligned first byte of every box row
+      const int ex = mxx - mnx + 2, ey = mxy - mny + 2;                    // source pixels from the anchor to the last corner
+      int bw = 0, bh = 0;
+      if (ex <= WS_SMALL_W && ey <= WS_SMALL_H && !(a.dbg & 2)) { bw = WS_SMALL_W; bh = WS_SMALL_H; }
+      else if (ex <= WS_BW && ey <= BH) { bw = WS_BW; bh = BH; }
+      if (a.dbg & 1) bw = bh = 0;
+      *reinterpret_cast<int4*>(&s.plan[slot][0]) = make_int4(mnx, mny, bw, bh);
+      if (bw) {
+        const uint32_t bar_a = ws_smem_u32(&s.bar[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(3 * bw * bh * sizeof(TS))) : "memory");
+        if (bw == WS_SMALL_W) ws_tma_load(ws_smem_u32(&s.box[slot][0]), &a.tm_small, mnx, mny, o.b, bar_a);
+        else ws_tma_load(ws_smem_u32(&s.box[slot][0]), &a.tm_big, mnx, mny, o.b, bar_a);
+      }
+      if (a.tile_counts) atomicAdd(a.tile_counts + (bw ? 0 : 1), 1ull);
+    }
+  };
+
+  int t = (int)blockIdx.x;
+  if (t >= N) return;
+  WsOrigin oc, on = first(t), of;                                          // tile being produced / planned / whose flow is in flight
+  FP fx[2], fy[2];
+  float nix[4], niy[4];
+  uint32_t phase = 0;                                                      // bit s: parity of window s's next completed copy
+  load_flow(on, fx, fy);
+  plan_tile(on, 0, fx, fy, nix, niy);
+  of = advance(on);
+  if (t + G < N) load_flow(of, fx, fy);
+  for (int it = 0; t < N; ++it, t += G) {
+    const int slot = it & 1;
+    float ix[4], iy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ix[i] = nix[i]; iy[i] = niy[i]; }
+    oc = on; on = of;
+    if (t + G < N) plan_tile(on, slot ^ 1, fx, fy, nix, niy);              // (A); its barrier also publishes plan[slot]
+    else __syncthreads();
+    of = advance(on);
+    if (t + 2 * G < N) load_flow(of, fx, fy);                              // (B)
+    // ---- (C) tile t
+    const int4 pl = *reinterpret_cast<const int4*>(&s.plan[slot][0]);
+    const int ax0 = pl.x, ay0 = pl.y, bw = pl.z, bh = pl.w;
+    const bool ok = oc.x < W;                                              // W is even: both pixels of a pair or neither
+    float r[4][3];
+    if (bw) {
+      const uint32_t bar_a = ws_smem_u32(&s.bar[slot]), par = (phase >> slot) & 1u;
       uint32_t done = 0;
       while (!done)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
-    }
-    const int plane = bw * bh;
+                     : "=r"(done) : "r"(bar_a), "r"(par) : "memory");
+      phase ^= 1u << slot;
+      const TS* box = &s.box[slot][0];
+      const int plane = bw * bh;
 #pragma unroll
-    for (int i = 0; i < WS_ROWS; ++i) {
-      const float x0f = (float)x0[i], y0f = (float)y0[i];
-      const float wx1 = ix[i] - x0f, wx0 = (x0f + 1.0f) - ix[i], wy1 = iy[i] - y0f, wy0 = (y0f + 1.0f) - iy[i];
-      const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
-      const int o = ok[i] ? (y0[i] - ay0) * bw + (x0[i] - ax0) : 0;       // pixels past the frame edge are not stored: any address
+      for (int i = 0; i < 4; ++i) {
+        const int xi = __float2int_rd(ix[i]), yi = __float2int_rd(iy[i]);
+        const float x0f = (float)xi, y0f = (float)yi;
+        const float wx1 = ix[i] - x0f, wx0 = (x0f + 1.0f) - ix[i], wy1 = iy[i] - y0f, wy0 = (y0f + 1.0f) - iy[i];
+        const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+        const int o = (ok && oc.y + 2 * (i >> 1) < H) ? (yi - ay0) * bw + (xi - ax0) : 0;   // pixels past the frame edge are not stored
+        const TS* q = box + o;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const TS* q = box + c * plane + o;
-        const float v00 = to_f32<TS>(q[0]), v01 = to_f32<TS>(q[1]), v10 = to_f32<TS>(q[bw]), v11 = to_f32<TS>(q[bw + 1]);
-        r[i][c] = fmaf(v11, w11, fmaf(v10, w10, fmaf(v01, w01, v00 * w00)));
+        for (int c = 0; c < 3; ++c, q += plane) {
+          const float v00 = to_f32<TS>(q[0]), v01 = to_f32<TS>(q[1]), v10 = to_f32<TS>(q[bw]), v11 = to_f32<TS>(q[bw + 1]);
+          r[i][c] = fmaf(v11, w11, fmaf(v10, w10, fmaf(v01, w01, v00 * w00)));
+        }
       }
-    }
-  } else {
-    // ---- 3b. the fast kernel's L1 path (tile's corners do not fit a window)
-    const TS* s0 = reinterpret_cast<const TS*>(p.src) + b * p.s_sn;
-#pragma unroll
-    for (int i = 0; i < WS_ROWS; ++i)
-      sample3<TS, RECIP>(s0, s0 + p.s_sc, s0 + 2 * p.s_sc, (int)p.s_sh, H, W, min(x, W - 1), min(ybase + 8 * i, H - 1), fx[i], fy[i], p.ax,
-                         p.ay, r[i]);
-  }
-  // ---- 4. store
-#pragma unroll
-  for (int i = 0; i < WS_ROWS; ++i) {
-    if (!ok[i]) continue;
-    const int y = ybase + 8 * i;
-    if constexpr (REC) {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + (long long)x * p.o_sw;
-      const __nv_bfloat162 c01 = __floats2bfloat162_rn(r[i][0], r[i][1]), c2z = __floats2bfloat162_rn(r[i][2], 0.0f);
-      const uint32_t lo = *reinterpret_cast<const uint32_t*>(&c01), hi = *reinterpret_cast<const uint32_t*>(&c2z);
-      __stcs(reinterpret_cast<uint4*>(out), make_uint4(lo, hi, lo, hi));
     } else {
-      TS* out = reinterpret_cast<TS*>(p.out) + b * p.o_sn + (long long)y * p.o_sh + x;
+      // the fast kernel's L1 path (the tile's corners do not fit a window)
+      const TS* s0 = reinterpret_cast<const TS*>(p.src) + oc.b * p.s_sn;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) __stcs(out + c * p.o_sc, from_f32<TS>(r[i][c]));
+      for (int i = 0; i < 4; ++i) sample3_at<TS>(s0, s0 + p.s_sc, s0 + 2 * p.s_sc, (int)p.s_sh, H, W, ix[i], iy[i], r[i]);
+    }
+    if (ok) {
+      if constexpr (REC) {
+        uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oc.b * p.o_sn + (long long)oc.y * p.o_sh +
+                                              (long long)oc.x * p.o_sw);
+        const long long row2 = 2 * p.o_sh / 8, px = p.o_sw / 8;            // in 16-byte records
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (oc.y + 2 * (i >> 1) >= H) continue;
+          const uint32_t lo = pack_pair(r[i][0], r[i][1], static_cast<const __nv_bfloat16*>(nullptr));
+          const uint32_t hi = pack_pair(r[i][2], 0.0f, static_cast<const __nv_bfloat16*>(nullptr));
+          __stcs(out + (i >> 1) * row2 + (i & 1) * px, make_uint4(lo, hi, lo, hi));
+        }
+      } else {
+        TS* out = reinterpret_cast<TS*>(p.out) + oc.b * p.o_sn + (long long)oc.y * p.o_sh + oc.x;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (oc.y + 2 * j >= H) continue;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            __stcs(reinterpret_cast<SP*>(out + c * p.o_sc + 2 * j * p.o_sh), pack_pair(r[2 * j][c], r[2 * j + 1][c], static_cast<const TS*>(nullptr)));
+        }
+      }
     }
   }
 }
@@ -612,7 +719,13 @@ __device__ unsigned long long g_warp_tile_counts[2];                       // VF
 
 template <typename TS, typename TF>
 int launch_fwd(const WarpParams& p, bool rec, bool fast, int flags, cudaStream_t st) {
-  if (fast && !(flags & VFI_WARP_NO_STAGING) && p.W >= WS_TILE && p.H >= 8) {
+  // the staged kernel moves pixel PAIRS: even width, flow rows / planes and (planar) output rows / planes aligned to a pair
+  const auto pair_ok = [](const void* base, size_t es, long long a, long long b, long long c) {
+    return aligned(base, 2 * es) && a % 2 == 0 && b % 2 == 0 && c % 2 == 0;
+  };
+  const bool pairs = p.W % 2 == 0 && pair_ok(p.flow, sizeof(TF), p.f_sh, p.f_sc, p.f_sn) &&
+                     (rec || pair_ok(p.out, sizeof(TS), p.o_sh, p.o_sc, p.o_sn));
+  if (fast && pairs && !(flags & VFI_WARP_NO_STAGING) && p.W >= WS_TILE && p.H >= 8) {
     // staged path (TMA window + shared-memory gathers); falls through to the L1 kernels when the source cannot be mapped
     WarpStagedArgs a;
     a.p = p;
@@ -621,20 +734,50 @@ int launch_fwd(const WarpParams& p, bool rec, bool fast, int flags, cudaStream_t
     a.dbg = dbg_env ? atoi(dbg_env) : 0;
     if (warp_src_map<TS>(&a.tm_big, p, WS_BW, WsBox<TS>::H) && warp_src_map<TS>(&a.tm_small, p, WS_SMALL_W, WS_SMALL_H)) {
       if (flags & VFI_WARP_COUNT_TILES) VFI_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&a.tile_counts), g_warp_tile_counts));
-      dim3 grid(ceil_div(p.W, WS_TILE), ceil_div(p.H, WS_TILE), p.B);
+      a.tiles_x = ceil_div(p.W, WS_TILE); a.tiles_y = ceil_div(p.H, WS_TILE);
+      const long long tiles = (long long)a.tiles_x * a.tiles_y * p.B;
+      VFI_REQUIRE(tiles < (1LL << 30), VFI_ERR_UNSUPPORTED, "vfi_warp_fwd: too many tiles");
+      a.num_tiles = (int)tiles;
       const bool recip = p.ax.recip != 0;
+      const size_t smem = sizeof(WsSmem<TS>) + 128;
+      // persistent grid: every CTA the SMs can hold at once
+      auto launch = [&](void (*kern)(const WarpStagedArgs)) -> int {
+        // resident CTAs per SM of this instantiation on this device: asked once (the answer also records that the kernel's
+        // dynamic shared-memory limit has been raised)
+        static std::mutex mu;
+        static std::map<std::pair<const void*, int>, int> resident;
+        static int sms_of[64] = {0};
+        int dev = 0;
+        VFI_CUDA(cudaGetDevice(&dev));
+        int ctas = 0, sms = 0;
+        {
+          std::lock_guard<std::mutex> lock(mu);
+          auto it = resident.find({reinterpret_cast<const void*>(kern), dev});
+          if (it != resident.end()) { ctas = it->second; sms = sms_of[dev & 63]; }
+        }
+        if (!ctas) {
+          VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+          VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          VFI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, WS_THREADS, smem));
+          if (ctas < 1) ctas = 1;
+          std::lock_guard<std::mutex> lock(mu);
+          resident[{reinterpret_cast<const void*>(kern), dev}] = ctas;
+          sms_of[dev & 63] = sms;
+        }
+        const int grid = (int)(tiles < (long long)sms * ctas ? tiles : (long long)sms * ctas);
+        kern<<<grid, WS_THREADS, smem, st>>>(a);
+        return VFI_OK;
+      };
       bool launched = false;
+      int lrc = VFI_OK;
       if constexpr (std::is_same<TS, __nv_bfloat16>::value) {
         if (rec) {
-          if (recip) warp_fwd_staged_kernel<TS, TF, true, true><<<grid, WS_THREADS, 0, st>>>(a);
-          else warp_fwd_staged_kernel<TS, TF, true, false><<<grid, WS_THREADS, 0, st>>>(a);
+          lrc = recip ? launch(warp_fwd_staged_kernel<TS, TF, true, true>) : launch(warp_fwd_staged_kernel<TS, TF, true, false>);
           launched = true;
         }
       }
-      if (!launched) {
-        if (recip) warp_fwd_staged_kernel<TS, TF, false, true><<<grid, WS_THREADS, 0, st>>>(a);
-        else warp_fwd_staged_kernel<TS, TF, false, false><<<grid, WS_THREADS, 0, st>>>(a);
-      }
+      if (!launched) lrc = recip ? launch(warp_fwd_staged_kernel<TS, TF, false, true>) : launch(warp_fwd_staged_kernel<TS, TF, false, false>);
+      if (lrc) return lrc;
       VFI_LAUNCH_CHECK("warp_fwd_staged_kernel");
       return VFI_OK;
     }
