@@ -162,7 +162,7 @@ def test_warp_low_precision(dtype):
 @pytest.mark.parametrize("division", ["ieee", "reciprocal"])
 def test_warp_staged_kernel_is_bit_identical_to_the_l1_kernel(dtype, division):
     """The TMA-staged warp (source window in shared memory, zero fill by the copy engine) against round 1's L1-gather
-    kernel on every flow class the staging decision distinguishes: near-identity (40 x 40 window), sheared / translated
+    kernel on every flow class the staging decision distinguishes: near-identity (48 x 40 window), sheared / translated
     (64-wide window, anchored at the tile's north-west corner wherever it lies, also outside the frame), incoherent large
     displacement (tiles fall back to L1 inside the same launch), NaN / inf flow, frames whose size is not a multiple of the
     tile.  Results must not depend on the route: exact equality, and the tile counters prove both routes ran."""
