@@ -193,8 +193,10 @@ def test_warp_staged_kernel_is_bit_identical_to_the_l1_kernel(dtype, division):
         b = vfi_b200.warp(src, flow, division=division, staging=False)
         tiles = B * ((H + 31) // 32) * ((W + 31) // 32)
         assert staged + direct == tiles, (kind, staged, direct, tiles)
-        if kind in ("tiny", "shear", "translate", "edge"):
+        if kind in ("tiny", "translate", "edge") or (kind == "shear" and dtype != torch.float32):
             assert direct == 0, (kind, staged, direct)
+        if kind == "shear":                                        # fp32 frames have a 64 x 32 big window: some tiles do not fit
+            assert staged > 0, (kind, staged, direct)
         if kind == "iid":
             assert direct == tiles
         assert torch.equal(torch.nan_to_num(a.float(), nan=123.0), torch.nan_to_num(b.float(), nan=123.0)), kind
