@@ -541,9 +541,12 @@ def main():
                    "sharding": "independent frame pairs per rank, no data-path collective"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "DCNv2 forward (one launch per layer, 3 per step)",
-                     "achieved": dcn_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                     "frac": dcn_tflops / pk["tensor_sustained"], "traffic": tr.get("dcn_fwd"), "traffic_source": tr.get("dcn_fwd_source"), "peak_source": pk["source"] + " sustained bf16",
-                     "frac_of_burst_peak": dcn_tflops / pk["tensor_burst"], "ms_per_launch": dcn_ms,
+                     # the timed region is ~0.1-0.3 s: the BURST bf16 figure is the applicable peak (the sustained one belongs to
+                     # kernels timed inside multi-second steps); both fractions are reported
+                     "achieved": dcn_tflops, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
+                     "frac": dcn_tflops / pk["tensor_burst"], "traffic": tr.get("dcn_fwd"), "traffic_source": tr.get("dcn_fwd_source"), "peak_source": pk["source"] + " burst bf16",
+                     "frac_of_burst_peak": dcn_tflops / pk["tensor_burst"], "frac_of_sustained_peak": dcn_tflops / pk["tensor_sustained"],
+                     "ms_per_launch": dcn_ms,
                      "algorithmic_flop_per_launch": P * FLOP_PER_PX,
                      # what actually bounds the operator on this SM: building one A row reads
                      # 9 taps x 4 corners x 128 B of activations through the 128 B/clk/SM load/store data path

@@ -376,9 +376,11 @@ def choose_interpolation_factor(fps: float, target_fps: Optional[float], max_int
 
 def stream_video(input_video_path: str, output_video_path: str, model, device, *, target_fps: Optional[float] = None,
                  max_interpolation_factor: int = 4, frame_interval: int = 1, codec: str = "mp4v", scale: float = 0.5,
-                 batch_pairs: int = 8, autocast_dtype: Optional[torch.dtype] = None, queue_depth: int = 32) -> int:
+                 batch_pairs: int = 8, autocast_dtype="reference", queue_depth: int = 32) -> int:
     """``interpolate_video`` of inference.py:60-205 with the frame loop replaced by ``PairStreamer.run_iter``: same arguments
-    (the model object instead of a checkpoint path), same file written.  Decoding + resizing (:47) and encoding run in
+    (the model object instead of a checkpoint path), same file written.  ``autocast_dtype="reference"`` (default) mirrors
+    inference.py:158-159 -- ``torch.cuda.amp.autocast()``, i.e. fp16 on a CUDA device and nothing on CPU; pass a dtype or ``None``
+    to choose otherwise.  Decoding + resizing (:47) and encoding run in
     their own threads behind bounded queues, so they overlap the copies and the model.  Returns the number of frames written.
     A video that cannot be opened raises ``ValueError`` (the reference logs the same message and returns)."""
     import queue
@@ -446,6 +448,10 @@ def stream_video(input_video_path: str, output_video_path: str, model, device, *
     t_enc.start()
     written = 0
     try:
+        if isinstance(autocast_dtype, str):
+            if autocast_dtype != "reference":
+                raise ValueError("autocast_dtype: a torch dtype, None, or 'reference'")
+            autocast_dtype = torch.float16 if torch.device(device).type == "cuda" else None
         streamer = PairStreamer(model, device, batch_pairs=batch_pairs, autocast_dtype=autocast_dtype)
         for _, frame in streamer.run_iter(frames(), frame_interval, factor):
             if not put(q_out, frame):
