@@ -275,6 +275,8 @@ def run_cfg3(args, desc):
     torch.cuda.set_device(dev)
     math = "bf16_tc" if args.math == "auto" else args.math
     ts = TrainStep(topo, dev, math=math, overlap=not args.no_overlap)
+    if args.cuda_graph:
+        ts.capture()
     for _ in range(args.warmup):
         ts.step()
     if topo.world > 1:
@@ -299,7 +301,7 @@ def run_cfg3(args, desc):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    for _ in range(5):                                   # separate, synchronising pass: how long the step waits for the exchange
+    for _ in range(0 if args.cuda_graph else 5):         # separate, synchronising pass: how long the step waits for the exchange
         ts.step(measure=True)
     exposed_us = 1e3 * statistics.fmean(ts.exposed_ms) if ts.exposed_ms else 0.0
     ok = bool(torch.isfinite(ts.flow.grad).all()) and bool(torch.isfinite(ts.bucket.flat).all())
@@ -310,8 +312,9 @@ def run_cfg3(args, desc):
                 "config": {"workload": desc, "global_batch": ts.global_batch, "batch_per_gpu": ts.B, "height": ts.H, "width": ts.W, "math": math,
                            "exchange": ("3 group all-reduces launched from autograd hooks (block 3 first), overlapped with backward"
                                         if ts.overlap else "one flat-bucket all-reduce after backward"),
-                           "bucket_bytes": ts.bucket.numel * 4},
-                "gpu_launches": int(launches), "allreduce_exposed_us": exposed_us, "gradients_finite": ok, "clocks": clocks}
+                           "bucket_bytes": ts.bucket.numel * 4,
+                           "launch": "one CUDA graph replay per step" if args.cuda_graph else "eager (one launch per kernel)"},
+                "gpu_launches": int(launches) if not args.cuda_graph else int(ts.graph_launches * args.steps), "allreduce_exposed_us": None if args.cuda_graph else exposed_us, "gradients_finite": ok, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if topo.world > 1:
         dist.destroy_process_group()
@@ -332,6 +335,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--cuda-graph", action="store_true", help="cfg3: capture the whole step in a CUDA graph and replay it (SURVEY H7)")
     ap.add_argument("--no-overlap", action="store_true", help="cfg3: one all-reduce after backward instead of the overlapped group exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -871,6 +871,28 @@ def test_fusion_block_training_step_matches_stock_torchvision():
         assert maxabs(p.grad, ref[k]) <= tol(ref[k], 3e-5), k
 
 
+def test_training_step_cuda_graph_replay_matches_eager():
+    """TrainStep.capture(): the whole cfg3 step (bucket zeroing, forward, backward into the flat gradient bucket) replayed as
+    one CUDA graph gives the gradients of the eager step -- same kernels, same order; the only non-determinism is the order of
+    the fp32 atomics, hence a relative bar instead of equality."""
+    from vfi_b200 import shard
+    from vfi_b200.trainstep import TrainStep
+
+    topo = shard.Topology(rank=0, world=1, local_rank=0)
+    ts = TrainStep(topo, DEV, math="bf16_tc", global_batch=2, size=64)
+    ts.step()
+    torch.cuda.synchronize()
+    ref_flat, ref_flow = ts.bucket.flat.clone(), ts.flow.grad.clone()
+    ts.capture()
+    assert ts.graph is not None and ts.graph_launches > 0
+    for _ in range(2):
+        ts.step()
+    torch.cuda.synchronize()
+    assert torch.isfinite(ts.bucket.flat).all()
+    assert relerr(ts.bucket.flat, ref_flat) <= 1e-3
+    assert relerr(ts.flow.grad, ref_flow) <= 1e-3
+
+
 def test_smoke_entry():
     import __graft_entry__
 

@@ -79,8 +79,39 @@ class TrainStep:
         self.feat = torch.randn(B, 64, H, W, device=self.dev, generator=g).to(dt)
         self.flow = (2.0 * torch.randn(B, 2, H, W, device=self.dev, generator=g)).to(dt).requires_grad_(True)
         self.exposed_ms = []
+        self.graph = None
+        self.graph_launches = 0
+
+    # ---------------------------------------------------------------------------------------------- CUDA graph
+    def capture(self, warmup: int = 3) -> None:
+        """Capture one whole step -- zero the bucket, forward, backward with its hook-launched group all-reduces, the final wait --
+        into a CUDA graph; ``step()`` then replays it.  At 16 / world samples per GPU the step is ~200 launches of a few
+        microseconds each (half of them the stock convolutions): launch latency, not the kernels, bounds it from N = 4 on.  All
+        tensors of a step are static (inputs, the flat gradient bucket) or live in the graph's private pool (activations,
+        workspaces, TMA tensor maps are encoded from those fixed addresses at capture time)."""
+        if self.graph is not None:
+            return
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):                           # eager warm-up on the side stream the capture will use
+            for _ in range(warmup):
+                self._body(measure=False)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g, stream=s):
+            self._body(measure=False)
+        self.graph_launches = ops.launch_count() - n0        # kernels of this library inside one replay
+        self.graph = g
 
     def step(self, measure: bool = False) -> Optional[float]:
+        if self.graph is not None and not measure:
+            self.graph.replay()
+            return None
+        return self._body(measure)
+
+    def _body(self, measure: bool = False) -> Optional[float]:
         self.bucket.zero()
         self.flow.grad = None
         if self.overlap:
