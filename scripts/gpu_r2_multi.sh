@@ -10,6 +10,9 @@ timeout 600 $TR --master-port 29511 bench.py --gpus $N --workload cfg3 --math bf
 import json; d=json.loads(open('gpurun_out/bench_cfg3_n$N.json').read().strip().splitlines()[-1]); print('cfg3 overlap', d['ms_per_step'], d['value'], d['allreduce_exposed_us'])"
 timeout 600 $TR --master-port 29512 bench.py --gpus $N --workload cfg3 --math bf16_tc --steps 20 --warmup 5 --no-overlap > gpurun_out/bench_cfg3_noov_n$N.json 2> gpurun_out/bench_cfg3_noov_n$N.err; python -c "
 import json; d=json.loads(open('gpurun_out/bench_cfg3_noov_n$N.json').read().strip().splitlines()[-1]); print('cfg3 no overlap', d['ms_per_step'], d['value'], d['allreduce_exposed_us'])"
+timeout 600 $TR --master-port 29516 bench.py --gpus $N --workload cfg3 --math bf16_tc --steps 20 --warmup 5 --cuda-graph > gpurun_out/bench_cfg3_graph_n$N.json 2> gpurun_out/bench_cfg3_graph_n$N.err; echo "cfg3 graph exit $?"; tail -2 gpurun_out/bench_cfg3_graph_n$N.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_cfg3_graph_n$N.json').read().strip().splitlines()[-1]); print('cfg3 cuda graph', d['ms_per_step'], d['value'])"
+[ -n "$ONLY_CFG3" ] && exit 0
 timeout 900 $TR --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "cfg2 exit $?"; python -c "
 import json; d=json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1]); print('cfg2', d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['h2d_gbs_this_rank'], d['e2e']['cpu_affinity'])"
 timeout 900 $TR --master-port 29514 bench.py --gpus $N --workload cfg5 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg5_n$N.json 2> gpurun_out/bench_cfg5_n$N.err; echo "cfg5 exit $?"; python -c "

@@ -890,7 +890,7 @@ def test_training_step_cuda_graph_replay_matches_eager():
     torch.cuda.synchronize()
     assert torch.isfinite(ts.bucket.flat).all()
     assert relerr(ts.bucket.flat, ref_flat) <= 1e-3
-    assert relerr(ts.flow.grad, ref_flow) <= 1e-3
+    assert relerr(ts.flow.grad, ref_flow) <= 1e-2      # a bf16 tensor: one ulp is 4e-3 of the value
 
 
 def test_smoke_entry():
