@@ -274,7 +274,7 @@ def run_cfg3(args, desc):
     dev = torch.device("cuda", topo.local_rank)
     torch.cuda.set_device(dev)
     math = "bf16_tc" if args.math == "auto" else args.math
-    ts = TrainStep(topo, dev, math=math, overlap=not args.no_overlap)
+    ts = TrainStep(topo, dev, math=math, overlap=not args.no_overlap, fused=args.fused_blocks)
     if args.cuda_graph:
         ts.capture()
     for _ in range(args.warmup):
@@ -313,7 +313,9 @@ def run_cfg3(args, desc):
                            "exchange": ("3 group all-reduces launched from autograd hooks (block 3 first), overlapped with backward"
                                         if ts.overlap else "one flat-bucket all-reduce after backward"),
                            "bucket_bytes": ts.bucket.numel * 4,
-                           "launch": "one CUDA graph replay per step" if args.cuda_graph else "eager (one launch per kernel)"},
+                           "launch": "one CUDA graph replay per step" if args.cuda_graph else "eager (one launch per kernel)",
+                           "blocks": ("record activations [B,H,W,72] + fused DCN block (vfi_dcn_fwd_fused / vfi_dcn_bwd_*_fused)" if ts.fused
+                                      else "the reference's glue as stock ops (chunk / cat / sigmoid) around vfi_dcn_fwd / vfi_dcn_bwd_*")},
                 "gpu_launches": int(launches) if not args.cuda_graph else int(ts.graph_launches * args.steps), "allreduce_exposed_us": None if args.cuda_graph else exposed_us, "gradients_finite": ok, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if topo.world > 1:
@@ -335,6 +337,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--fused-blocks", action="store_true",
+                    help="cfg3: 72-channel record activations + ops.deform_conv2d_block (chunk / cat / sigmoid, layout and padding passes folded away, forward and backward)")
     ap.add_argument("--cuda-graph", action="store_true", help="cfg3: capture the whole step in a CUDA graph and replay it (SURVEY H7)")
     ap.add_argument("--no-overlap", action="store_true", help="cfg3: one all-reduce after backward instead of the overlapped group exchange")
     args = ap.parse_args()

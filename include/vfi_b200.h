@@ -203,6 +203,23 @@ int vfi_dcn_bwd_data_cols(const void* gcol, int32_t gcol_dtype, int64_t gcol_ld,
                           const vfi_tensor* mask, float* grad_x_rows, int64_t grad_x_ld, const vfi_tensor* grad_offset,
                           const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
 
+/* Backward of vfi_dcn_fwd_fused (the training companion of the hot-path form; round 2).  The glue of ema_vfi.py:57-59 stays
+ * folded in: offsets and the mask come from the raw 27-channel offset_conv output conv27 (16-bit; sigmoid computed in the
+ * kernel exactly as the forward does), and the data gradient goes back to THAT tensor.
+ *  - vfi_dcn_bwd_weight_tc_fused: vfi_dcn_bwd_weight_tc with (offset, mask) replaced by conv27 (NCHW with 16-byte aligned rows,
+ *    or dense channels-last [B,H,W,27]); same workspace, same limits, same accumulation into grad_weight / grad_bias.
+ *  - vfi_dcn_bwd_data_cols_fused: vfi_dcn_bwd_data_cols for bf16 columns with x given as planes, read where they lie (x_main
+ *    [B,64,H,W] + x_tail [B,<=4,H,W], bf16 channels-last views with dense rows and a pixel stride that is a multiple of 16
+ *    bytes: two dense plane buffers or the channel ranges 0..63 / 64.. of one [B,H,W,72] record buffer -- no packing pass, no
+ *    workspace); grad_conv27: f32 [B,27,H,W], any strides, receives d loss / d conv27 (channels 0..8 and 18..26: the offset
+ *    gradient in the reference's cat(o1, o2) order; channels 9..17: grad_mask * m * (1 - m)).  grad_x_rows as in
+ *    vfi_dcn_bwd_data_cols.  Either output may be NULL. */
+int vfi_dcn_bwd_weight_tc_fused(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* conv27, int64_t O,
+                                float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes, vfi_stream_t stream);
+int vfi_dcn_bwd_data_cols_fused(const void* gcol, int64_t gcol_ld, const vfi_tensor* x_main, const vfi_tensor* x_tail,
+                                const vfi_tensor* conv27, float* grad_x_rows, int64_t grad_x_ld, const vfi_tensor* grad_conv27,
+                                vfi_stream_t stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 /* D[128,80] (f32, row-major) = A[128,K] * B[80,K]^T with A, B row-major bf16 in device memory, K % 64 == 0.  One CTA,
  * serialised; exercises exactly the shared-memory descriptors, swizzle, tcgen05.mma/commit/ld and TMEM allocation the

@@ -871,6 +871,77 @@ def test_fusion_block_training_step_matches_stock_torchvision():
         assert maxabs(p.grad, ref[k]) <= tol(ref[k], 3e-5), k
 
 
+@pytest.mark.parametrize("c27_layout", ["nchw", "channels_last"])
+def test_fused_training_block_on_records_matches_the_unfused_ops(c27_layout):
+    """ops.deform_conv2d_block (record activations in / out, raw 27-channel offset_conv output in, glue folded into the kernels
+    forward AND backward) against the same block built from the reference's glue as stock ops (chunk / cat / sigmoid, ema_vfi.py:
+    57-59) around vfi_b200.deform_conv2d with the same bf16 tensor-core math, and against the fp32 oracle for the forward."""
+    from vfi_b200 import ops
+
+    g = torch.Generator().manual_seed(91)
+    B, H, W, C = 2, 32, 48, 67
+    x = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16)
+    c27 = torch.randn(B, 27, H, W, generator=g)
+    c27[:, :9] *= 1.5
+    c27[:, 18:] *= 1.5
+    c27 = c27.to(torch.bfloat16)
+    w = ((torch.rand(C, C, 3, 3, generator=g) * 2 - 1) / 603 ** 0.5)
+    b = ((torch.rand(C, generator=g) * 2 - 1) / 603 ** 0.5)
+    gy = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16)
+
+    # ---- unfused reference: stock glue + the drop-in op
+    xr = x.to(DEV).requires_grad_(True)
+    cr = c27.to(DEV).requires_grad_(True)
+    wr, br = w.to(DEV).to(torch.bfloat16).requires_grad_(True), b.to(DEV).to(torch.bfloat16).requires_grad_(True)
+    o1, m, o2 = cr.chunk(3, dim=1)
+    yr = vfi_b200.deform_conv2d(xr, torch.cat((o1, o2), 1), wr, br, stride=1, padding=1, dilation=1, mask=torch.sigmoid(m), math="bf16_tc")
+    yr.backward(gy.to(DEV))
+
+    # ---- fused block on records (fp32 master parameters passed as they are)
+    x72 = ops.records_buffer(B, H, W, DEV, zero=True)
+    x72[:, :C] = x.to(DEV)
+    x72[:, 68:71] = x[:, 64:67].to(DEV)
+    x72.requires_grad_(True)
+    cf = c27.to(DEV)
+    if c27_layout == "channels_last":
+        cf = cf.contiguous(memory_format=torch.channels_last)
+    cf.requires_grad_(True)
+    wf, bf = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    y72 = ops.deform_conv2d_block(x72, cf, wf, bf)
+    assert ops._is_records(y72)
+    g72 = torch.zeros_like(y72)
+    g72[:, :C] = gy.to(DEV)
+    g72[:, 67:] = 3.0                                            # whatever reaches the derived channels must not matter
+    y72.backward(g72)
+
+    off, msk = oracle.pack_split(c27.float().numpy())
+    ref = oracle.dcn_fwd(x.float().numpy(), off, bf16_round(msk), bf16_round(w.numpy()), b.numpy())
+    assert relerr(y72[:, :C], ref) <= 1e-2
+    assert relerr(y72[:, :C], yr) <= 1e-2
+    assert float(y72[:, 67].abs().max()) == 0.0 and torch.equal(y72[:, 68:72], y72[:, 64:68])     # a valid record again
+    assert relerr(x72.grad[:, :C], xr.grad) <= 2e-2 and float(x72.grad[:, 67:].abs().max()) == 0.0
+    assert relerr(cf.grad, cr.grad) <= 2e-2
+    assert relerr(wf.grad, wr.grad) <= 2e-2 and relerr(bf.grad, br.grad) <= 2e-2
+    assert wf.grad.dtype == torch.float32
+
+
+def test_training_step_fused_blocks_match_the_unfused_step():
+    """TrainStep(fused=True) (record activations, ops.deform_conv2d_block, padded offset_conv) computes the gradients of the
+    unfused step: same parameters, same inputs, bf16 tolerance."""
+    from vfi_b200 import shard
+    from vfi_b200.trainstep import TrainStep
+
+    topo = shard.Topology(rank=0, world=1, local_rank=0)
+    a = TrainStep(topo, DEV, math="bf16_tc", global_batch=2, size=64, fused=False)
+    b = TrainStep(topo, DEV, math="bf16_tc", global_batch=2, size=64, fused=True)
+    assert b.fused
+    a.step()
+    b.step()
+    torch.cuda.synchronize()
+    assert relerr(b.bucket.flat, a.bucket.flat) <= 2e-2
+    assert relerr(b.flow.grad, a.flow.grad) <= 3e-2
+
+
 def test_training_step_cuda_graph_replay_matches_eager():
     """TrainStep.capture(): the whole cfg3 step (bucket zeroing, forward, backward into the flat gradient bucket) replayed as
     one CUDA graph gives the gradients of the eager step -- same kernels, same order; the only non-determinism is the order of

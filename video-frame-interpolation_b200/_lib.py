@@ -59,6 +59,8 @@ SIGNATURES = {
     "vfi_dcn_bwd_data_cols_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32]),
     "vfi_dcn_bwd_data_cols": (c_int, [c_void_p, c_int32, c_int64, _T, _T, _T, c_void_p, c_int64, _T, _T, c_void_p, c_size_t,
                               c_void_p]),
+    "vfi_dcn_bwd_weight_tc_fused": (c_int, [_T, _T, _T, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vfi_dcn_bwd_data_cols_fused": (c_int, [c_void_p, c_int64, _T, _T, _T, c_void_p, c_int64, _T, c_void_p]),
     "vfi_dcn_bwd_weight_tc": (c_int, [_T, _T, _T, _T, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vfi_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "vfi_selftest_umma_ts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

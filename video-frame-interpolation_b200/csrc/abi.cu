@@ -36,6 +36,11 @@ size_t dcn_tc_bwd_data_cols_workspace_bytes(long long B, long long H, long long 
 int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, const vfi_tensor* x, const vfi_tensor* offset,
                          const vfi_tensor* mask, float* gx_rows, long long gx_ld, const vfi_tensor* grad_offset,
                          const vfi_tensor* grad_mask, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int dcn_tc_bwd_weight_fused(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* conv27, long long O, float* gw, float* gb,
+                            void* workspace, size_t workspace_bytes, cudaStream_t st);
+int dcn_tc_bwd_data_cols_fused(const void* gcol, long long gcol_ld, const vfi_tensor* x_main, const vfi_tensor* x_tail,
+                               const vfi_tensor* conv27, float* gx_rows, long long gx_ld, const vfi_tensor* grad_conv27,
+                               cudaStream_t st);
 int umma_selftest(const void* A, const void* Bm, float* D, int K, cudaStream_t st);
 size_t dcn_tc_gcol_workspace_bytes();
 int dcn_tc_gcol(const vfi_tensor* grad_out, const void* weight, int weight_dtype, long long C, void* gcol, long long gcol_ld,
@@ -136,6 +141,18 @@ extern "C" int vfi_dcn_bwd_data_cols(const void* gcol, int32_t gcol_dtype, int64
                                      size_t workspace_bytes, vfi_stream_t stream) {
   return dcn_tc_bwd_data_cols(gcol, gcol_dtype, gcol_ld, x, offset, mask, grad_x_rows, grad_x_ld, grad_offset, grad_mask,
                               workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_bwd_weight_tc_fused(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* conv27, int64_t O,
+                                           float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes,
+                                           vfi_stream_t stream) {
+  return dcn_tc_bwd_weight_fused(grad_out, x, conv27, O, grad_weight, grad_bias, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int vfi_dcn_bwd_data_cols_fused(const void* gcol, int64_t gcol_ld, const vfi_tensor* x_main, const vfi_tensor* x_tail,
+                                           const vfi_tensor* conv27, float* grad_x_rows, int64_t grad_x_ld,
+                                           const vfi_tensor* grad_conv27, vfi_stream_t stream) {
+  return dcn_tc_bwd_data_cols_fused(gcol, gcol_ld, x_main, x_tail, conv27, grad_x_rows, grad_x_ld, grad_conv27, (cudaStream_t)stream);
 }
 
 extern "C" size_t vfi_dcn_gcol_workspace_bytes(void) { return dcn_tc_gcol_workspace_bytes(); }

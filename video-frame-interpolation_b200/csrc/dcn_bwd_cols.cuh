@@ -34,15 +34,23 @@ constexpr int BC_THREADS = BC_PT;             // 9 warps
 constexpr int BC_TAP_LD = 72;                 // gcol columns per tap: 64 main, 3 tail, 5 zero
 
 struct BcParams {
-  const uint8_t* x_main; const uint8_t* x_tail;            // planes [P][64] / [P][8] of TP (bf16 or f32; tail: channels 64.. first)
-  const void* offset; const void* mask;
+  const uint8_t* x_main; const uint8_t* x_tail;            // planes of TP (bf16 or f32): 64 main channels / the tail record (channels 64.. first)
+  long long main_px, tail_px;                              // bytes from one pixel to the next (dense planes: 64 / 8 elements; one
+                                                           // [B,H,W,72] record buffer: 144 bytes for both)
+  const void* offset; const void* mask;                    // FUSED27: both unused fields point at the 27-channel offset_conv output
   long long f_sn, f_sc, f_sh, f_sw, m_sn, m_sc, m_sh, m_sw;
   const void* gcol; long long gcol_ld;                     // [P][gcol_ld] of TP, column k * 72 + c
   float* gx; long long gx_ld;                              // [P][gx_ld] fp32 accumulator, channel c at column c (may be null)
   float* goff; long long gf_sn, gf_sc, gf_sh, gf_sw;       // [B,18,H,W] f32 (may be null)
   float* gmask; long long gm_sn, gm_sc, gm_sh, gm_sw;      // [B,9,H,W] f32 (may be null)
+  // FUSED27: goff is the gradient of the raw 27-channel tensor (channel map below), gmask unused
   int B, H, W;
 };
+
+// FUSED27 (the ModulatedDeformConvPack glue of ema_vfi.py:57-59 folded in, as in the forward kernels): channel of the raw
+// offset_conv output that holds offset channel j (j = 2k: dy, 2k + 1: dx of tap k) / the mask logit of tap k.
+__device__ __forceinline__ int bc_off_chan(int j) { return j < 9 ? j : j + 9; }
+__device__ __forceinline__ int bc_mask_chan(int k) { return 9 + k; }
 
 struct BcGeo {
   int pix00;                    // linear pixel index (b, y0, x0) of the upper-left corner; only dereferenced when its flag is set
@@ -78,9 +86,12 @@ __device__ __forceinline__ float dot4(const float (&g)[4], const float (&v)[4]) 
 }
 
 // TO: dtype of offset / mask; TP: dtype of gcol and of the x planes (bf16: the tensor-core training path; f32: the fp32 path).
-template <typename TO, typename TP>
+// FUSED27: offsets and mask logits come from the raw 27-channel offset_conv output (sigmoid folded in, rounded to TO as the
+// forward kernels do), and the gradient goes back to that tensor (d sigmoid folded in).
+template <typename TO, typename TP, bool FUSED27>
 __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) dcn_bwd_cols_kernel(const BcParams q) {
-  constexpr int ES = (int)sizeof(TP), MAIN_PX = 64 * ES, TAIL_PX = 8 * ES;
+  constexpr int ES = (int)sizeof(TP);
+  const long long MAIN_PX = q.main_px, TAIL_PX = q.tail_px;
   const uint8_t* gcol = reinterpret_cast<const uint8_t*>(q.gcol);
   __shared__ BcSmem s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,10 +109,18 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) dcn_bwd_cols_kernel
     if (pp < HW) {
       const int y = (int)(pp / q.W), x = (int)(pp % q.W);
       const TO* off = reinterpret_cast<const TO*>(q.offset) + b * q.f_sn + y * q.f_sh + x * q.f_sw;
-      const TO* msk = reinterpret_cast<const TO*>(q.mask) + b * q.m_sn + y * q.m_sh + x * q.m_sw;
-      const float dy = to_f32<TO>(__ldg(off + (2 * k) * q.f_sc));
-      const float dx = to_f32<TO>(__ldg(off + (2 * k + 1) * q.f_sc));
-      g.mk = to_f32<TO>(__ldg(msk + k * q.m_sc));
+      float dy, dx;
+      if (FUSED27) {
+        dy = to_f32<TO>(__ldg(off + bc_off_chan(2 * k) * q.f_sc));
+        dx = to_f32<TO>(__ldg(off + bc_off_chan(2 * k + 1) * q.f_sc));
+        const float logit = to_f32<TO>(__ldg(off + bc_mask_chan(k) * q.f_sc));
+        g.mk = to_f32<TO>(from_f32<TO>(__fdividef(1.0f, 1.0f + __expf(-logit))));   // the forward kernels' sigmoid, rounded to TO
+      } else {
+        const TO* msk = reinterpret_cast<const TO*>(q.mask) + b * q.m_sn + y * q.m_sh + x * q.m_sw;
+        dy = to_f32<TO>(__ldg(off + (2 * k) * q.f_sc));
+        dx = to_f32<TO>(__ldg(off + (2 * k + 1) * q.f_sc));
+        g.mk = to_f32<TO>(__ldg(msk + k * q.m_sc));
+      }
       float py = __fadd_rn((float)(y - 1 + k / 3), dy);
       float px = __fadd_rn((float)(x - 1 + k % 3), dx);
       const bool live = (py > -1.0f) && (py < (float)q.H) && (px > -1.0f) && (px < (float)q.W);
@@ -219,11 +238,21 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MIN_BLOCKS) dcn_bwd_cols_kernel
     const long long pp = p0 + lane;
     if (pp < HW) {
       const int y = (int)(pp / q.W), x = (int)(pp % q.W);
-      if (q.gmask) q.gmask[b * q.gm_sn + k * q.gm_sc + y * q.gm_sh + x * q.gm_sw] = s.part[0][tid];
-      if (q.goff) {
-        float* go = q.goff + b * q.gf_sn + y * q.gf_sh + x * q.gf_sw;
-        go[(2 * k) * q.gf_sc] = s.part[1][tid];
-        go[(2 * k + 1) * q.gf_sc] = s.part[2][tid];
+      if (FUSED27) {
+        if (q.goff) {
+          float* go = q.goff + b * q.gf_sn + y * q.gf_sh + x * q.gf_sw;
+          const float mk = s.geo[tid].mk;
+          go[bc_off_chan(2 * k) * q.gf_sc] = s.part[1][tid];
+          go[bc_off_chan(2 * k + 1) * q.gf_sc] = s.part[2][tid];
+          go[bc_mask_chan(k) * q.gf_sc] = s.part[0][tid] * mk * (1.0f - mk);        // d sigmoid
+        }
+      } else {
+        if (q.gmask) q.gmask[b * q.gm_sn + k * q.gm_sc + y * q.gm_sh + x * q.gm_sw] = s.part[0][tid];
+        if (q.goff) {
+          float* go = q.goff + b * q.gf_sn + y * q.gf_sh + x * q.gf_sw;
+          go[(2 * k) * q.gf_sc] = s.part[1][tid];
+          go[(2 * k + 1) * q.gf_sc] = s.part[2][tid];
+        }
       }
     }
   }

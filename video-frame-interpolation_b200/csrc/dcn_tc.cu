@@ -777,6 +777,78 @@ int dcn_tc_bwd_weight(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi
   return VFI_OK;
 }
 
+// The same with offsets / mask taken from the raw 27-channel offset_conv output (the backward of vfi_dcn_fwd_fused).
+int dcn_tc_bwd_weight_fused(const vfi_tensor* grad_out, const vfi_tensor* x, const vfi_tensor* conv27, long long O, float* gw, float* gb,
+                            void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const char* who = "vfi_dcn_bwd_weight_tc_fused";
+  VFI_REQUIRE(grad_out && x && conv27, VFI_ERR_INVALID, "%s: null tensor descriptor", who);
+  const long long C = x->c;
+  VFI_REQUIRE(C > 0 && C <= TC_CMAIN + 4 && O > 0 && O <= TC_M, VFI_ERR_UNSUPPORTED, "%s: supports C <= %d, O <= %d", who,
+              TC_CMAIN + 4, TC_M);
+  VFI_REQUIRE(conv27->n == x->n && conv27->c == 27 && conv27->h == x->h && conv27->w == x->w && grad_out->n == x->n && grad_out->c == O &&
+                  grad_out->h == x->h && grad_out->w == x->w, VFI_ERR_INVALID, "%s: shape mismatch", who);
+  const long long P = (long long)x->n * x->h * x->w;
+  if (P == 0 || (!gw && !gb)) return VFI_OK;
+  auto bulk_ok = [](const vfi_tensor* t, int es) {
+    const int a = 16 / es;
+    return t->sw == 1 && t->w % a == 0 && t->sh % a == 0 && t->sc % a == 0 && t->sn % a == 0 && aligned(t->data, 16) && t->sh >= 0 &&
+           t->sc >= 0 && t->sn >= 0;
+  };
+  // the staged-box geometry role streams the raw values with bulk copies: NCHW rows, or dense channels-last pixels ([P][27])
+  const bool geo_cl = conv27->sc == 1 && conv27->sw == 27 && conv27->sh == conv27->w * 27 && conv27->sn == conv27->h * conv27->sh &&
+                      aligned(conv27->data, 16) && (conv27->w * 27) % 8 == 0;
+  VFI_REQUIRE((conv27->dtype == VFI_BF16 || conv27->dtype == VFI_F16) && (geo_cl || bulk_ok(conv27, 2)), VFI_ERR_UNSUPPORTED,
+              "%s: conv27 must be a 16-bit tensor, NCHW with 16-byte aligned rows (W %% 8 == 0) or dense channels-last", who);
+  VFI_REQUIRE(grad_out->dtype == VFI_BF16 || grad_out->dtype == VFI_F32, VFI_ERR_UNSUPPORTED, "%s: grad_out must be bf16 or f32",
+              who);
+  VFI_REQUIRE(x->w % 8 == 0, VFI_ERR_UNSUPPORTED, "%s: W must be a multiple of 8", who);
+  VFI_REQUIRE(P < 2147483647LL / 2, VFI_ERR_UNSUPPORTED, "%s: more than 2^30 pixels per call", who);
+  const size_t need = dcn_tc_workspace_bytes(x->n, x->h, x->w);
+  VFI_REQUIRE(workspace && workspace_bytes >= need && aligned(workspace, 256), VFI_ERR_WORKSPACE,
+              "%s: workspace of %zu bytes (256-byte aligned) required, got %zu", who, need, workspace_bytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = dcn_tc_pack_input(x, ws + ws_main_off(), ws + ws_tail_off(P), st);
+  if (rc) return rc;
+  WgParams q;
+  TcParams& p = q.t;
+  p.x_main = ws + ws_main_off(); p.x_tail = ws + ws_tail_off(P);
+  p.main_stride = TC_CMAIN * 2; p.tail_stride = TC_CTAIL * 2;
+  p.offset = conv27->data; p.mask = conv27->data; p.fused27 = 1; p.geo_cl = geo_cl ? 1 : 0;
+  p.f_sn = conv27->sn; p.f_sc = conv27->sc; p.f_sh = conv27->sh; p.f_sw = conv27->sw;
+  p.m_sn = conv27->sn; p.m_sc = conv27->sc; p.m_sh = conv27->sh; p.m_sw = conv27->sw;
+  p.wpacked = nullptr; p.bias = nullptr; p.out = nullptr; p.out_tail = nullptr;
+  p.o_sn = p.o_sc = p.o_sh = p.o_sw = 0; p.out_rows = 0;
+  p.B = (int)x->n; p.H = (int)x->h; p.W = (int)x->w; p.O = (int)O;
+  p.tiles_x = ceil_div(x->w, TC_TW); p.tiles_y = ceil_div(x->h, TC_TH);
+  p.num_tiles = p.B * p.tiles_x * p.tiles_y;
+  p.experiment = 0; p.debug = nullptr;
+  q.gout = grad_out->data; q.g_sn = grad_out->sn; q.g_sc = grad_out->sc; q.g_sh = grad_out->sh; q.g_sw = grad_out->sw;
+  q.g_vec = (grad_out->dtype == VFI_BF16 && bulk_ok(grad_out, 2)) ? 1 : 0;
+  q.gw = gw; q.gb = gb; q.C = (int)C;
+  int dev = 0, sms = 148;
+  VFI_CUDA(cudaGetDevice(&dev));
+  VFI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  const size_t smem = sizeof(WgSmem) + 1024;
+  for (int pass = 0; pass < 2; ++pass) {
+    q.pass = pass;
+#define VFI_WG_LAUNCH(TO, TG)                                                                         \
+  do {                                                                                                \
+    auto kern = dcn_tc6_wgrad_kernel<TO, TG, true>;                                                   \
+    VFI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, V6_THREADS, smem, st>>>(q);                                                          \
+  } while (0)
+    if (conv27->dtype == VFI_BF16) {
+      if (grad_out->dtype == VFI_BF16) VFI_WG_LAUNCH(__nv_bfloat16, __nv_bfloat16); else VFI_WG_LAUNCH(__nv_bfloat16, float);
+    } else {
+      if (grad_out->dtype == VFI_BF16) VFI_WG_LAUNCH(__half, __nv_bfloat16); else VFI_WG_LAUNCH(__half, float);
+    }
+#undef VFI_WG_LAUNCH
+    VFI_LAUNCH_CHECK("dcn_tc6_wgrad_kernel<fused27>");
+  }
+  return VFI_OK;
+}
+
 // grad_x / grad_offset / grad_mask from the column gradient gcol = grad_out x W (see dcn_bwd_cols.cuh).
 static size_t cols_tail_off(long long P, size_t es) { return (((size_t)P * TC_CMAIN * es + 255) / 256) * 256; }
 size_t dcn_tc_bwd_data_cols_workspace_bytes(long long B, long long H, long long W, int gcol_dtype) {
@@ -876,6 +948,7 @@ int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, co
   }
   BcParams q{};
   q.x_main = main_plane; q.x_tail = tail_plane;
+  q.main_px = (long long)(TC_CMAIN * es); q.tail_px = (long long)(TC_CTAIL * es);
   q.offset = offset->data; q.mask = mask->data;
   q.f_sn = offset->sn; q.f_sc = offset->sc; q.f_sh = offset->sh; q.f_sw = offset->sw;
   q.m_sn = mask->sn; q.m_sc = mask->sc; q.m_sh = mask->sh; q.m_sw = mask->sw;
@@ -886,11 +959,57 @@ int dcn_tc_bwd_data_cols(const void* gcol, int gcol_dtype, long long gcol_ld, co
   q.B = (int)x->n; q.H = (int)x->h; q.W = (int)x->w;
   dim3 grid(ceil_div((long long)x->h * x->w, BC_PIX), (unsigned)x->n);
   if (gcol_dtype == VFI_F32) {
-    VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO, float><<<grid, BC_THREADS, 0, st>>>(q); });
+    VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO, float, false><<<grid, BC_THREADS, 0, st>>>(q); });
   } else {
-    VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO, __nv_bfloat16><<<grid, BC_THREADS, 0, st>>>(q); });
+    VFI_DISPATCH(offset->dtype, TO, { dcn_bwd_cols_kernel<TO, __nv_bfloat16, false><<<grid, BC_THREADS, 0, st>>>(q); });
   }
   VFI_LAUNCH_CHECK("dcn_bwd_cols_kernel");
+  return VFI_OK;
+}
+
+// A plane pair as the fused entry points take it: bf16 channels-last views [B,64,H,W] / [B,<=8,H,W] with dense rows and images
+// (sh = W * sw, sn = H * sh) and a pixel stride that is a multiple of 16 bytes -- two dense buffers or the channel ranges
+// 0..63 / 64..71 of ONE [B,H,W,72] record buffer.
+static bool is_plane_view(const vfi_tensor* t, long long c_max, long long B, long long H, long long W) {
+  return t && t->data && t->dtype == VFI_BF16 && t->n == B && t->h == H && t->w == W && t->c > 0 && t->c <= c_max && t->sc == 1 &&
+         t->sw >= c_max && t->sw % 8 == 0 && t->sh == W * t->sw && (B == 1 || t->sn == H * t->sh) && aligned(t->data, 16);
+}
+
+// The fused training form of the data gradients (the backward of vfi_dcn_fwd_fused): x as planes, read where they lie;
+// offsets / mask from the raw 27-channel offset_conv output; the gradient goes back to that tensor.
+int dcn_tc_bwd_data_cols_fused(const void* gcol, long long gcol_ld, const vfi_tensor* x_main, const vfi_tensor* x_tail,
+                               const vfi_tensor* conv27, float* gx_rows, long long gx_ld, const vfi_tensor* grad_conv27,
+                               cudaStream_t st) {
+  const char* who = "vfi_dcn_bwd_data_cols_fused";
+  VFI_REQUIRE(gcol && x_main && x_tail && conv27, VFI_ERR_INVALID, "%s: null pointer", who);
+  const long long B = x_main->n, H = x_main->h, W = x_main->w;
+  VFI_REQUIRE(is_plane_view(x_main, TC_CMAIN, B, H, W) && x_main->c == TC_CMAIN && is_plane_view(x_tail, TC_CTAIL, B, H, W) &&
+                  x_tail->c <= 4, VFI_ERR_UNSUPPORTED,
+              "%s: x must be bf16 planes (main [B,64,H,W] + tail [B,<=4,H,W] channels-last views, 16-byte aligned pixels)", who);
+  VFI_REQUIRE(conv27->data && conv27->n == B && conv27->c == 27 && conv27->h == H && conv27->w == W &&
+                  (conv27->dtype == VFI_BF16 || conv27->dtype == VFI_F16), VFI_ERR_INVALID, "%s: conv27 must be a 16-bit [B,27,H,W] tensor", who);
+  VFI_REQUIRE(gcol_ld >= 9 * BC_TAP_LD && gcol_ld % 4 == 0 && aligned(gcol, 16), VFI_ERR_INVALID,
+              "%s: gcol rows must hold 9 x %d columns, row length a multiple of 4, 16-byte aligned", who, BC_TAP_LD);
+  if (gx_rows) VFI_REQUIRE(gx_ld >= TC_CMAIN + 4 && gx_ld % 4 == 0 && aligned(gx_rows, 16), VFI_ERR_INVALID,
+                           "%s: grad_x rows must hold >= %d floats, 16-byte aligned", who, TC_CMAIN + 4);
+  if (grad_conv27) VFI_REQUIRE(grad_conv27->data && grad_conv27->dtype == VFI_F32 && same_shape(grad_conv27, conv27), VFI_ERR_INVALID,
+                               "%s: grad_conv27 must be f32 [B,27,H,W]", who);
+  const long long P = B * H * W;
+  if (P == 0 || (!gx_rows && !grad_conv27)) return VFI_OK;
+  VFI_REQUIRE(P < 2147483647LL / 2 && B <= 65535, VFI_ERR_UNSUPPORTED, "%s: more than 2^30 pixels or 65535 images per call", who);
+  BcParams q{};
+  q.x_main = reinterpret_cast<const uint8_t*>(x_main->data); q.x_tail = reinterpret_cast<const uint8_t*>(x_tail->data);
+  q.main_px = x_main->sw * 2; q.tail_px = x_tail->sw * 2;
+  q.offset = conv27->data; q.mask = conv27->data;
+  q.f_sn = conv27->sn; q.f_sc = conv27->sc; q.f_sh = conv27->sh; q.f_sw = conv27->sw;
+  q.gcol = gcol; q.gcol_ld = gcol_ld;
+  q.gx = gx_rows; q.gx_ld = gx_ld;
+  if (grad_conv27) { q.goff = (float*)grad_conv27->data; q.gf_sn = grad_conv27->sn; q.gf_sc = grad_conv27->sc; q.gf_sh = grad_conv27->sh; q.gf_sw = grad_conv27->sw; }
+  q.B = (int)B; q.H = (int)H; q.W = (int)W;
+  dim3 grid(ceil_div(H * W, BC_PIX), (unsigned)B);
+  if (conv27->dtype == VFI_BF16) dcn_bwd_cols_kernel<__nv_bfloat16, __nv_bfloat16, true><<<grid, BC_THREADS, 0, st>>>(q);
+  else dcn_bwd_cols_kernel<__half, __nv_bfloat16, true><<<grid, BC_THREADS, 0, st>>>(q);
+  VFI_LAUNCH_CHECK("dcn_bwd_cols_kernel<fused27>");
   return VFI_OK;
 }
 

@@ -459,6 +459,112 @@ def deform_conv2d_fused(x_main: torch.Tensor, x_tail: Optional[torch.Tensor], co
     return out
 
 
+# ------------------------------------------------------------------------------------------------------ fused training block
+def records_buffer(B: int, H: int, W: int, device, zero: bool = False) -> torch.Tensor:
+    """A 72-channel *record* activation: a [B,72,H,W] bf16 tensor whose memory is dense channels-last ([B,H,W,72], 144 bytes
+    per pixel).  Channels 0..66 are data, 67 is zero and 68..71 mirror 64..67 (the tail record of :class:`Planes`).  Stock
+    cuDNN convolutions take it as it lies (zero weights for channels 67..71); the DCN kernels read and write it in place."""
+    alloc = torch.zeros if zero else torch.empty
+    return alloc((B, H, W, MAIN_C + TAIL_C), dtype=torch.bfloat16, device=device).permute(0, 3, 1, 2)
+
+
+def _is_records(t: torch.Tensor) -> bool:
+    return (t.dim() == 4 and t.shape[1] == MAIN_C + TAIL_C and t.dtype == torch.bfloat16 and t.is_cuda
+            and t.permute(0, 2, 3, 1).is_contiguous())
+
+
+class _DcnBlockFn(torch.autograd.Function):
+    """y72 = DCNv2(x72[:, :67]; split / sigmoid of conv27) as records -- forward ``vfi_dcn_fwd_fused``, backward
+    ``vfi_dcn_gcol`` + ``vfi_dcn_bwd_data_cols_fused`` + ``vfi_dcn_bwd_weight_tc_fused``."""
+
+    @staticmethod
+    def forward(ctx, x72, conv27, weight, bias):
+        dev = require_cuda(x72, conv27, weight, bias)
+        B, _, H, W = x72.shape
+        O, C = weight.shape[:2]
+        src = Planes.from_buffer72(x72.permute(0, 2, 3, 1), channels=C)
+        out72 = records_buffer(B, H, W, dev)
+        out = Planes.from_buffer72(out72.permute(0, 2, 3, 1), channels=O)
+        weight = weight.contiguous()
+        deform_conv2d_fused(src.main_nchw, src.tail_nchw(), conv27, weight, bias, math="bf16_tc", out=out)
+        ctx.save_for_backward(x72, conv27, weight)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return out72
+
+    @staticmethod
+    def backward(ctx, grad_y72):
+        x72, conv27, weight = ctx.saved_tensors
+        dev = x72.device
+        need_x, need_c27, need_w, need_b = ctx.needs_input_grad
+        need_b = need_b and ctx.has_bias
+        B, _, H, W = x72.shape
+        O, C = weight.shape[:2]
+        lib = _lib.load()
+        f32 = dict(dtype=torch.float32, device=dev)
+        # channels 67..71 of a record are derived (zero pad + mirror): what reaches them from downstream is not a gradient of
+        # anything (stock convolutions carry zero weights there, the next block returns zeros) -- only [:, :O] counts
+        g_out = grad_y72[:, :O]
+        if g_out.dtype != torch.bfloat16:
+            g_out = g_out.to(torch.bfloat16)
+        src = Planes.from_buffer72(x72.permute(0, 2, 3, 1), channels=C)
+        gx72 = g27 = gw = gb = None
+        hw = H * W
+        with torch.cuda.device(dev):
+            if need_x or need_c27:
+                gx_rows = torch.zeros((B * hw, _GX_LD), **f32) if need_x else None
+                g27 = torch.empty(conv27.shape, **f32).contiguous(memory_format=torch.channels_last) if need_c27 else None
+                step = max(1, _COLS_CHUNK_BYTES // max(1, hw * _COLS_LD * 2))
+                wsg = _workspace(dev, int(lib.vfi_dcn_gcol_workspace_bytes()))
+                for b0 in range(0, B, step):
+                    b1 = min(B, b0 + step)
+                    n = (b1 - b0) * hw
+                    gcol = torch.empty((n, _COLS_LD), dtype=torch.bfloat16, device=dev)
+                    check(lib.vfi_dcn_gcol(ref(desc(g_out[b0:b1])), weight.data_ptr(), dtype_code(weight.dtype), C, gcol.data_ptr(),
+                                           _COLS_LD, wsg.data_ptr(), wsg.numel(), stream_handle(dev)), "vfi_dcn_gcol")
+                    check(lib.vfi_dcn_bwd_data_cols_fused(gcol.data_ptr(), _COLS_LD, ref(desc(src.main_nchw[b0:b1])),
+                                                          ref(desc(src.tail_nchw()[b0:b1])), ref(desc(conv27[b0:b1])),
+                                                          gx_rows[b0 * hw:].data_ptr() if need_x else None, _GX_LD,
+                                                          ref(desc(g27[b0:b1])) if need_c27 else None, stream_handle(dev)),
+                          "vfi_dcn_bwd_data_cols_fused")
+                if need_x:
+                    gx72 = records_buffer(B, H, W, dev, zero=True)
+                    gx72[:, :C] = gx_rows.view(B, H, W, _GX_LD)[..., :C].permute(0, 3, 1, 2)      # one cast pass; 67.. stay zero
+                if need_c27:
+                    g27 = g27.to(conv27.dtype)
+            if need_w or need_b:
+                gw = torch.zeros(weight.shape, **f32) if need_w else None
+                gb = torch.zeros((O,), **f32) if need_b else None
+                ws = _workspace(dev, int(lib.vfi_dcn_workspace_bytes(B, C, O, H, W, _lib.MATH_BF16_TC)))
+                # the kernel's grad_out^T loaders want unit pixel stride (see _DcnFn.backward): one 134 B/px copy
+                g_w = g_out.contiguous()
+                check(lib.vfi_dcn_bwd_weight_tc_fused(ref(desc(g_w)), ref(desc(src.nchw_view())), ref(desc(conv27)), O,
+                                                      gw.data_ptr() if need_w else None, gb.data_ptr() if need_b else None,
+                                                      ws.data_ptr(), ws.numel(), stream_handle(dev)), "vfi_dcn_bwd_weight_tc_fused")
+                if need_w:
+                    gw = gw.to(weight.dtype)                 # fp32 master weights may be passed as they are: no rounding then
+                if need_b:
+                    gb = gb.to(ctx.bias_dtype)
+        return gx72, g27, gw, gb
+
+
+def deform_conv2d_block(x72: torch.Tensor, conv27: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The fusion block's DCNv2 (ema_vfi.py:57-60) with its glue folded in, forward AND backward, on 72-channel record
+    activations (:func:`records_buffer`): ``x72`` in, the raw 27-channel ``offset_conv`` output in (16-bit, NCHW or
+    channels_last; chunk / cat / sigmoid happen in the kernels, and the gradient returns to this tensor), records out.
+    bf16 tensor-core math; ``weight`` [O,C,3,3] with 64 < C, O <= 68, W % 8 == 0.  Differentiable in all four arguments."""
+    if not _is_records(x72):
+        raise ValueError("deform_conv2d_block: x72 must be a bf16 [B,72,H,W] record tensor (ops.records_buffer)")
+    if conv27.dim() != 4 or conv27.shape[1] != 27 or conv27.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("deform_conv2d_block: conv27 must be a 16-bit [B,27,H,W] tensor")
+    O, C = weight.shape[:2]
+    if not (MAIN_C < C <= MAIN_C + 4 and MAIN_C < O <= MAIN_C + 4) or tuple(weight.shape[2:]) != (3, 3):
+        raise NotImplementedError("deform_conv2d_block implements 64 < C, O <= 68 and 3x3 kernels")
+    if x72.shape[3] % 8:
+        raise NotImplementedError("deform_conv2d_block needs W % 8 == 0")
+    return _DcnBlockFn.apply(x72, conv27, weight, bias)
+
+
 def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 

@@ -39,6 +39,17 @@ class FusionBlockParams(torch.nn.Module):
         return self.dcn(x, torch.cat((o1, o2), 1), self.weight.to(dt), self.bias.to(dt), stride=1, padding=1, dilation=1,
                         mask=torch.sigmoid(m))
 
+    def forward_records(self, x72):
+        """The same block on 72-channel record activations (ops.records_buffer) with the glue folded into the kernels, forward
+        and backward (ops.deform_conv2d_block): the stock offset_conv runs on the record buffer as it lies (zero weights for
+        the pad / mirror channels 67..71, so cuDNN neither pads nor converts layouts), its raw 27-channel output goes straight
+        to the DCN kernels, and the fp32 master parameters of the DCN are passed as they are."""
+        w = self.offset_conv.weight
+        w72 = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, x72.shape[1] - w.shape[1])).to(torch.bfloat16)
+        w72 = w72.contiguous(memory_format=torch.channels_last)
+        c27 = torch.nn.functional.conv2d(x72, w72, self.offset_conv.bias.to(torch.bfloat16), padding=1)
+        return ops.deform_conv2d_block(x72, c27, self.weight, self.bias)
+
 
 def stock_warp(frame, flow):
     """ema_vfi.py:149-171 with stock ops on the device (the --stock arm)."""
@@ -51,7 +62,7 @@ def stock_warp(frame, flow):
 
 class TrainStep:
     def __init__(self, topo: shard.Topology, device, *, math: str = "bf16_tc", stock: bool = False, global_batch: int = 16,
-                 size: int = 256, overlap: bool = True, seed: int = 7):
+                 size: int = 256, overlap: bool = True, seed: int = 7, fused: bool = False):
         self.topo, self.dev = topo, torch.device(device)
         if global_batch % topo.world:
             raise ValueError(f"global batch {global_batch} does not divide over {topo.world} ranks")
@@ -65,6 +76,8 @@ class TrainStep:
         else:
             dcn, self.warp = functools.partial(ops.deform_conv2d, math=math), ops.warp
         self.dtype = torch.bfloat16 if (math == "bf16_tc" and not stock) else torch.float32
+        # fused: record activations + ops.deform_conv2d_block (tensor-core math only)
+        self.fused = fused and not stock and math == "bf16_tc"
         self.blocks = torch.nn.ModuleList([FusionBlockParams(dcn) for _ in range(3)]).to(self.dev)
         groups = [list(b.parameters()) for b in reversed(self.blocks)]      # backward order: block 3's gradients are final first
         self.bucket = shard.GradBucket(self.blocks.parameters(), groups=groups)
@@ -78,6 +91,9 @@ class TrainStep:
         self.frame2 = torch.randn(B, 3, H, W, device=self.dev, generator=g).to(dt)
         self.feat = torch.randn(B, 64, H, W, device=self.dev, generator=g).to(dt)
         self.flow = (2.0 * torch.randn(B, 2, H, W, device=self.dev, generator=g)).to(dt).requires_grad_(True)
+        if self.fused:
+            self.feat = self.feat.contiguous(memory_format=torch.channels_last)
+            self._zero1 = torch.zeros(B, 1, H, W, device=self.dev, dtype=dt)
         self.exposed_ms = []
         self.graph = None
         self.graph_launches = 0
@@ -116,9 +132,19 @@ class TrainStep:
         self.flow.grad = None
         if self.overlap:
             self.bucket.begin_step()
-        x = torch.cat((self.feat, self.warp(self.frame2, self.flow)), 1)
-        for blk in self.blocks:
-            x = blk(x)
+        if self.fused:
+            # [feat | warped | 0 | warped | 0] = the record layout (channel 67 zero, 68..71 mirror 64..67); the mirror's gradient
+            # is zero by construction (deform_conv2d_block returns zeros for channels 67..71)
+            w = self.warp(self.frame2, self.flow)
+            z = self._zero1
+            x = torch.cat((self.feat, w, z, w, z), 1).contiguous(memory_format=torch.channels_last)
+            for blk in self.blocks:
+                x = blk.forward_records(x)
+            x = x[:, :67]
+        else:
+            x = torch.cat((self.feat, self.warp(self.frame2, self.flow)), 1)
+            for blk in self.blocks:
+                x = blk(x)
         # mean over the GLOBAL batch: every rank contributes sum over its shard / (global count), summed by the all-reduce
         (x.float().square().sum() / (x.numel() * self.topo.world)).backward()
         if self.overlap:
