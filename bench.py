@@ -319,6 +319,14 @@ def run_cfg3(args, desc):
                 "gpu_launches": int(launches) if not args.cuda_graph else int(ts.graph_launches * args.steps), "allreduce_exposed_us": None if args.cuda_graph else exposed_us, "gradients_finite": ok, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if topo.world > 1:
+        if args.cuda_graph:
+            # Tearing the process group down while a captured graph still references its NCCL kernels hung for the full
+            # timeout on an 8-GPU box (profiles/r02_w_*: the line above had been printed).  Drop the graph, drain the device and
+            # leave without the collective teardown.
+            ts.graph = None
+            torch.cuda.synchronize(dev)
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
