@@ -583,7 +583,10 @@ def main():
                                   "achieved": 2 * P * WARP_BYTES_PER_PX_BF16 / (planar_ms["f32"] * 1e-3) / 1e9,
                                   "frac": 2 * P * WARP_BYTES_PER_PX_BF16 / (planar_ms["f32"] * 1e-3) / 1e9 / pk["hbm"]},
                           "in_step": {"kernel": "warp_fwd_rec (writes the DCN tail records in place of torch.cat)",
-                                      "ms_per_launch": warp_ms, "achieved": warp_gbs, "frac": warp_gbs / pk["hbm"]}},
+                                      "ms_per_launch": warp_ms, "achieved": warp_gbs, "frac": warp_gbs / pk["hbm"],
+                                      # the record form writes 16 bytes per pixel (3 channels + pad + mirrored half) where the planar
+                                      # form writes 6: 26 bytes actually cross HBM per pixel against the 16 algorithmic ones above
+                                      "dram_bytes_per_px": 26, "achieved_dram": warp_gbs * 26 / 16, "frac_dram": warp_gbs * 26 / 16 / pk["hbm"]}},
         "clocks": clocks,
     }
     if model_like.get("bf16") and model_like.get("f32"):
