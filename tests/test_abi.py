@@ -105,6 +105,42 @@ def test_abi_argument_validation_without_a_gpu():
     assert rc == 2 and b"supports C <=" in lib.vfi_last_error()
 
 
+def test_fused_training_entry_points_validate_without_a_gpu():
+    """vfi_dcn_bwd_data_cols_fused / vfi_dcn_bwd_weight_tc_fused (backward of vfi_dcn_fwd_fused) reject bad descriptors before any
+    CUDA call; the record helpers of the Python layer refuse tensors that are not records."""
+    import pytest
+
+    from vfi_b200 import ops
+
+    lib = _lib.load()
+    # one [1,8,16,72] bf16 record buffer at a fake address: main = channels 0..63, tail = 64.., pixel stride 72 elements
+    main = _lib.VfiTensor(256, 1, 0, 1, 64, 8, 16, 72 * 128, 1, 72 * 16, 72)
+    tail = _lib.VfiTensor(256 + 128, 1, 0, 1, 3, 8, 16, 72 * 128, 1, 72 * 16, 72)
+    c27 = _lib.VfiTensor(256, 1, 0, 1, 27, 8, 16, 27 * 128, 128, 16, 1)
+    rc = lib.vfi_dcn_bwd_data_cols_fused(256, 640, ctypes.byref(main), ctypes.byref(tail), ctypes.byref(c27), None, 68, None, None)
+    assert rc == 1 and b"gcol rows must hold 9 x 72" in lib.vfi_last_error()
+    nchw_main = _lib.VfiTensor(256, 1, 0, 1, 64, 8, 16, 64 * 128, 128, 16, 1)                    # planar: not a plane view
+    rc = lib.vfi_dcn_bwd_data_cols_fused(256, 648, ctypes.byref(nchw_main), ctypes.byref(tail), ctypes.byref(c27), None, 68, None, None)
+    assert rc == 2 and b"x must be bf16 planes" in lib.vfi_last_error()
+    c26 = _lib.VfiTensor(256, 1, 0, 1, 26, 8, 16, 26 * 128, 128, 16, 1)
+    rc = lib.vfi_dcn_bwd_data_cols_fused(256, 648, ctypes.byref(main), ctypes.byref(tail), ctypes.byref(c26), None, 68, None, None)
+    assert rc == 1 and b"conv27 must be a 16-bit [B,27,H,W]" in lib.vfi_last_error()
+    assert lib.vfi_dcn_bwd_data_cols_fused(256, 648, ctypes.byref(main), ctypes.byref(tail), ctypes.byref(c27), None, 68, None, None) == 0  # nothing asked for
+    x67 = _lib.VfiTensor(256, 1, 0, 1, 67, 8, 16, 72 * 128, 1, 72 * 16, 72)
+    g67 = _lib.VfiTensor(256, 1, 0, 1, 67, 8, 16, 67 * 128, 128, 16, 1)
+    c27f = _lib.VfiTensor(256, 0, 0, 1, 27, 8, 16, 27 * 128, 128, 16, 1)                          # f32 conv27
+    rc = lib.vfi_dcn_bwd_weight_tc_fused(ctypes.byref(g67), ctypes.byref(x67), ctypes.byref(c27f), 67, 256, None, None, 0, None)
+    assert rc == 2 and b"conv27 must be a 16-bit tensor" in lib.vfi_last_error()
+    rc = lib.vfi_dcn_bwd_weight_tc_fused(ctypes.byref(g67), ctypes.byref(x67), ctypes.byref(c27), 67, 256, None, None, 0, None)
+    assert rc != 0 and b"workspace" in lib.vfi_last_error()
+    # Python layer
+    r = ops.records_buffer(2, 4, 8, "cpu", zero=True)
+    assert tuple(r.shape) == (2, 72, 4, 8) and r.stride() == (72 * 32, 1, 72 * 8, 72) and r.dtype == torch.bfloat16
+    assert not ops._is_records(r)                                                  # records live on the GPU
+    with pytest.raises(ValueError, match="record tensor"):
+        ops.deform_conv2d_block(r, torch.zeros(2, 27, 4, 8, dtype=torch.bfloat16), torch.zeros(67, 67, 3, 3))
+
+
 def test_dropin_patches_and_restores_both_seams():
     import torchvision.ops
     import torchvision.ops.deform_conv as tv
