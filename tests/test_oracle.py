@@ -168,3 +168,64 @@ def test_column_gradient_split_matches_oracle(C, O, H, W, sigma):
     ref = oracle.dcn_bwd(go.numpy(), x.numpy(), off.numpy(), m.numpy(), w.numpy())
     for got, r, name in ((gx, ref[0], "grad_x"), (goff, ref[1], "grad_offset"), (gmask, ref[2], "grad_mask")):
         assert np.max(np.abs(got - r)) <= 2e-5 * max(1.0, float(np.max(np.abs(r)))), name
+
+
+def test_fused_block_gradient_formula_matches_autograd_through_the_reference_glue():
+    """The backward of the fused block (vfi_dcn_bwd_data_cols_fused; checked on the GPU against exactly this composition in
+    smoke() and tests/test_gpu_parity.py): d loss / d conv27 = [grad_offset[:, :9] | grad_mask * m * (1 - m) | grad_offset[:, 9:]]
+    with (grad_offset, grad_mask) from the oracle's DCN backward and m = sigmoid(conv27[:, 9:18]).  Pinned here against autograd
+    through the reference's glue (chunk / cat / sigmoid, ema_vfi.py:57-59) around the stock torchvision op on CPU -- and through
+    the unmodified ModulatedDeformConvPack itself where the reference tree is present."""
+    torch = pytest.importorskip("torch")
+    tv = pytest.importorskip("torchvision")
+
+    g = torch.Generator().manual_seed(21)
+    B, C, H, W = 1, 67, 9, 11
+    x = torch.randn(B, C, H, W, generator=g)
+    c27 = torch.randn(B, 27, H, W, generator=g)
+    c27[:, :9] *= 1.5
+    c27[:, 18:] *= 1.5
+    w = (torch.rand(C, C, 3, 3, generator=g) * 2 - 1) / 603 ** 0.5
+    b = (torch.rand(C, generator=g) * 2 - 1) / 603 ** 0.5
+    gy = torch.randn(B, C, H, W, generator=g)
+
+    ct = c27.clone().requires_grad_(True)
+    xt = x.clone().requires_grad_(True)
+    o1, m, o2 = torch.chunk(ct, 3, dim=1)
+    y = tv.ops.deform_conv2d(xt, torch.cat((o1, o2), dim=1), w, b, stride=1, padding=1, dilation=1, mask=torch.sigmoid(m))
+    y.backward(gy)
+
+    off, msk = oracle.pack_split(c27.numpy())
+    gx, goff, gmask, _, _ = oracle.dcn_bwd(gy.numpy(), x.numpy(), off, msk, w.numpy())
+    g27 = np.concatenate([goff[:, :9], gmask * msk * (1.0 - msk), goff[:, 9:]], axis=1)
+    assert maxabs(g27, ct.grad.numpy()) <= tol(ct.grad.numpy())
+    assert maxabs(gx, xt.grad.numpy()) <= tol(xt.grad.numpy())
+
+    if os.path.isdir("/root/reference/src"):
+        sys.dont_write_bytecode = True
+        sys.path.insert(0, "/root/reference")
+        try:
+            from src.models.ema_vfi import ModulatedDeformConvPack
+        finally:
+            sys.path.remove("/root/reference")
+        blk = ModulatedDeformConvPack(C, C)                      # ema_vfi.py:24: 3x3, stride 1, padding 1
+        with torch.no_grad():
+            blk.offset_conv.weight.normal_(0, 0.02, generator=g)
+            blk.offset_conv.bias.normal_(0, 0.5, generator=g)
+        xr = x.clone().requires_grad_(True)
+        seen = {}
+
+        def keep(mod, inp, out):                                 # returns None: the output is not replaced
+            out.retain_grad()
+            seen["c27"] = out
+
+        h = blk.offset_conv.register_forward_hook(keep)
+        try:
+            blk(xr).backward(gy)
+        finally:
+            h.remove()
+        cr = seen["c27"]
+        off, msk = oracle.pack_split(cr.detach().numpy())
+        _, goff, gmask, _, _ = oracle.dcn_bwd(gy.numpy(), x.numpy(), off, msk, blk.dcn_v2.weight.detach().numpy())
+        g27 = np.concatenate([goff[:, :9], gmask * msk * (1.0 - msk), goff[:, 9:]], axis=1)
+        assert maxabs(g27, cr.grad.numpy()) <= tol(cr.grad.numpy())
