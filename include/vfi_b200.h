@@ -121,9 +121,11 @@ size_t vfi_dcn_workspace_bytes(int64_t B, int64_t C, int64_t O, int64_t H, int64
  *    line per bilinear corner) and tail [B,H,W,8] (16 B per pixel: channels 64..71, zero beyond C; when there are at most four tail channels -- the
  *    reference's C = 67 -- bytes 8..15 of every record must MIRROR bytes 0..7, which every kernel of this library that
  *    writes planes does: the gather may then read either half and spreads its 8-byte reads over all shared-memory banks).
- *  - Weight image: 11 K blocks x [80 rows (o, zero padded)] x 128 B; K block t < 9 holds the 64 main channels of tap t,
- *    block 9 the 8-channel tails of taps 0..7, block 10 the tail of tap 8 + zeros; each row's eight 16-byte chunks are
- *    already permuted for the SWIZZLE_128B canonical layout (chunk j of row r stored at j ^ (r & 7)).
+ *  - Weight image (the v6 / v7 kernels' K order, vfi_dcn_k_order): 11 K blocks x [80 rows (o, zero padded)] x 128 B; K block
+ *    t < 9 holds the 64 main channels of tap t in the order the producers' tcgen05.st.16x256b mapping implies, block 9 four
+ *    tail channels of each of the nine taps (K elements 0..35) and the two bias slots 36 / 37 (the kernels add the bias on the
+ *    tensor core; vfi_dcn_pack_weight itself writes no bias), block 10 is zero; each row's eight 16-byte chunks are already
+ *    permuted for the SWIZZLE_128B canonical layout (chunk j of row r stored at j ^ (r & 7)).
  *    vfi_dcn_packed_weight_bytes() = 112,640 bytes, 16-byte aligned. */
 size_t vfi_dcn_packed_weight_bytes(void);
 int vfi_dcn_pack_weight(const void* weight, int32_t weight_dtype, int64_t O, int64_t C, void* packed,
@@ -180,7 +182,7 @@ int vfi_dcn_bwd_weight_tc(const vfi_tensor* grad_out, const vfi_tensor* x, const
 
 /* grad_x / grad_offset / grad_mask, column-gradient form.  torchvision::_deform_conv2d_backward (reference call site
  * src/models/ema_vfi.py:60 via autograd) splits into a dense product and a position-dependent part:
- *   gcol[p, k*72 + c] = sum_o grad_out[p, o] * weight[o, c, k]      (plain GEMM [P,72] x [72,648]: the caller's BLAS; rows of
+ *   gcol[p, k*72 + c] = sum_o grad_out[p, o] * weight[o, c, k]      (plain GEMM [P,72] x [72,648]: vfi_dcn_gcol below for bf16 columns, the caller's BLAS for true-fp32 ones; rows of
  *                                                                   gcol_ld >= 648 elements, gcol_ld % 4 == 0, columns
  *                                                                   c >= C of every tap zero; gcol_dtype VFI_BF16 or VFI_F32)
  * and this call, which gathers the four corner rows of x per (pixel, tap), reduces <gcol, corner> to grad_mask [B,9,H,W] and
