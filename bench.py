@@ -193,7 +193,8 @@ def run_reference_arm(args, desc, H, W):
     cores = os.cpu_count() or 1
     sample = (f"{rows}x{W} stripe of one {W}x{H} frame (batch 1, fp32, {rows * W} px = {frames_per_step:.5f} frame) per step; "
               "stock torch grid_sample + torchvision deform_conv2d CPU kernels (the reference's own third-party ops) "
-              "driven by oracle/torch_ref.py; frames/s scaled linearly in pixels")
+              "driven by oracle/torch_ref.py; frames/s scaled linearly in pixels "
+              "(checked against one full 1080p frame on this pool: 50.1 s, the extrapolation is 4 % conservative -- profiles/r02_s_cpu_full_frame.json)")
     line = {"impl": "reference", "metric": "1080p warp+DeformConv path frames/sec", "value": value, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -611,7 +612,7 @@ def main():
         fps = (rows * W / float(H * W)) / min(ts)
         line["cpu_baseline"] = {
             "value": fps, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": f"{rows}x{W} stripe (batch 1, fp32) of the same path, min of 3 after 1 warm-up, scaled linearly in pixels; "
+            "sample": f"{rows}x{W} stripe (batch 1, fp32) of the same path, min of 3 after 1 warm-up, scaled linearly in pixels (checked against one full 1080p frame on this pool: 50.1 s, the extrapolation is 4 % conservative -- profiles/r02_s_cpu_full_frame.json); "
                       "stock torch grid_sample + torchvision deform_conv2d CPU kernels via oracle/torch_ref.py"}
     print(json.dumps(line), flush=True)
     if world > 1:
