@@ -10,7 +10,8 @@ lib = sys.argv[1] if len(sys.argv) > 1 else "video-frame-interpolation_b200/libv
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 pats = {"UTCHMMA": r"\bUTCHMMA", "UTCBAR": r"\bUTCBAR", "STTM": r"\bSTTM", "LDTM": r"\bLDTM", "UBLKCP": r"\bUBLKCP",
         "LDGSTS": r"\bLDGSTS", "SYNCS": r"\bSYNCS", "REDG.F32x4": r"\bREDG\.E\.ADD\.F32x4", "HFMA2.BF16": r"HFMA2\.BF16",
-        "LDS.128": r"\bLDS\.128", "FENCE.VIEW.ASYNC": r"FENCE\.VIEW\.ASYNC"}
+        "LDS.128": r"\bLDS\.128", "FENCE.VIEW.ASYNC": r"FENCE\.VIEW\.ASYNC", "UTMALDG": r"\bUTMALDG", "UTMASTG": r"\bUTMASTG",
+        "CREDUX": r"\bCREDUX", "LDS.U16": r"\bLDS\.U16"}
 cur, counts = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -26,6 +27,6 @@ for line in out.splitlines():
                 counts[cur][k] += 1
 print(f"# {lib}: static SASS instruction counts per kernel (sm_100a)")
 for name, c in counts.items():
-    if any(c[k] for k in ("UTCHMMA", "STTM", "LDTM", "UBLKCP", "LDGSTS", "REDG.F32x4")):
+    if any(c[k] for k in ("UTCHMMA", "STTM", "LDTM", "UBLKCP", "LDGSTS", "REDG.F32x4", "UTMALDG", "UTMASTG")):
         print(name)
         print("    " + "  ".join(f"{k}={v}" for k, v in c.items() if v))
