@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--impl", default="vfi_b200", choices=["vfi_b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "bf16_tc"])
-    ap.add_argument("--dcn-kernel", default="", choices=["", "v4", "v6"], help="A/B switch for the tcgen05 DCN kernel variant")
+    ap.add_argument("--dcn-kernel", default="", choices=["", "v6"], help="A/B switch: v6 = the round-1 tcgen05 DCN kernel (default: v7)")
     ap.add_argument("--conv27-layout", default="nchw", choices=["nchw", "channels_last"],
                     help="memory format of the three offset_conv outputs the DCN layers read")
     ap.add_argument("--no-cpu-baseline", action="store_true")
