@@ -54,6 +54,29 @@ def test_no_cpu_fallback():
                                torch.zeros(67), stride=1, padding=1, dilation=1, mask=torch.zeros(1, 9, 4, 4))
 
 
+def test_the_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke()/build() and bench.py's CPU reference legs may touch it.
+    Static check over the package sources (imports, importlib calls, ctypes loads of the oracle library) plus a dynamic one:
+    importing every product module leaves no `oracle` module behind."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|import_module\(\s*[\"']oracle|libvfi_oracle|oracle/_build|oracle/_ref", re.M)
+    for f in sorted((root / "video-frame-interpolation_b200").rglob("*")):
+        if f.suffix in (".py", ".cu", ".cuh", ".h") and "_obj" not in f.parts:
+            assert not pat.search(f.read_text(errors="ignore")), f
+    hits = [ln for ln in (root / "bench.py").read_text().splitlines() if re.search(r"\bfrom oracle\b|\bimport oracle\b", ln)]
+    assert len(hits) == 1                                   # cpu_reference_step_factory: the cpu_baseline / --impl reference legs
+    code = ("import sys; sys.path.insert(0, %r); import vfi_b200; "
+            "from vfi_b200 import ops, dropin, hotpath, shard, stream, trainstep, refmodel, run, _lib, _build; "
+            "assert not [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')], 'oracle imported by the product'" % str(root))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+
+
 def test_geometry_outside_the_path_is_refused():
     x, w = torch.zeros(1, 67, 4, 4), torch.zeros(67, 67, 3, 3)
     off, m = torch.zeros(1, 18, 4, 4), torch.zeros(1, 9, 4, 4)
